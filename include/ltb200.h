@@ -1,0 +1,111 @@
+/*
+ * libltb200 — C ABI of the B200-native lip-sync engine (sm_100a only, no CPU fallback).
+ *
+ * This is the drop-in boundary behind LiveTalking's avatar plugin surface.  Every entry point names the
+ * reference interface it replaces (paths relative to the lipku/LiveTalking tree).  Conventions:
+ *   - plain C types, host pointers unless a name ends in _dev; the library owns all device memory;
+ *   - every function returns 0 on success, non-zero on failure; ltb_last_error() returns the message
+ *     (thread-local).  Nothing aborts the process; the Python shim raises RuntimeError.
+ *   - handles are opaque pointers; a session is bound to one CUDA device and one stream and may be driven
+ *     by one thread at a time (different sessions may be driven concurrently; ctypes releases the GIL).
+ */
+#ifndef LTB200_H_
+#define LTB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ltb_w2l_model ltb_w2l_model;
+typedef struct ltb_w2l_avatar ltb_w2l_avatar;
+typedef struct ltb_w2l_session ltb_w2l_session;
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+int ltb_version(void);
+const char* ltb_last_error(void);
+/* replaces utils/device.py:4-9 (reference always picks "cuda" = device 0) */
+int ltb_device_count(int* count);
+int ltb_set_device(int device);
+
+/* ---- wav2lip256 model ------------------------------------------------------------------------------- */
+/* replaces load_model(path), avatars/wav2lip_avatar.py:59-70.  `blob` is the packed weight image produced by
+ * livetalking_b200.w2l_pack.pack_state_dict() from the reference checkpoint's state_dict (BN folded, fp16,
+ * K-major rows).  The blob is copied to the current device. */
+int ltb_w2l_model_create(const void* blob, size_t nbytes, ltb_w2l_model** out);
+/* same, but adopts a blob that already lives in device memory (e.g. received by ncclBroadcast at init — the one
+ * collective of the multi-GPU design).  No copy is made: the caller keeps ownership and must keep it alive. */
+int ltb_w2l_model_create_from_device(void* blob_dev, size_t nbytes, ltb_w2l_model** out);
+int ltb_w2l_model_destroy(ltb_w2l_model* m);
+
+/* ---- avatar assets ---------------------------------------------------------------------------------- */
+/* replaces load_avatar(avatar_id), avatars/wav2lip_avatar.py:72-88: face crops (n,256,256,3) u8 BGR, full frames
+ * (n,H,W,3) u8 BGR and coords (n,4) int32 = (y1,y2,x1,x2) are uploaded once and stay resident in HBM. */
+int ltb_w2l_avatar_create(const uint8_t* faces, const uint8_t* frames, const int32_t* coords, int n, int H, int W,
+                          ltb_w2l_avatar** out);
+int ltb_w2l_avatar_destroy(ltb_w2l_avatar* a);
+
+/* ---- session (one avatar stream) -------------------------------------------------------------------- */
+#define LTB_SESSION_KEEP_LAYERS 1 /* keep every layer's activations (debug / per-layer parity tests) */
+#define LTB_SESSION_NO_GRAPH 2    /* launch kernels eagerly instead of replaying a CUDA graph */
+/* replaces LipReal.__init__ (avatars/wav2lip_avatar.py:101-114) + warm_up (:90-96): allocates the activation
+ * arena for `batch` frames, builds the layer plan and (unless NO_GRAPH) captures it into a CUDA graph.
+ * stride_left/right = opt.l / opt.r (20 ms chunks), fps = opt.fps. */
+int ltb_w2l_session_create(ltb_w2l_model* m, ltb_w2l_avatar* a, int batch, int stride_left, int stride_right, int fps,
+                           int flags, ltb_w2l_session** out);
+int ltb_w2l_session_destroy(ltb_w2l_session* s);
+
+/* replaces audio.melspectrogram + the window slicing of MelASR.run_step
+ * (avatars/audio_features/mel.py:46-63, avatars/wav2lip/audio.py:45-51).
+ * pcm: (stride_left+stride_right+2*batch)*320 float32 samples.  The B windows stay on the device as the next
+ * infer's audio input; if out_mel != NULL they are also copied back as float32 [batch,80,16]. */
+int ltb_w2l_mel_step(ltb_w2l_session* s, const float* pcm, int nsamples, float* out_mel);
+
+/* replaces LipReal.inference_batch(index, audiofeat_batch), avatars/wav2lip_avatar.py:116-139.
+ * mel: float32 [batch,80,16] host windows (NULL = use the windows left on the device by ltb_w2l_mel_step).
+ * pred_out: float32 [batch,256,256,3] BGR in [0,255] (the reference's return value) or NULL to leave the
+ * predictions on the device for ltb_w2l_paste*.  Synchronous. */
+int ltb_w2l_infer(ltb_w2l_session* s, int index, const float* mel, float* pred_out);
+
+/* replaces LipReal.paste_back_frame(pred_frame, idx), avatars/wav2lip_avatar.py:141-147, for the prediction in
+ * `slot` (0..batch-1) of the last infer.  out_frame: uint8 [H,W,3] host buffer.  Synchronous. */
+int ltb_w2l_paste(ltb_w2l_session* s, int slot, int idx, uint8_t* out_frame);
+/* all `batch` frames of the last infer at once (frame i uses mirror_index(n, index+i), utils/image.py:26-32).
+ * out_frames: uint8 [batch,H,W,3] host buffer (pinned recommended) or NULL to keep them on the device. */
+int ltb_w2l_paste_batch(ltb_w2l_session* s, int index, uint8_t* out_frames);
+
+/* whole step with everything resident: forward (audio windows already on the device) + batched paste-back,
+ * enqueued on the session stream WITHOUT synchronising — used for device-timed throughput. */
+int ltb_w2l_step_async(ltb_w2l_session* s, int index);
+int ltb_w2l_sync(ltb_w2l_session* s);
+/* the session's cudaStream_t (so a caller can record CUDA events on it) */
+int ltb_w2l_stream(ltb_w2l_session* s, void** cuda_stream);
+/* number of kernels the engine has launched on this session so far (graph replays count their nodes) */
+int ltb_w2l_launch_count(ltb_w2l_session* s, long long* n);
+/* pinned host memory helpers for the e2e path */
+int ltb_host_alloc(size_t nbytes, void** out);
+int ltb_host_free(void* p);
+
+/* ---- debug / test hooks ----------------------------------------------------------------------------- */
+/* number of conv blocks (54) ; copy layer `layer`'s post-activation output as dense fp16 NHWC [batch,H,W,C]
+ * (requires LTB_SESSION_KEEP_LAYERS).  layer = 54 returns the head input (same as 53). */
+int ltb_w2l_num_layers(void);
+int ltb_w2l_layer_shape(ltb_w2l_session* s, int layer, int* H, int* W, int* C);
+int ltb_w2l_layer_read(ltb_w2l_session* s, int layer, void* out_f16, size_t nbytes);
+
+/* stand-alone conv on the tensor-core kernel (unit parity tests): NHWC fp16 host tensors.
+ * transposed != 0: ConvTranspose2d(k=3,s=2,p=1,op=1) via 4 sub-pixel phases; weights are passed in the PyTorch
+ * layouts ([Cout,Cin,KH,KW] for conv, [Cin,Cout,3,3] for transposed) as float32 and packed internally.
+ * force_path: 0 = auto, 1 = gather kernel, 2 = TMA kernel. */
+typedef struct ltb_conv_desc {
+  int N, IH, IW, Cin, Cout, KH, KW, sy, sx, pad, transposed, relu, has_res, force_path;
+} ltb_conv_desc;
+int ltb_conv2d_f16(const ltb_conv_desc* d, const void* in_f16, const float* w_f32, const float* bias_f32,
+                   const void* res_f16, void* out_f16);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTB200_H_ */

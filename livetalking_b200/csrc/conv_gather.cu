@@ -1,0 +1,292 @@
+// Generic implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+//   A (im2col rows, 128 output pixels x KB channels of one tap) : gathered with cp.async (zero-fill = padding)
+//                                                                 into the canonical K-major swizzled smem layout
+//   B (weights, BN x KB)                                         : cp.async, same layout
+//   D (128 x BN fp32)                                            : TMEM accumulator, tcgen05.mma kind::f16
+//   epilogue                                                     : tcgen05.ld -> +bias (+residual) -> ReLU -> fp16 NHWC,
+//                                                                  written straight into a channel slice of the
+//                                                                  destination (concat-free U-Net skips)
+//
+// This kernel handles EVERY conv geometry of the hot path (any stride / padding / kernel size, ConvTranspose
+// sub-pixel phases, channel-sliced inputs/outputs).  conv_tma.cu is the TMA-fed fast path for the FLOP-heavy
+// stride-1 layers.  Reference op being replaced: avatars/wav2lip/models/conv.py:5-19,33-44 (cuDNN conv + BN + add + ReLU).
+#include "conv_params.h"
+#include "ltb_internal.h"
+#include "ptx_sm100.cuh"
+
+namespace ltb {
+
+template <int BN, int KB>
+struct GatherCfg {
+  static constexpr int CH = KB / 8;      // 16-byte chunks per smem row
+  static constexpr int ROWB = KB * 2;    // bytes per smem row (= swizzle span)
+  static constexpr int RSTEP = 128 / CH; // row step between the rows one producer thread fills
+  static constexpr int A_BYTES = 128 * ROWB;
+  static constexpr int B_BYTES = (BN * ROWB < 1024) ? 1024 : BN * ROWB;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (STAGE_BYTES >= 32768) ? 3 : 4;
+  static constexpr int LAG = STAGES - 1;
+  static constexpr uint32_t LAYOUT = (KB == 64) ? 2u : (KB == 32) ? 4u : 6u;
+  static constexpr uint32_t SBO = 8 * ROWB;
+  static constexpr int TCOLS = (BN < 32) ? 32 : BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+};
+
+template <int KB>
+__device__ __forceinline__ uint32_t swz_chunk(int row, int j) {
+  if (KB == 64) return (uint32_t)(j ^ (row & 7));
+  if (KB == 32) return (uint32_t)(j ^ ((row >> 1) & 3));
+  return (uint32_t)(j ^ ((row >> 2) & 1));
+}
+
+template <int BN, int KB>
+__global__ void __launch_bounds__(160) conv_gather_umma_kernel(const __grid_constant__ ConvParams p) {
+  using C = GatherCfg<BN, KB>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[C::STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[C::STAGES];
+  __shared__ __align__(8) uint64_t bar_accum;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  const ConvPhase& ph = p.ph[blockIdx.z];
+  const int m0 = blockIdx.x * 128;
+  const int n0 = blockIdx.y * BN;
+  const int cpt = p.Cin / KB;  // K chunks per tap
+  const int kiters = ph.ntaps * cpt;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 128);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bar_accum), 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(smem_u32(&tmem_base_slot), C::TCOLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers
+    const int j = tid % C::CH;
+    const int r0 = tid / C::CH;
+    int rb[C::CH], riy[C::CH], rix[C::CH];
+    const int gsz = p.GH * p.GW;
+#pragma unroll
+    for (int i = 0; i < C::CH; ++i) {
+      const int m = m0 + r0 + i * C::RSTEP;
+      if (m < p.M) {
+        const int b = m / gsz;
+        const int rem = m - b * gsz;
+        const int gy = rem / p.GW;
+        const int gx = rem - gy * p.GW;
+        rb[i] = b;
+        riy[i] = gy * p.sy;
+        rix[i] = gx * p.sx;
+      } else {
+        rb[i] = 0;
+        riy[i] = -(1 << 20);  // forces the bounds test to fail -> zero rows
+        rix[i] = 0;
+      }
+    }
+    int tap = 0, cc = 0;
+    for (int it = 0; it < kiters; ++it) {
+      const int stage = it % C::STAGES;
+      mbar_wait(smem_u32(&bar_empty[stage]), (((uint32_t)it / C::STAGES) & 1u) ^ 1u);
+      const uint32_t a_base = tiles + stage * C::STAGE_BYTES;
+      const uint32_t b_base = a_base + C::A_BYTES;
+      const int dy = ph.dy[tap], dx = ph.dx[tap];
+#pragma unroll
+      for (int i = 0; i < C::CH; ++i) {
+        const int row = r0 + i * C::RSTEP;
+        const int iy = riy[i] + dy, ix = rix[i] + dx;
+        const bool inb = ((unsigned)iy < (unsigned)p.IH) && ((unsigned)ix < (unsigned)p.IW);
+        const size_t off = ((size_t)(rb[i] * p.IH + iy) * p.IW + ix) * p.ICtot + p.ic_off + cc * KB + j * 8;
+        const __half* src = inb ? (p.in + off) : p.in;
+        cp_async16(a_base + row * C::ROWB + swz_chunk<KB>(row, j) * 16, src, inb ? 16u : 0u);
+      }
+      const size_t wk = (size_t)ph.koff + (size_t)tap * p.Cin + cc * KB + j * 8;
+#pragma unroll
+      for (int i = 0; i < C::CH; ++i) {
+        const int n = r0 + i * C::RSTEP;
+        if (n < BN) {
+          cp_async16(b_base + n * C::ROWB + swz_chunk<KB>(n, j) * 16, p.w + (size_t)(n0 + n) * p.Ktot + wk, 16u);
+        }
+      }
+      cp_async_commit();
+      if (it >= C::LAG) {
+        cp_async_wait<C::LAG>();
+        fence_proxy_async_smem();
+        mbar_arrive(smem_u32(&bar_full[(it - C::LAG) % C::STAGES]));
+      }
+      if (++cc == cpt) {
+        cc = 0;
+        ++tap;
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    for (int it = (kiters > C::LAG ? kiters - C::LAG : 0); it < kiters; ++it) mbar_arrive(smem_u32(&bar_full[it % C::STAGES]));
+
+    // ------------------------------------------------------------------ epilogue (same 4 warps)
+    mbar_wait(smem_u32(&bar_accum), 0);
+    tc_fence_after();
+    const int m = m0 + tid;
+    const bool valid = m < p.M;
+    size_t opix = 0;
+    if (valid) {
+      const int b = m / gsz;
+      const int rem = m - b * gsz;
+      const int gy = rem / p.GW;
+      const int gx = rem - gy * p.GW;
+      opix = (size_t)(b * p.OH + gy * p.osy + ph.ooy) * p.OW + gx * p.osx + ph.oox;
+    }
+    __half* optr = p.out + opix * p.OCtot + p.oc_off + n0;
+    const __half* rptr = p.res ? (p.res + opix * p.RCtot + p.rc_off + n0) : nullptr;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    constexpr int CW = (BN >= 32) ? 32 : 16;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += CW) {
+      uint32_t v[CW];
+      if constexpr (CW == 32) {
+        tmem_ld32(trow + c0, v);
+      } else {
+        tmem_ld16(trow + c0, reinterpret_cast<uint32_t(&)[16]>(v));
+      }
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < CW; g += 8) {
+          float f[8];
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + g));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + g + 4));
+          f[0] = __uint_as_float(v[g + 0]) + b0.x;
+          f[1] = __uint_as_float(v[g + 1]) + b0.y;
+          f[2] = __uint_as_float(v[g + 2]) + b0.z;
+          f[3] = __uint_as_float(v[g + 3]) + b0.w;
+          f[4] = __uint_as_float(v[g + 4]) + b1.x;
+          f[5] = __uint_as_float(v[g + 5]) + b1.y;
+          f[6] = __uint_as_float(v[g + 6]) + b1.z;
+          f[7] = __uint_as_float(v[g + 7]) + b1.w;
+          if (rptr) {
+            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rptr + c0 + g));
+            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 rf = __half22float2(rh[q]);
+              f[2 * q] += rf.x;
+              f[2 * q + 1] += rf.y;
+            }
+          }
+          uint4 ov;
+          __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float x = f[2 * q], y = f[2 * q + 1];
+            if (p.relu) {
+              x = fmaxf(x, 0.f);
+              y = fmaxf(y, 0.f);
+            }
+            x = fminf(fmaxf(x, -65504.f), 65504.f);
+            y = fminf(fmaxf(y, -65504.f), 65504.f);
+            oh[q] = __floats2half2_rn(x, y);
+          }
+          *reinterpret_cast<uint4*>(optr + c0 + g) = ov;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issuer (warp 4, one lane)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(128, BN);
+      for (int it = 0; it < kiters; ++it) {
+        const int stage = it % C::STAGES;
+        mbar_wait(smem_u32(&bar_full[stage]), ((uint32_t)it / C::STAGES) & 1u);
+        tc_fence_after();
+        const uint32_t a_base = tiles + stage * C::STAGE_BYTES;
+        const uint32_t b_base = a_base + C::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < KB / 16; ++k) {
+          const uint64_t ad = umma_smem_desc(a_base + k * 32, C::SBO, C::LAYOUT);
+          const uint64_t bd = umma_smem_desc(b_base + k * 32, C::SBO, C::LAYOUT);
+          umma_f16(tmem, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bar_empty[stage]));
+      }
+      umma_commit(smem_u32(&bar_accum));
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, C::TCOLS);
+  }
+}
+
+template <int BN, int KB>
+static cudaError_t launch_one(const ConvParams& p, cudaStream_t st) {
+  using C = GatherCfg<BN, KB>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gather_umma_kernel<BN, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((p.M + 127) / 128, p.Cout / BN, p.nphases);
+  conv_gather_umma_kernel<BN, KB><<<grid, 160, C::SMEM_BYTES, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int KB>
+static cudaError_t launch_kb(const ConvParams& p, int bn, cudaStream_t st) {
+  switch (bn) {
+    case 128: return launch_one<128, KB>(p, st);
+    case 64: return launch_one<64, KB>(p, st);
+    case 32: return launch_one<32, KB>(p, st);
+    case 16: return launch_one<16, KB>(p, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+int conv_gather_pick_bn(const ConvParams& p) {
+  int bn = 0;
+  for (int c : {128, 64, 32, 16})
+    if (p.Cout % c == 0) {
+      bn = c;
+      break;
+    }
+  if (!bn) return 0;
+  // small-M layers are weight-bandwidth bound: prefer more, narrower CTAs until the grid fills the 148 SMs
+  const long mt = (p.M + 127) / 128;
+  while (bn > 32 && mt * (p.Cout / bn) * p.nphases < 148) bn >>= 1;
+  return bn;
+}
+
+cudaError_t launch_conv_gather(const ConvParams& p, cudaStream_t st) {
+  if (p.Cout % 16 != 0 || p.Cin % 16 != 0 || (p.ICtot % 8) || (p.OCtot % 8) || (p.ic_off % 8) || (p.oc_off % 8) ||
+      (p.Ktot % 8) || p.nphases < 1 || p.nphases > kMaxPhases)
+    return cudaErrorInvalidValue;
+  if (p.res && ((p.RCtot % 8) || (p.rc_off % 8))) return cudaErrorInvalidValue;
+  const int bn = conv_gather_pick_bn(p);
+  if (!bn) return cudaErrorInvalidValue;
+  if (p.Cin % 64 == 0) return launch_kb<64>(p, bn, st);
+  if (p.Cin % 32 == 0) return launch_kb<32>(p, bn, st);
+  return launch_kb<16>(p, bn, st);
+}
+
+}  // namespace ltb

@@ -1,0 +1,46 @@
+// Internal declarations shared by the engine translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "conv_params.h"
+
+namespace ltb {
+
+// ---- error plumbing (C ABI returns int status; message via ltb_last_error) ----
+void set_error(const std::string& msg);
+int fail(const char* file, int line, const std::string& msg);
+#define LTB_FAIL(msg) ::ltb::fail(__FILE__, __LINE__, (msg))
+#define LTB_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) return LTB_FAIL(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+// ---- kernel launchers ----
+cudaError_t launch_conv_gather(const ConvParams& p, cudaStream_t st);
+int conv_gather_pick_bn(const ConvParams& p);
+
+// wav2lip-specific small kernels (w2l_small.cu)
+// faces u8 [nf,256,256,3] BGR -> padded fp16 [B,262,264,8]: ch0-2 = face/255 with rows >= 128 zeroed, ch3-5 = face/255
+cudaError_t launch_w2l_prep_faces(const uint8_t* faces, int nfaces, int index, int B, __half* img_pad, cudaStream_t st);
+// mel f32 [B,80,16] -> fp16 NHWC [B,80,16,32]: conv3x3 p1 (1->32) + folded BN + ReLU
+cudaError_t launch_w2l_audio_conv0(const float* mel, const float* w9x32, const float* bias, __half* out, int B, cudaStream_t st);
+// x fp16 [npix,32] -> pred f32 [npix,3] = sigmoid(W x + b) * 255 ; optional u8 copy (truncation)
+cudaError_t launch_w2l_head(const __half* x, const float* w3x32, const float* b3, float* pred, int npix, cudaStream_t st);
+
+// mel.cu : PCM f32 [nsamp] -> mel windows f32 [B,80,16] (float64 arithmetic, see mel.cu)
+cudaError_t launch_mel_step(const float* pcm, int nsamp, int B, int stride_left_chunks, int fps, double* scratch_spec,
+                            double* scratch_mel, float* out, cudaStream_t st);
+size_t mel_scratch_spec_doubles(int nsamp);
+size_t mel_scratch_mel_doubles(int nsamp);
+
+// paste.cu : wav2lip paste-back for `count` frames in one launch.
+//   frame index of job i = explicit_idx (>= 0, count must be 1) or mirror_index(nf, index + i); prediction slot = slot0 + i
+cudaError_t launch_w2l_paste(const uint8_t* frames, const int* coords, int nf, int H, int W, const float* pred, int slot0,
+                             int index, int explicit_idx, int count, uint8_t* out, cudaStream_t st);
+
+}  // namespace ltb

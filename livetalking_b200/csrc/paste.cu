@@ -1,0 +1,129 @@
+// wav2lip paste-back composite (replaces the CPU OpenCV path of LipReal.paste_back_frame,
+// avatars/wav2lip_avatar.py:141-147):
+//     combine = frame.copy(); res = cv2.resize(pred.astype(np.uint8), (x2-x1, y2-y1)); combine[y1:y2, x1:x2] = res
+// Integer/byte work, bit-exact with OpenCV's 8-bit INTER_LINEAR: 11-bit fixed-point taps computed with the same
+// float32/float64 expression order, int32 horizontal pass, ((b0*(S0>>4))>>16 + (b1*(S1>>4))>>16 + 2)>>2 vertical
+// pass, and the INTER_AREA 2x2 box average OpenCV silently substitutes for an exact 2x decimation.
+// HBM-bound: 2*H*W*3 bytes per frame; one thread = 4 output pixels (12 contiguous bytes).
+#include "ltb_internal.h"
+
+namespace ltb {
+
+__device__ __forceinline__ int mirror_index_p(int size, int index) {
+  const int turn = index / size, res = index % size;
+  return (turn % 2 == 0) ? res : size - res - 1;
+}
+
+// OpenCV linear-resize tap for destination index d: source index s (clamped) and fixed-point weights
+__device__ __forceinline__ void cv_tap(int d, double scale, int src_len, bool clamp_taps, int& s, int& w0, int& w1) {
+  float f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+  int si = (int)floorf(f);
+  f = __fsub_rn(f, (float)si);
+  if (clamp_taps) {  // horizontal: resize.cpp clamps the tap position and zeroes the fraction
+    if (si < 0) {
+      si = 0;
+      f = 0.f;
+    }
+    if (si >= src_len - 1) {
+      si = src_len - 1;
+      f = 0.f;
+    }
+  }
+  s = si;
+  w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  w1 = __float2int_rn(__fmul_rn(f, 2048.f));
+}
+
+__device__ __forceinline__ int trunc_u8(float v) { return (int)(unsigned char)v; }  // ndarray.astype(np.uint8)
+
+struct PasteArgs {
+  const uint8_t* frames;  // [nf,H,W,3]
+  const int* coords;      // [nf,4] = (y1,y2,x1,x2)
+  const float* pred;      // [B,256,256,3]
+  uint8_t* out;           // [count,H,W,3]
+  int nf, H, W;
+  int index;         // first avatar index (mirror_index applied) when explicit_idx < 0
+  int explicit_idx;  // >= 0: use this frame index for the (single) job
+  int slot0;         // first prediction slot
+};
+
+__global__ void __launch_bounds__(256) w2l_paste_kernel(const PasteArgs a) {
+  const int job = blockIdx.z;
+  const int y = blockIdx.y;
+  const int xg = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (xg >= a.W) return;
+  const int idx = a.explicit_idx >= 0 ? a.explicit_idx : mirror_index_p(a.nf, a.index + job);
+  const int y1 = a.coords[idx * 4 + 0], y2 = a.coords[idx * 4 + 1], x1 = a.coords[idx * 4 + 2], x2 = a.coords[idx * 4 + 3];
+  const uint8_t* frow = a.frames + ((size_t)idx * a.H + y) * a.W * 3;
+  uint8_t* orow = a.out + ((size_t)job * a.H + y) * a.W * 3;
+  const float* pred = a.pred + (size_t)(a.slot0 + job) * 256 * 256 * 3;
+  const int dw = x2 - x1, dh = y2 - y1;
+  const int npx = min(4, a.W - xg);
+  uint8_t px[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) px[i] = (i < npx * 3) ? frow[xg * 3 + i] : 0;
+  if (y >= y1 && y < y2 && xg + npx > x1 && xg < x2) {
+    const int dy = y - y1;
+    const bool same = (dw == 256 && dh == 256);
+    const bool area = (dw == 128 && dh == 128);
+    int sy = 0, b0 = 2048, b1 = 0;
+    if (!same && !area) cv_tap(dy, 1.0 / ((double)dh / 256.0), 256, false, sy, b0, b1);
+    const int sy0 = min(max(sy, 0), 255), sy1 = min(max(sy + 1, 0), 255);
+    for (int i = 0; i < npx; ++i) {
+      const int x = xg + i;
+      if (x < x1 || x >= x2) continue;
+      const int dx = x - x1;
+      if (same) {
+        const float* p = pred + ((size_t)dy * 256 + dx) * 3;
+        for (int c = 0; c < 3; ++c) px[i * 3 + c] = (uint8_t)trunc_u8(p[c]);
+      } else if (area) {
+        const float* p = pred + ((size_t)(2 * dy) * 256 + 2 * dx) * 3;
+        for (int c = 0; c < 3; ++c) {
+          const int s = trunc_u8(p[c]) + trunc_u8(p[3 + c]) + trunc_u8(p[768 + c]) + trunc_u8(p[771 + c]);
+          px[i * 3 + c] = (uint8_t)((s + 2) >> 2);
+        }
+      } else {
+        int sx, a0, a1;
+        cv_tap(dx, 1.0 / ((double)dw / 256.0), 256, true, sx, a0, a1);
+        const int sx1 = min(sx + 1, 255);
+        const float* r0 = pred + (size_t)sy0 * 768;
+        const float* r1 = pred + (size_t)sy1 * 768;
+        for (int c = 0; c < 3; ++c) {
+          const int S0 = trunc_u8(r0[sx * 3 + c]) * a0 + trunc_u8(r0[sx1 * 3 + c]) * a1;
+          const int S1 = trunc_u8(r1[sx * 3 + c]) * a0 + trunc_u8(r1[sx1 * 3 + c]) * a1;
+          const int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+          px[i * 3 + c] = (uint8_t)min(max(v, 0), 255);
+        }
+      }
+    }
+  }
+  if (npx == 4 && ((a.W * 3) % 4 == 0)) {
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(orow + xg * 3);
+    const uint32_t* p32 = reinterpret_cast<const uint32_t*>(px);
+    o32[0] = p32[0];
+    o32[1] = p32[1];
+    o32[2] = p32[2];
+  } else {
+    for (int i = 0; i < npx * 3; ++i) orow[xg * 3 + i] = px[i];
+  }
+}
+
+cudaError_t launch_w2l_paste(const uint8_t* frames, const int* coords, int nf, int H, int W, const float* pred, int slot0,
+                             int index, int explicit_idx, int count, uint8_t* out, cudaStream_t st) {
+  PasteArgs a;
+  a.frames = frames;
+  a.coords = coords;
+  a.pred = pred;
+  a.out = out;
+  a.nf = nf;
+  a.H = H;
+  a.W = W;
+  a.index = index;
+  a.explicit_idx = explicit_idx;
+  a.slot0 = slot0;
+  dim3 grid((W + 1023) / 1024, H, count);
+  w2l_paste_kernel<<<grid, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace ltb

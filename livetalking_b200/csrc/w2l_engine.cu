@@ -1,0 +1,907 @@
+// wav2lip256 engine: weight blob -> layer plan -> CUDA-graph replay, behind the C ABI of include/ltb200.h.
+//
+// Data layout in HBM (per session, batch B):
+//   faces/frames/coords : resident u8 / int32 avatar assets (uploaded once)
+//   img_pad   [B,262,264,8]   fp16   zero-bordered 8-channel image (3 masked + 3 full + 2 zero) for the 7x7 stem
+//   cat0..7   [B,h,w,Cdec+Cskip] fp16 NHWC  : U-Net skip concat buffers; the decoder block writes channels [0,Cdec),
+//                                             the matching encoder block writes [Cdec, Cdec+Cskip)  (torch.cat is gone)
+//   tmp ring  fp16 NHWC                      : intra-block activations
+//   pred      [B,256,256,3]   f32            : sigmoid*255, the reference's inference_batch return layout
+//   frames_out[B,H,W,3]       u8             : composited frames
+// Reference topology: avatars/wav2lip/models/wav2lip_v2.py:12-91, forward :123-163.
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ltb200.h"
+#include "ltb_internal.h"
+
+namespace ltb {
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(const char* file, int line, const std::string& msg) {
+  const char* base = std::strrchr(file, '/');
+  g_last_error = std::string(base ? base + 1 : file) + ":" + std::to_string(line) + ": " + msg;
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------ layer table
+struct LDef {
+  char kind;  // 'c' conv, 't' transposed conv
+  int cin, cout, k, sy, sx, pad;
+  bool res;
+};
+// execution order: audio encoder (0..12), face encoder (13..32), decoder (33..52), output_block.0 (53)
+static const LDef kLayers[54] = {
+    // audio_encoder, wav2lip_v2.py:41-58
+    {'c', 1, 32, 3, 1, 1, 1, false},   {'c', 32, 32, 3, 1, 1, 1, true},    {'c', 32, 32, 3, 1, 1, 1, true},
+    {'c', 32, 64, 3, 3, 1, 1, false},  {'c', 64, 64, 3, 1, 1, 1, true},    {'c', 64, 64, 3, 1, 1, 1, true},
+    {'c', 64, 128, 3, 3, 3, 1, false}, {'c', 128, 128, 3, 1, 1, 1, true},  {'c', 128, 128, 3, 1, 1, 1, true},
+    {'c', 128, 256, 3, 3, 2, 1, false}, {'c', 256, 256, 3, 1, 1, 1, true}, {'c', 256, 512, 3, 1, 1, 0, false},
+    {'c', 512, 512, 1, 1, 1, 0, false},
+    // face_encoder_blocks, wav2lip_v2.py:12-39
+    {'c', 6, 16, 7, 1, 1, 3, false},
+    {'c', 16, 32, 3, 2, 2, 1, false},  {'c', 32, 32, 3, 1, 1, 1, true},    {'c', 32, 32, 3, 1, 1, 1, true},
+    {'c', 32, 64, 3, 2, 2, 1, false},  {'c', 64, 64, 3, 1, 1, 1, true},    {'c', 64, 64, 3, 1, 1, 1, true},
+    {'c', 64, 64, 3, 1, 1, 1, true},
+    {'c', 64, 128, 3, 2, 2, 1, false}, {'c', 128, 128, 3, 1, 1, 1, true},  {'c', 128, 128, 3, 1, 1, 1, true},
+    {'c', 128, 256, 3, 2, 2, 1, false}, {'c', 256, 256, 3, 1, 1, 1, true}, {'c', 256, 256, 3, 1, 1, 1, true},
+    {'c', 256, 512, 3, 2, 2, 1, false}, {'c', 512, 512, 3, 1, 1, 1, true},
+    {'c', 512, 512, 3, 2, 2, 1, false}, {'c', 512, 512, 3, 1, 1, 1, true},
+    {'c', 512, 512, 4, 1, 1, 0, false}, {'c', 512, 512, 1, 1, 1, 0, false},
+    // face_decoder_blocks, wav2lip_v2.py:60-87
+    {'c', 512, 512, 1, 1, 1, 0, false},
+    {'t', 1024, 512, 4, 1, 1, 0, false}, {'c', 512, 512, 3, 1, 1, 1, true},
+    {'t', 1024, 512, 3, 2, 2, 1, false}, {'c', 512, 512, 3, 1, 1, 1, true},
+    {'t', 1024, 512, 3, 2, 2, 1, false}, {'c', 512, 512, 3, 1, 1, 1, true}, {'c', 512, 512, 3, 1, 1, 1, true},
+    {'t', 768, 384, 3, 2, 2, 1, false},  {'c', 384, 384, 3, 1, 1, 1, true}, {'c', 384, 384, 3, 1, 1, 1, true},
+    {'t', 512, 256, 3, 2, 2, 1, false},  {'c', 256, 256, 3, 1, 1, 1, true}, {'c', 256, 256, 3, 1, 1, 1, true},
+    {'t', 320, 128, 3, 2, 2, 1, false},  {'c', 128, 128, 3, 1, 1, 1, true}, {'c', 128, 128, 3, 1, 1, 1, true},
+    {'t', 160, 64, 3, 2, 2, 1, false},   {'c', 64, 64, 3, 1, 1, 1, true},   {'c', 64, 64, 3, 1, 1, 1, true},
+    // output_block.0, wav2lip_v2.py:89
+    {'c', 80, 32, 3, 1, 1, 1, false},
+};
+constexpr int kNumLayers = 54;
+constexpr int kStem = 13, kConvT4 = 34;
+
+// expected packed sizes (elements) of layer i's weight matrix [rows][K]
+static void packed_dims(int i, int* rows, int* K) {
+  const LDef& L = kLayers[i];
+  if (i == 0) {
+    *rows = 32;
+    *K = 9;
+  } else if (i == kStem) {
+    *rows = 16;
+    *K = 7 * 64;
+  } else if (i == kConvT4) {
+    *rows = 16 * 512;
+    *K = 1024;
+  } else {
+    *rows = L.cout;
+    *K = L.k * L.k * L.cin;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ geometry helpers
+static void phases_conv(ConvParams& p, int KH, int KW, int pad, int cin) {
+  p.nphases = 1;
+  ConvPhase& ph = p.ph[0];
+  ph.ntaps = KH * KW;
+  ph.koff = 0;
+  ph.ooy = ph.oox = 0;
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw) {
+      ph.dy[kh * KW + kw] = (signed char)(kh - pad);
+      ph.dx[kh * KW + kw] = (signed char)(kw - pad);
+    }
+  (void)cin;
+}
+
+// ConvTranspose2d(k=3, s=2, p=1, op=1): out[2g+a] gathers (d=0,k=1) for a=0 and (d=0,k=2),(d=+1,k=0) for a=1.
+static const int kTd[2][2] = {{0, 0}, {0, 1}};
+static const int kTk[2][2] = {{1, 0}, {2, 0}};
+static const int kTn[2] = {1, 2};
+static void phases_convT(ConvParams& p, int cin) {
+  p.nphases = 4;
+  int koff = 0;
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      ConvPhase& ph = p.ph[a * 2 + b];
+      ph.ntaps = kTn[a] * kTn[b];
+      ph.koff = koff;
+      ph.ooy = a;
+      ph.oox = b;
+      int t = 0;
+      for (int i = 0; i < kTn[a]; ++i)
+        for (int j = 0; j < kTn[b]; ++j, ++t) {
+          ph.dy[t] = (signed char)kTd[a][i];
+          ph.dx[t] = (signed char)kTd[b][j];
+        }
+      koff += ph.ntaps * cin;
+    }
+}
+
+// host-side packing of PyTorch-layout float weights into the kernels' K-major fp16 rows (used by ltb_conv2d_f16;
+// the model path receives rows already packed by livetalking_b200/w2l_pack.py, which follows the same order)
+static void pack_conv_w(const float* w, int cout, int cin, int KH, int KW, std::vector<__half>& out) {
+  out.resize((size_t)cout * KH * KW * cin);
+  for (int co = 0; co < cout; ++co)
+    for (int kh = 0; kh < KH; ++kh)
+      for (int kw = 0; kw < KW; ++kw)
+        for (int ci = 0; ci < cin; ++ci)
+          out[((size_t)co * KH * KW + kh * KW + kw) * cin + ci] = __float2half(w[(((size_t)co * cin + ci) * KH + kh) * KW + kw]);
+}
+static void pack_convT_w(const float* w, int cin, int cout, std::vector<__half>& out) {
+  out.resize((size_t)cout * 9 * cin);
+  for (int co = 0; co < cout; ++co) {
+    size_t k = 0;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int i = 0; i < kTn[a]; ++i)
+          for (int j = 0; j < kTn[b]; ++j) {
+            const int kh = kTk[a][i], kw = kTk[b][j];
+            for (int ci = 0; ci < cin; ++ci, ++k)
+              out[(size_t)co * 9 * cin + k] = __float2half(w[(((size_t)ci * cout + co) * 3 + kh) * 3 + kw]);
+          }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ objects
+struct BlobEntry {
+  char name[40];
+  uint32_t dtype;  // 0 = f16, 1 = f32
+  uint32_t pad;
+  uint64_t offset;
+  uint64_t nbytes;
+};
+struct BlobHeader {
+  char magic[8];  // "LTBW2L1"
+  uint32_t n_entries;
+  uint32_t header_bytes;
+};
+
+}  // namespace ltb
+
+using namespace ltb;
+
+struct ltb_w2l_model {
+  int device = 0;
+  uint8_t* blob = nullptr;
+  bool owns = false;
+  size_t nbytes = 0;
+  const __half* w[kNumLayers] = {nullptr};
+  const float* w0 = nullptr;  // layer 0 weights (f32 [32][9])
+  const float* bias[kNumLayers] = {nullptr};
+  const float* head_w = nullptr;
+  const float* head_b = nullptr;
+};
+
+struct ltb_w2l_avatar {
+  int device = 0;
+  int n = 0, H = 0, W = 0;
+  uint8_t* faces = nullptr;
+  uint8_t* frames = nullptr;
+  int* coords = nullptr;
+  std::vector<int> coords_host;
+};
+
+namespace ltb {
+struct Tensor {
+  __half* p = nullptr;
+  int H = 0, W = 0, C = 0;  // C = pixel pitch (total channels)
+};
+struct Op {
+  int type;  // 0 = conv (gather kernel), 1 = prep, 2 = audio conv0, 3 = head
+  ConvParams cp;
+};
+struct LayerOut {
+  const __half* p;
+  int H, W, C, Ctot, c_off;
+};
+}  // namespace ltb
+
+struct ltb_w2l_session {
+  ltb_w2l_model* m = nullptr;
+  ltb_w2l_avatar* a = nullptr;
+  int B = 0, l = 10, r = 10, fps = 25, flags = 0;
+  cudaStream_t st = nullptr;
+  std::vector<void*> allocs;
+  __half* img_pad = nullptr;
+  float* mel = nullptr;
+  float* pcm = nullptr;
+  int pcm_cap = 0;
+  double* mel_spec = nullptr;
+  double* mel_mel = nullptr;
+  float* pred = nullptr;
+  uint8_t* frames_out = nullptr;
+  int* d_index = nullptr;
+  std::vector<Op> ops;
+  LayerOut louts[kNumLayers];
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  long long launches = 0;
+  int graph_nodes = 0;
+};
+
+namespace ltb {
+
+static int dev_alloc(ltb_w2l_session* s, size_t bytes, void** out, bool zero) {
+  void* p = nullptr;
+  LTB_CUDA(cudaMalloc(&p, bytes));
+  if (zero) LTB_CUDA(cudaMemset(p, 0, bytes));
+  s->allocs.push_back(p);
+  *out = p;
+  return 0;
+}
+
+static int parse_blob(ltb_w2l_model* m, const uint8_t* host_header, size_t nbytes) {
+  if (nbytes < sizeof(BlobHeader)) return LTB_FAIL("weight blob too small");
+  BlobHeader h;
+  std::memcpy(&h, host_header, sizeof(h));
+  if (std::memcmp(h.magic, "LTBW2L1", 7) != 0) return LTB_FAIL("bad weight blob magic");
+  if (h.header_bytes > nbytes || h.header_bytes < sizeof(BlobHeader) + (size_t)h.n_entries * sizeof(BlobEntry))
+    return LTB_FAIL("bad weight blob header");
+  const BlobEntry* ent = reinterpret_cast<const BlobEntry*>(host_header + sizeof(BlobHeader));
+  auto find = [&](const std::string& name, uint32_t dtype, size_t expect_bytes, const void** out) -> int {
+    for (uint32_t i = 0; i < h.n_entries; ++i) {
+      if (name == ent[i].name) {
+        if (ent[i].dtype != dtype) return LTB_FAIL("blob entry " + name + ": wrong dtype");
+        if (ent[i].nbytes != expect_bytes)
+          return LTB_FAIL("blob entry " + name + ": expected " + std::to_string(expect_bytes) + " bytes, got " +
+                          std::to_string(ent[i].nbytes));
+        if (ent[i].offset % 256 != 0 || ent[i].offset + ent[i].nbytes > nbytes) return LTB_FAIL("blob entry " + name + ": bad offset");
+        *out = m->blob + ent[i].offset;
+        return 0;
+      }
+    }
+    return LTB_FAIL("blob entry " + name + " missing");
+  };
+  for (int i = 0; i < kNumLayers; ++i) {
+    int rows, K;
+    packed_dims(i, &rows, &K);
+    char nm[40];
+    const void* p = nullptr;
+    std::snprintf(nm, sizeof(nm), "L%02d.w", i);
+    if (i == 0) {
+      if (find(nm, 1, (size_t)rows * K * 4, &p)) return 1;
+      m->w0 = static_cast<const float*>(p);
+    } else {
+      if (find(nm, 0, (size_t)rows * K * 2, &p)) return 1;
+      m->w[i] = static_cast<const __half*>(p);
+    }
+    std::snprintf(nm, sizeof(nm), "L%02d.b", i);
+    if (find(nm, 1, (size_t)rows * 4, &p)) return 1;
+    m->bias[i] = static_cast<const float*>(p);
+  }
+  const void* p = nullptr;
+  if (find("head.w", 1, 96 * 4, &p)) return 1;
+  m->head_w = static_cast<const float*>(p);
+  if (find("head.b", 1, 3 * 4, &p)) return 1;
+  m->head_b = static_cast<const float*>(p);
+  return 0;
+}
+
+// fill the generic part of a ConvParams
+static ConvParams conv_base(const __half* in, int N, int IH, int IW, int ICtot, int ic_off, int Cin, __half* out, int OH,
+                            int OW, int OCtot, int oc_off, int Cout, const __half* w, int Ktot, const float* bias, bool relu) {
+  ConvParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.in = in;
+  p.N = N;
+  p.IH = IH;
+  p.IW = IW;
+  p.ICtot = ICtot;
+  p.ic_off = ic_off;
+  p.Cin = Cin;
+  p.sy = p.sx = 1;
+  p.GH = OH;
+  p.GW = OW;
+  p.out = out;
+  p.OH = OH;
+  p.OW = OW;
+  p.OCtot = OCtot;
+  p.oc_off = oc_off;
+  p.osy = p.osx = 1;
+  p.Cout = Cout;
+  p.w = w;
+  p.Ktot = Ktot;
+  p.bias = bias;
+  p.relu = relu ? 1 : 0;
+  p.M = N * OH * OW;
+  p.nphases = 1;
+  return p;
+}
+
+static int out_dim(int in, int k, int s, int pad) { return (in + 2 * pad - k) / s + 1; }
+
+struct View {
+  __half* p;
+  int H, W, Ctot, c_off, C;
+};
+
+static int build_plan(ltb_w2l_session* s) {
+  const int B = s->B;
+  const ltb_w2l_model* m = s->m;
+  const bool keep = (s->flags & LTB_SESSION_KEEP_LAYERS) != 0;
+
+  // concat buffers: {h, Cdec, Cskip}
+  const int catH[8] = {1, 4, 8, 16, 32, 64, 128, 256};
+  const int catD[8] = {512, 512, 512, 512, 384, 256, 128, 64};
+  const int catS[8] = {512, 512, 512, 256, 128, 64, 32, 16};
+  __half* cat[8];
+  for (int i = 0; i < 8; ++i) {
+    void* p;
+    if (dev_alloc(s, (size_t)B * catH[i] * catH[i] * (catD[i] + catS[i]) * 2, &p, true)) return 1;
+    cat[i] = static_cast<__half*>(p);
+  }
+  // temp ring (largest intra-block activation: [B,256,256,64])
+  const size_t tmp_bytes = (size_t)B * 256 * 256 * 64 * 2;
+  __half* ring[2] = {nullptr, nullptr};
+  int ring_next = 0;
+  auto new_tmp = [&](int H, int W, int C, View* v) -> int {
+    void* p = nullptr;
+    if (keep) {
+      if (dev_alloc(s, (size_t)B * H * W * C * 2, &p, true)) return 1;
+    } else {
+      if (!ring[ring_next]) {
+        if (dev_alloc(s, tmp_bytes, &p, true)) return 1;
+        ring[ring_next] = static_cast<__half*>(p);
+      }
+      p = ring[ring_next];
+      ring_next ^= 1;
+    }
+    *v = View{static_cast<__half*>(p), H, W, C, 0, C};
+    return 0;
+  };
+  // the audio encoder keeps its own small ring so it never aliases the face branch
+  __half* aring[2] = {nullptr, nullptr};
+  int aring_next = 0;
+  auto new_atmp = [&](int H, int W, int C, View* v) -> int {
+    void* p = nullptr;
+    if (keep) {
+      if (dev_alloc(s, (size_t)B * H * W * C * 2, &p, true)) return 1;
+    } else {
+      if (!aring[aring_next]) {
+        if (dev_alloc(s, (size_t)B * 80 * 16 * 32 * 2, &p, true)) return 1;
+        aring[aring_next] = static_cast<__half*>(p);
+      }
+      p = aring[aring_next];
+      aring_next ^= 1;
+    }
+    *v = View{static_cast<__half*>(p), H, W, C, 0, C};
+    return 0;
+  };
+  auto cat_dec = [&](int i) { return View{cat[i], catH[i], catH[i], catD[i] + catS[i], 0, catD[i]}; };
+  auto cat_skip = [&](int i) { return View{cat[i], catH[i], catH[i], catD[i] + catS[i], catD[i], catS[i]}; };
+  auto cat_all = [&](int i) { return View{cat[i], catH[i], catH[i], catD[i] + catS[i], 0, catD[i] + catS[i]}; };
+
+  auto record = [&](int li, const View& v) {
+    s->louts[li] = LayerOut{v.p, v.H, v.W, v.C, v.Ctot, v.c_off};
+  };
+  // regular conv block li: in -> out (+res)
+  auto add_conv = [&](int li, const View& in, const View& out, const View* res) -> int {
+    const LDef& L = kLayers[li];
+    if (in.C != L.cin || out.C != L.cout) return LTB_FAIL("plan: channel mismatch at layer " + std::to_string(li));
+    const int OH = out_dim(in.H, L.k, L.sy, L.pad), OW = out_dim(in.W, L.k, L.sx, L.pad);
+    if (OH != out.H || OW != out.W) return LTB_FAIL("plan: spatial mismatch at layer " + std::to_string(li));
+    ConvParams p = conv_base(in.p, B, in.H, in.W, in.Ctot, in.c_off, L.cin, out.p, OH, OW, out.Ctot, out.c_off, L.cout,
+                             m->w[li], L.k * L.k * L.cin, m->bias[li], true);
+    p.sy = L.sy;
+    p.sx = L.sx;
+    phases_conv(p, L.k, L.k, L.pad, L.cin);
+    if (res) {
+      p.res = res->p;
+      p.RCtot = res->Ctot;
+      p.rc_off = res->c_off;
+    }
+    s->ops.push_back(Op{0, p});
+    record(li, out);
+    return 0;
+  };
+  auto add_convT = [&](int li, const View& in, const View& out) -> int {
+    const LDef& L = kLayers[li];
+    if (in.C != L.cin || out.C != L.cout || out.H != 2 * in.H) return LTB_FAIL("plan: convT mismatch at layer " + std::to_string(li));
+    ConvParams p = conv_base(in.p, B, in.H, in.W, in.Ctot, in.c_off, L.cin, out.p, out.H, out.W, out.Ctot, out.c_off, L.cout,
+                             m->w[li], 9 * L.cin, m->bias[li], true);
+    p.GH = in.H;
+    p.GW = in.W;
+    p.M = B * in.H * in.W;
+    p.osy = p.osx = 2;
+    phases_convT(p, L.cin);
+    s->ops.push_back(Op{0, p});
+    record(li, out);
+    return 0;
+  };
+
+  // ---- prep (faces -> padded 8-channel fp16 image) and audio conv0
+  {
+    Op o;
+    std::memset(&o, 0, sizeof(o));
+    o.type = 1;
+    s->ops.push_back(o);
+  }
+  View a_prev;
+  if (new_atmp(80, 16, 32, &a_prev)) return 1;
+  {
+    Op o;
+    std::memset(&o, 0, sizeof(o));
+    o.type = 2;
+    o.cp.out = a_prev.p;
+    s->ops.push_back(o);
+    record(0, a_prev);
+  }
+  // ---- audio encoder 1..12
+  {
+    int H = 80, W = 16;
+    for (int li = 1; li <= 12; ++li) {
+      const LDef& L = kLayers[li];
+      const int OH = out_dim(H, L.k, L.sy, L.pad), OW = out_dim(W, L.k, L.sx, L.pad);
+      View o;
+      if (new_atmp(OH, OW, L.cout, &o)) return 1;
+      if (add_conv(li, a_prev, o, L.res ? &a_prev : nullptr)) return 1;
+      a_prev = o;
+      H = OH;
+      W = OW;
+    }
+  }
+  const View audio_emb = a_prev;  // [B,1,1,512]
+
+  // ---- face encoder
+  // stem (layer 13): 7 row-taps, each K block = 8 consecutive pixels x 8 channels of the padded image
+  {
+    const View out = cat_skip(7);
+    ConvParams p = conv_base(s->img_pad, B, 262, 264, 8, 0, 64, out.p, 256, 256, out.Ctot, out.c_off, 16, m->w[kStem], 7 * 64,
+                             m->bias[kStem], true);
+    p.nphases = 1;
+    p.ph[0].ntaps = 7;
+    for (int t = 0; t < 7; ++t) {
+      p.ph[0].dy[t] = (signed char)t;
+      p.ph[0].dx[t] = 0;
+    }
+    s->ops.push_back(Op{0, p});
+    record(kStem, out);
+  }
+  {
+    // blocks 1..7 : first layer strided from the previous skip slice, last layer writes the skip slice
+    const int first[8] = {13, 14, 17, 21, 24, 27, 29, 31};
+    const int last[8] = {13, 16, 20, 23, 26, 28, 30, 32};
+    for (int b = 1; b < 8; ++b) {
+      View prev = cat_skip(8 - b);  // output of block b-1 lives in cat[7-(b-1)]
+      for (int li = first[b]; li <= last[b]; ++li) {
+        const LDef& L = kLayers[li];
+        const int OH = out_dim(prev.H, L.k, L.sy, L.pad), OW = out_dim(prev.W, L.k, L.sx, L.pad);
+        View o;
+        if (li == last[b]) {
+          o = cat_skip(7 - b);
+        } else {
+          if (new_tmp(OH, OW, L.cout, &o)) return 1;
+        }
+        if (add_conv(li, prev, o, L.res ? &prev : nullptr)) return 1;
+        prev = o;
+      }
+    }
+  }
+  // ---- decoder
+  {
+    // block 0: 1x1 conv on the audio embedding -> cat0[0:512]
+    if (add_conv(33, audio_emb, cat_dec(0), nullptr)) return 1;
+    // block 1: ConvT(1024->512, k4, s1, p0) on a 1x1 map == 1x1 conv with 16*512 outputs laid out [4,4,512]
+    View t;
+    if (new_tmp(4, 4, 512, &t)) return 1;
+    {
+      const View in = cat_all(0);
+      ConvParams p = conv_base(in.p, B, 1, 1, in.Ctot, 0, 1024, t.p, 1, 1, 16 * 512, 0, 16 * 512, m->w[kConvT4], 1024,
+                               m->bias[kConvT4], true);
+      p.ph[0].ntaps = 1;
+      p.ph[0].dy[0] = p.ph[0].dx[0] = 0;
+      s->ops.push_back(Op{0, p});
+      record(kConvT4, t);
+    }
+    if (add_conv(35, t, cat_dec(1), &t)) return 1;
+    const int firstT[8] = {0, 0, 36, 38, 41, 44, 47, 50};
+    const int lastC[8] = {0, 0, 37, 40, 43, 46, 49, 52};
+    for (int b = 2; b < 8; ++b) {
+      View o;
+      const View in = cat_all(b - 1);
+      if (new_tmp(in.H * 2, in.W * 2, kLayers[firstT[b]].cout, &o)) return 1;
+      if (add_convT(firstT[b], in, o)) return 1;
+      View prev = o;
+      for (int li = firstT[b] + 1; li <= lastC[b]; ++li) {
+        View oo;
+        if (li == lastC[b]) {
+          oo = cat_dec(b);
+        } else {
+          if (new_tmp(prev.H, prev.W, kLayers[li].cout, &oo)) return 1;
+        }
+        if (add_conv(li, prev, oo, &prev)) return 1;
+        prev = oo;
+      }
+    }
+  }
+  // ---- output block: conv 80->32 on cat7, then 1x1 head + sigmoid
+  View h;
+  if (new_tmp(256, 256, 32, &h)) return 1;
+  if (add_conv(53, cat_all(7), h, nullptr)) return 1;
+  {
+    Op o;
+    std::memset(&o, 0, sizeof(o));
+    o.type = 3;
+    o.cp.in = h.p;
+    s->ops.push_back(o);
+  }
+  return 0;
+}
+
+static int run_ops(ltb_w2l_session* s, int index_for_eager) {
+  for (const Op& o : s->ops) {
+    cudaError_t e = cudaSuccess;
+    switch (o.type) {
+      case 0: e = launch_conv_gather(o.cp, s->st); break;
+      case 1: e = launch_w2l_prep_faces(s->a->faces, s->a->n, index_for_eager, s->B, s->img_pad, s->st); break;
+      case 2: e = launch_w2l_audio_conv0(s->mel, s->m->w0, s->m->bias[0], o.cp.out, s->B, s->st); break;
+      case 3: e = launch_w2l_head(o.cp.in, s->m->head_w, s->m->head_b, s->pred, s->B * 65536, s->st); break;
+    }
+    if (e != cudaSuccess) return LTB_FAIL(std::string("kernel launch failed: ") + cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+}  // namespace ltb
+
+// ==================================================================================================== C ABI
+extern "C" {
+
+int ltb_version(void) { return 100; }
+const char* ltb_last_error(void) { return g_last_error.c_str(); }
+
+int ltb_device_count(int* count) {
+  LTB_CUDA(cudaGetDeviceCount(count));
+  return 0;
+}
+int ltb_set_device(int device) {
+  LTB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  LTB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return LTB_FAIL(std::string("libltb200 needs an sm_100a GPU (B200); found ") + prop.name);
+  return 0;
+}
+
+int ltb_host_alloc(size_t nbytes, void** out) {
+  LTB_CUDA(cudaHostAlloc(out, nbytes, cudaHostAllocDefault));
+  return 0;
+}
+int ltb_host_free(void* p) {
+  LTB_CUDA(cudaFreeHost(p));
+  return 0;
+}
+
+static int model_from(ltb_w2l_model* m, const uint8_t* header_host, size_t nbytes, ltb_w2l_model** out) {
+  if (parse_blob(m, header_host, nbytes)) {
+    if (m->owns) cudaFree(m->blob);
+    delete m;
+    return 1;
+  }
+  *out = m;
+  return 0;
+}
+
+int ltb_w2l_model_create(const void* blob, size_t nbytes, ltb_w2l_model** out) {
+  if (!blob || !out) return LTB_FAIL("null argument");
+  auto* m = new ltb_w2l_model();
+  LTB_CUDA(cudaGetDevice(&m->device));
+  m->nbytes = nbytes;
+  m->owns = true;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->blob), nbytes);
+  if (e == cudaSuccess) e = cudaMemcpy(m->blob, blob, nbytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    delete m;
+    return LTB_FAIL(std::string("weight upload: ") + cudaGetErrorString(e));
+  }
+  return model_from(m, static_cast<const uint8_t*>(blob), nbytes, out);
+}
+
+int ltb_w2l_model_create_from_device(void* blob_dev, size_t nbytes, ltb_w2l_model** out) {
+  if (!blob_dev || !out) return LTB_FAIL("null argument");
+  if (nbytes < sizeof(BlobHeader)) return LTB_FAIL("weight blob too small");
+  BlobHeader h;
+  LTB_CUDA(cudaMemcpy(&h, blob_dev, sizeof(h), cudaMemcpyDeviceToHost));
+  if (h.header_bytes > nbytes || h.header_bytes > (1u << 24)) return LTB_FAIL("bad weight blob header");
+  std::vector<uint8_t> header(h.header_bytes);
+  LTB_CUDA(cudaMemcpy(header.data(), blob_dev, h.header_bytes, cudaMemcpyDeviceToHost));
+  auto* m = new ltb_w2l_model();
+  LTB_CUDA(cudaGetDevice(&m->device));
+  m->nbytes = nbytes;
+  m->owns = false;
+  m->blob = static_cast<uint8_t*>(blob_dev);
+  return model_from(m, header.data(), nbytes, out);
+}
+
+int ltb_w2l_model_destroy(ltb_w2l_model* m) {
+  if (!m) return 0;
+  if (m->owns && m->blob) cudaFree(m->blob);
+  delete m;
+  return 0;
+}
+
+int ltb_w2l_avatar_create(const uint8_t* faces, const uint8_t* frames, const int32_t* coords, int n, int H, int W,
+                          ltb_w2l_avatar** out) {
+  if (!faces || !frames || !coords || !out || n <= 0 || H <= 0 || W <= 0) return LTB_FAIL("bad avatar arguments");
+  for (int i = 0; i < n; ++i) {
+    const int y1 = coords[i * 4], y2 = coords[i * 4 + 1], x1 = coords[i * 4 + 2], x2 = coords[i * 4 + 3];
+    if (y1 < 0 || x1 < 0 || y2 > H || x2 > W || y2 <= y1 || x2 <= x1)
+      return LTB_FAIL("avatar coords[" + std::to_string(i) + "] outside the frame");
+  }
+  auto a = std::make_unique<ltb_w2l_avatar>();
+  LTB_CUDA(cudaGetDevice(&a->device));
+  a->n = n;
+  a->H = H;
+  a->W = W;
+  a->coords_host.assign(coords, coords + (size_t)n * 4);
+  LTB_CUDA(cudaMalloc(reinterpret_cast<void**>(&a->faces), (size_t)n * 65536 * 3));
+  LTB_CUDA(cudaMalloc(reinterpret_cast<void**>(&a->frames), (size_t)n * H * W * 3));
+  LTB_CUDA(cudaMalloc(reinterpret_cast<void**>(&a->coords), (size_t)n * 4 * sizeof(int)));
+  LTB_CUDA(cudaMemcpy(a->faces, faces, (size_t)n * 65536 * 3, cudaMemcpyHostToDevice));
+  LTB_CUDA(cudaMemcpy(a->frames, frames, (size_t)n * H * W * 3, cudaMemcpyHostToDevice));
+  LTB_CUDA(cudaMemcpy(a->coords, coords, (size_t)n * 4 * sizeof(int), cudaMemcpyHostToDevice));
+  *out = a.release();
+  return 0;
+}
+
+int ltb_w2l_avatar_destroy(ltb_w2l_avatar* a) {
+  if (!a) return 0;
+  cudaFree(a->faces);
+  cudaFree(a->frames);
+  cudaFree(a->coords);
+  delete a;
+  return 0;
+}
+
+int ltb_w2l_session_destroy(ltb_w2l_session* s) {
+  if (!s) return 0;
+  if (s->st) cudaStreamSynchronize(s->st);
+  if (s->gexec) cudaGraphExecDestroy(s->gexec);
+  if (s->graph) cudaGraphDestroy(s->graph);
+  for (void* p : s->allocs) cudaFree(p);
+  if (s->st) cudaStreamDestroy(s->st);
+  delete s;
+  return 0;
+}
+
+int ltb_w2l_session_create(ltb_w2l_model* m, ltb_w2l_avatar* a, int batch, int stride_left, int stride_right, int fps,
+                           int flags, ltb_w2l_session** out) {
+  if (!m || !a || !out) return LTB_FAIL("null argument");
+  if (batch < 1 || batch > 64) return LTB_FAIL("batch must be in [1,64]");
+  if (fps <= 0 || stride_left < 0 || stride_right < 0) return LTB_FAIL("bad fps/stride");
+  auto* s = new ltb_w2l_session();
+  s->m = m;
+  s->a = a;
+  s->B = batch;
+  s->l = stride_left;
+  s->r = stride_right;
+  s->fps = fps;
+  s->flags = flags;
+  auto bail = [&](int) {
+    ltb_w2l_session_destroy(s);
+    return 1;
+  };
+  if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) return bail(LTB_FAIL("stream create failed"));
+  void* p;
+  if (dev_alloc(s, (size_t)batch * 262 * 264 * 8 * 2, &p, true)) return bail(1);
+  s->img_pad = static_cast<__half*>(p);
+  if (dev_alloc(s, (size_t)batch * 80 * 16 * 4, &p, true)) return bail(1);
+  s->mel = static_cast<float*>(p);
+  s->pcm_cap = (stride_left + stride_right + 2 * batch) * 320;
+  if (dev_alloc(s, (size_t)s->pcm_cap * 4, &p, true)) return bail(1);
+  s->pcm = static_cast<float*>(p);
+  if (dev_alloc(s, mel_scratch_spec_doubles(s->pcm_cap) * 8, &p, true)) return bail(1);
+  s->mel_spec = static_cast<double*>(p);
+  if (dev_alloc(s, mel_scratch_mel_doubles(s->pcm_cap) * 8, &p, true)) return bail(1);
+  s->mel_mel = static_cast<double*>(p);
+  if (dev_alloc(s, (size_t)batch * 65536 * 3 * 4, &p, true)) return bail(1);
+  s->pred = static_cast<float*>(p);
+  if (dev_alloc(s, (size_t)batch * a->H * a->W * 3, &p, true)) return bail(1);
+  s->frames_out = static_cast<uint8_t*>(p);
+  if (dev_alloc(s, 256, &p, true)) return bail(1);
+  s->d_index = static_cast<int*>(p);
+  if (build_plan(s)) return bail(1);
+  // warm-up (also the reference's warm_up, wav2lip_avatar.py:90-96): one eager pass
+  if (run_ops(s, 0)) return bail(1);
+  cudaError_t e = cudaStreamSynchronize(s->st);
+  if (e != cudaSuccess) return bail(LTB_FAIL(std::string("warm-up forward failed: ") + cudaGetErrorString(e)));
+  *out = s;
+  return 0;
+}
+
+int ltb_w2l_mel_step(ltb_w2l_session* s, const float* pcm, int nsamples, float* out_mel) {
+  if (!s || !pcm) return LTB_FAIL("null argument");
+  const int expect = (s->l + s->r + 2 * s->B) * 320;
+  if (nsamples != expect) return LTB_FAIL("mel_step: expected " + std::to_string(expect) + " samples, got " + std::to_string(nsamples));
+  LTB_CUDA(cudaMemcpyAsync(s->pcm, pcm, (size_t)nsamples * 4, cudaMemcpyHostToDevice, s->st));
+  cudaError_t e = launch_mel_step(s->pcm, nsamples, s->B, s->l, s->fps, s->mel_spec, s->mel_mel, s->mel, s->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("mel kernels: ") + cudaGetErrorString(e));
+  s->launches += 3;
+  if (out_mel) {
+    LTB_CUDA(cudaMemcpyAsync(out_mel, s->mel, (size_t)s->B * 1280 * 4, cudaMemcpyDeviceToHost, s->st));
+    LTB_CUDA(cudaStreamSynchronize(s->st));
+  }
+  return 0;
+}
+
+static int forward_enqueue(ltb_w2l_session* s, int index) {
+  if (index < 0) return LTB_FAIL("negative index");
+  if (run_ops(s, index)) return 1;
+  s->launches += (long long)s->ops.size();
+  return 0;
+}
+
+int ltb_w2l_infer(ltb_w2l_session* s, int index, const float* mel, float* pred_out) {
+  if (!s) return LTB_FAIL("null session");
+  if (mel) LTB_CUDA(cudaMemcpyAsync(s->mel, mel, (size_t)s->B * 1280 * 4, cudaMemcpyHostToDevice, s->st));
+  if (forward_enqueue(s, index)) return 1;
+  if (pred_out) LTB_CUDA(cudaMemcpyAsync(pred_out, s->pred, (size_t)s->B * 65536 * 3 * 4, cudaMemcpyDeviceToHost, s->st));
+  LTB_CUDA(cudaStreamSynchronize(s->st));
+  return 0;
+}
+
+int ltb_w2l_paste(ltb_w2l_session* s, int slot, int idx, uint8_t* out_frame) {
+  if (!s || !out_frame) return LTB_FAIL("null argument");
+  if (slot < 0 || slot >= s->B) return LTB_FAIL("paste: slot out of range");
+  if (idx < 0 || idx >= s->a->n) return LTB_FAIL("paste: idx out of range");
+  const size_t fb = (size_t)s->a->H * s->a->W * 3;
+  cudaError_t e = launch_w2l_paste(s->a->frames, s->a->coords, s->a->n, s->a->H, s->a->W, s->pred, slot, 0, idx, 1,
+                                   s->frames_out + (size_t)slot * fb, s->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("paste kernel: ") + cudaGetErrorString(e));
+  s->launches += 1;
+  LTB_CUDA(cudaMemcpyAsync(out_frame, s->frames_out + (size_t)slot * fb, fb, cudaMemcpyDeviceToHost, s->st));
+  LTB_CUDA(cudaStreamSynchronize(s->st));
+  return 0;
+}
+
+static int paste_batch_enqueue(ltb_w2l_session* s, int index) {
+  cudaError_t e = launch_w2l_paste(s->a->frames, s->a->coords, s->a->n, s->a->H, s->a->W, s->pred, 0, index, -1, s->B,
+                                   s->frames_out, s->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("paste kernel: ") + cudaGetErrorString(e));
+  s->launches += 1;
+  return 0;
+}
+
+int ltb_w2l_paste_batch(ltb_w2l_session* s, int index, uint8_t* out_frames) {
+  if (!s) return LTB_FAIL("null session");
+  if (index < 0) return LTB_FAIL("negative index");
+  if (paste_batch_enqueue(s, index)) return 1;
+  if (out_frames) {
+    LTB_CUDA(cudaMemcpyAsync(out_frames, s->frames_out, (size_t)s->B * s->a->H * s->a->W * 3, cudaMemcpyDeviceToHost, s->st));
+    LTB_CUDA(cudaStreamSynchronize(s->st));
+  }
+  return 0;
+}
+
+int ltb_w2l_step_async(ltb_w2l_session* s, int index) {
+  if (!s) return LTB_FAIL("null session");
+  if (forward_enqueue(s, index)) return 1;
+  return paste_batch_enqueue(s, index);
+}
+
+int ltb_w2l_sync(ltb_w2l_session* s) {
+  if (!s) return LTB_FAIL("null session");
+  LTB_CUDA(cudaStreamSynchronize(s->st));
+  return 0;
+}
+
+int ltb_w2l_stream(ltb_w2l_session* s, void** cuda_stream) {
+  if (!s || !cuda_stream) return LTB_FAIL("null argument");
+  *cuda_stream = static_cast<void*>(s->st);
+  return 0;
+}
+
+int ltb_w2l_launch_count(ltb_w2l_session* s, long long* n) {
+  if (!s || !n) return LTB_FAIL("null argument");
+  *n = s->launches;
+  return 0;
+}
+
+int ltb_w2l_num_layers(void) { return kNumLayers; }
+
+int ltb_w2l_layer_shape(ltb_w2l_session* s, int layer, int* H, int* W, int* C) {
+  if (!s || layer < 0 || layer >= kNumLayers) return LTB_FAIL("bad layer");
+  *H = s->louts[layer].H;
+  *W = s->louts[layer].W;
+  *C = s->louts[layer].C;
+  return 0;
+}
+
+int ltb_w2l_layer_read(ltb_w2l_session* s, int layer, void* out_f16, size_t nbytes) {
+  if (!s || layer < 0 || layer >= kNumLayers || !out_f16) return LTB_FAIL("bad layer");
+  if (!(s->flags & LTB_SESSION_KEEP_LAYERS)) return LTB_FAIL("session was not created with LTB_SESSION_KEEP_LAYERS");
+  const LayerOut& lo = s->louts[layer];
+  const size_t rows = (size_t)s->B * lo.H * lo.W;
+  if (nbytes != rows * lo.C * 2) return LTB_FAIL("layer_read: wrong buffer size");
+  LTB_CUDA(cudaStreamSynchronize(s->st));
+  LTB_CUDA(cudaMemcpy2D(out_f16, (size_t)lo.C * 2, lo.p + lo.c_off, (size_t)lo.Ctot * 2, (size_t)lo.C * 2, rows,
+                        cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int ltb_conv2d_f16(const ltb_conv_desc* d, const void* in_f16, const float* w_f32, const float* bias_f32,
+                   const void* res_f16, void* out_f16) {
+  if (!d || !in_f16 || !w_f32 || !bias_f32 || !out_f16) return LTB_FAIL("null argument");
+  if (d->has_res && !res_f16) return LTB_FAIL("has_res set but res is null");
+  int OH, OW, Ktot;
+  std::vector<__half> wp;
+  if (d->transposed) {
+    if (d->KH != 3 || d->KW != 3) return LTB_FAIL("transposed conv: only k=3,s=2,p=1,op=1");
+    OH = d->IH * 2;
+    OW = d->IW * 2;
+    Ktot = 9 * d->Cin;
+    pack_convT_w(w_f32, d->Cin, d->Cout, wp);
+  } else {
+    if (d->KH * d->KW > kMaxTaps) return LTB_FAIL("kernel too large");
+    OH = out_dim(d->IH, d->KH, d->sy, d->pad);
+    OW = out_dim(d->IW, d->KW, d->sx, d->pad);
+    Ktot = d->KH * d->KW * d->Cin;
+    pack_conv_w(w_f32, d->Cout, d->Cin, d->KH, d->KW, wp);
+  }
+  if (OH <= 0 || OW <= 0) return LTB_FAIL("empty output");
+  const size_t in_b = (size_t)d->N * d->IH * d->IW * d->Cin * 2, out_b = (size_t)d->N * OH * OW * d->Cout * 2;
+  __half *din = nullptr, *dout = nullptr, *dw = nullptr, *dres = nullptr;
+  float* dbias = nullptr;
+  int rc = 0;
+  auto cleanup = [&]() {
+    cudaFree(din);
+    cudaFree(dout);
+    cudaFree(dw);
+    cudaFree(dres);
+    cudaFree(dbias);
+  };
+#define CK(x)                                                             \
+  do {                                                                    \
+    cudaError_t _e = (x);                                                 \
+    if (_e != cudaSuccess) {                                              \
+      rc = LTB_FAIL(std::string(#x) + ": " + cudaGetErrorString(_e));     \
+      cleanup();                                                          \
+      return rc;                                                          \
+    }                                                                     \
+  } while (0)
+  CK(cudaMalloc(&din, in_b));
+  CK(cudaMalloc(&dout, out_b));
+  CK(cudaMalloc(&dw, wp.size() * 2));
+  CK(cudaMalloc(&dbias, (size_t)d->Cout * 4));
+  CK(cudaMemcpy(din, in_f16, in_b, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dbias, bias_f32, (size_t)d->Cout * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dout, 0xFF, out_b));  // NaN pattern: unwritten outputs are caught by the test
+  if (d->has_res) {
+    CK(cudaMalloc(&dres, out_b));
+    CK(cudaMemcpy(dres, res_f16, out_b, cudaMemcpyHostToDevice));
+  }
+  ConvParams p = conv_base(din, d->N, d->IH, d->IW, d->Cin, 0, d->Cin, dout, OH, OW, d->Cout, 0, d->Cout, dw, Ktot, dbias,
+                           d->relu != 0);
+  if (d->transposed) {
+    p.GH = d->IH;
+    p.GW = d->IW;
+    p.M = d->N * d->IH * d->IW;
+    p.osy = p.osx = 2;
+    phases_convT(p, d->Cin);
+  } else {
+    p.sy = d->sy;
+    p.sx = d->sx;
+    phases_conv(p, d->KH, d->KW, d->pad, d->Cin);
+  }
+  if (d->has_res) {
+    p.res = dres;
+    p.RCtot = d->Cout;
+    p.rc_off = 0;
+  }
+  CK(launch_conv_gather(p, nullptr));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out_f16, dout, out_b, cudaMemcpyDeviceToHost));
+#undef CK
+  cleanup();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,126 @@
+"""Generate the committed golden fixtures.  Run in the BUILD container (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+* w2l_golden.npz   — the UNMODIFIED reference nn.Module (avatars/wav2lip/models/wav2lip_v2.py, imported by file
+                     path) run on CPU fp32 with the seeded synthetic weights of oracle.wav2lip_ref.synth_state_dict(0)
+                     and oracle.wav2lip_ref.synth_inputs(1, seed=5).  Pins oracle/wav2lip_ref.py to the reference code.
+* paste_golden.npz — cv2.resize / LipReal.paste_back_frame semantics (avatars/wav2lip_avatar.py:141-147) produced
+                     with the installed OpenCV, for several bbox sizes (up-scale, down-scale, exact 2x, identity).
+* mel_golden.npz   — librosa is not installed anywhere we can reach, so the mel fixture is produced by an
+                     INDEPENDENT torch pipeline (torch.stft + torchaudio Slaney filterbank + scipy.lfilter) following
+                     avatars/wav2lip/audio.py:45-51; it pins oracle/mel_ref.py against a second implementation
+                     ("parity unpinned" w.r.t. librosa itself, see oracle/__init__.py).
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from oracle import wav2lip_ref as R  # noqa: E402
+
+REF = "/root/reference"
+
+
+def load_reference_wav2lip():
+    pk = types.ModuleType("refmodels")
+    pk.__path__ = [f"{REF}/avatars/wav2lip/models"]
+    sys.modules["refmodels"] = pk
+    mods = {}
+    for n in ("conv", "wav2lip_v2"):
+        spec = importlib.util.spec_from_file_location(f"refmodels.{n}", f"{REF}/avatars/wav2lip/models/{n}.py")
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[f"refmodels.{n}"] = m
+        spec.loader.exec_module(m)
+        mods[n] = m
+    return mods["wav2lip_v2"].Wav2Lip
+
+
+def make_w2l():
+    sd = R.synth_state_dict(0)
+    mel, img = R.synth_inputs(1, seed=5)
+    net = load_reference_wav2lip()()
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    taps = {}
+    hooks = []
+    names = [p for p, _ in R.layer_list()]
+    for n in names:
+        mod = net.get_submodule(n)
+        hooks.append(mod.register_forward_hook(lambda m, i, o, n=n: taps.__setitem__(n, o.detach())))
+    with torch.no_grad():
+        out = net(mel, img)
+    for h in hooks:
+        h.remove()
+    pred = (out.numpy().transpose(0, 2, 3, 1) * 255.0)  # wav2lip_avatar.py:138
+    stats = np.array([[float(taps[n].mean()), float(taps[n].abs().mean()), float(taps[n].std())] for n in names], np.float64)
+    np.savez_compressed(os.path.join(HERE, "w2l_golden.npz"),
+                        pred_u8=pred.astype(np.uint8),
+                        pred_f32_sub=pred[:, ::4, ::4, :].astype(np.float32),
+                        layer_stats=stats,
+                        audio_emb=taps["audio_encoder.12"].numpy().reshape(-1).astype(np.float32),
+                        seed=np.array([0, 5]))
+    print("w2l golden: pred mean", pred.mean(), "std", pred.std())
+
+
+def synth_pred():
+    """Deterministic (256,256,3) float prediction with fractional parts (exercises the astype(uint8) truncation)."""
+    seed = np.random.default_rng(7).integers(0, 256, (32, 32, 3))
+    yy, xx = np.mgrid[0:256, 0:256]
+    base = np.kron(seed, np.ones((8, 8, 1), dtype=np.int64))
+    u8 = (base + (xx * 3 + yy * 5)[..., None]) % 256
+    return (u8 + 0.63).astype(np.float32).clip(0, 255)
+
+
+def synth_frame(h, w):
+    yy, xx = np.mgrid[0:h, 0:w]
+    return np.stack([(yy * 2) % 256, (xx * 3) % 256, (yy + xx) % 256], -1).astype(np.uint8)
+
+
+def make_paste():
+    import zlib
+    import cv2
+    pred = synth_pred()
+    # (y1,y2,x1,x2): up-scale, down-scale, exact 2x decimation (INTER_AREA substitution), identity, thin, full-frame
+    boxes = np.array([[10, 110, 20, 150], [5, 69, 8, 104], [30, 31, 40, 45], [2, 118, 3, 51], [10, 138, 20, 148],
+                      [20, 276, 30, 286], [0, 300, 0, 300], [7, 295, 1, 130]], np.int32)
+    crcs, subs = [], []
+    for (y1, y2, x1, x2) in boxes:
+        comb = synth_frame(300, 300)
+        comb[y1:y2, x1:x2] = cv2.resize(pred.astype(np.uint8), (int(x2 - x1), int(y2 - y1)))  # wav2lip_avatar.py:145-146
+        crcs.append(zlib.crc32(comb.tobytes()))
+        subs.append(comb[::3, ::3].copy())
+    np.savez_compressed(os.path.join(HERE, "paste_golden.npz"), boxes=boxes, crc32=np.array(crcs, np.uint64),
+                        sub=np.stack(subs))
+    print("paste golden ok")
+
+
+def make_mel():
+    import scipy.signal
+    import torchaudio
+    rng = np.random.default_rng(42)
+    t = np.arange(16640) / 16000.0
+    pcm = (0.3 * np.sin(2 * np.pi * 440 * t) + 0.1 * np.sin(2 * np.pi * 1330 * t + 1.0) +
+           0.05 * rng.standard_normal(t.size)).astype(np.float32)
+    y = scipy.signal.lfilter([1, -0.97], [1], pcm)
+    D = torch.stft(torch.from_numpy(y), 800, 200, 800, window=torch.hann_window(800, periodic=True, dtype=torch.float64),
+                   center=True, pad_mode="constant", return_complex=True).abs().numpy()
+    fb = torchaudio.functional.melscale_fbanks(401, 55.0, 7600.0, 80, 16000, norm="slaney", mel_scale="slaney").T.numpy()
+    S = fb.astype(np.float64) @ D
+    S = 20 * np.log10(np.maximum(1e-5, S)) - 20
+    mel = np.clip(8.0 * ((S + 100.0) / 100.0) - 4.0, -4.0, 4.0)
+    starts = [int(16.0 + i * 3.2) for i in range(16)]
+    win = np.stack([mel[:, s:s + 16] for s in starts], 0)
+    np.savez_compressed(os.path.join(HERE, "mel_golden.npz"), pcm=pcm, windows=win.astype(np.float32), mel=mel.astype(np.float32))
+    print("mel golden ok", win.shape, float((win == -4).mean()))
+
+
+if __name__ == "__main__":
+    make_w2l()
+    make_paste()
+    make_mel()

@@ -1,0 +1,77 @@
+"""GPU: the tcgen05 implicit-GEMM conv kernel against a plain PyTorch fp32 reference of the same op,
+called through the C ABI (ltb_conv2d_f16).  Tolerance: fp16 in/out, fp32 accumulate -> |err| <= 2e-2 + 1e-2*|ref|."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # N, H, W, Cin, Cout, k, (sy,sx), pad, transposed, res
+    (2, 16, 16, 64, 64, 3, (1, 1), 1, False, True),      # KB=64 BN=64, residual
+    (1, 12, 10, 32, 32, 3, (1, 1), 1, False, True),      # KB=32, ragged M (120 rows)
+    (2, 20, 20, 16, 32, 3, (2, 2), 1, False, False),     # KB=16, stride 2
+    (1, 12, 10, 128, 256, 3, (2, 2), 1, False, False),   # stride 2, 2 N tiles
+    (3, 80, 16, 32, 64, 3, (3, 1), 1, False, False),     # audio encoder stride (3,1)
+    (3, 27, 16, 64, 128, 3, (3, 3), 1, False, False),    # audio encoder stride 3
+    (3, 9, 6, 128, 256, 3, (3, 2), 1, False, False),     # audio encoder stride (3,2)
+    (16, 1, 1, 512, 512, 1, (1, 1), 0, False, False),    # 1x1 on the bottleneck (M = 16)
+    (4, 4, 4, 512, 512, 4, (1, 1), 0, False, False),     # 4x4 valid conv -> 1x1 (16 taps)
+    (4, 3, 3, 256, 512, 3, (1, 1), 0, False, False),     # 3x3 valid conv -> 1x1
+    (1, 5, 7, 64, 32, 3, (2, 2), 1, True, False),        # ConvT phases, ragged
+    (2, 8, 8, 160, 64, 3, (2, 2), 1, True, False),       # ConvT KB=32
+    (2, 4, 4, 1024, 512, 3, (2, 2), 1, True, False),     # ConvT deep K
+    (1, 16, 16, 384, 384, 3, (1, 1), 1, False, True),    # 3 N tiles of 128
+    (1, 24, 24, 80, 32, 3, (1, 1), 1, False, False),     # head conv: KB=16, 5 chunks per tap
+    (1, 64, 64, 64, 64, 3, (1, 1), 1, False, True),      # many M tiles
+    (1, 32, 32, 320, 128, 3, (2, 2), 1, True, False),    # ConvT 320 -> 128
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"c{i}" for i in range(len(CASES))])
+def test_conv_matches_torch_fp32(case):
+    from livetalking_b200 import engine
+    engine.set_device(0)
+    N, H, W, Cin, Cout, k, s, pad, transposed, res = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = (torch.randn(N, Cin, H, W, generator=g) * 0.7).half()
+    fan = Cin * k * k
+    if transposed:
+        w = torch.randn(Cin, Cout, k, k, generator=g) * (2.0 / (fan / 4)) ** 0.5
+    else:
+        w = torch.randn(Cout, Cin, k, k, generator=g) * (2.0 / fan) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.2
+    wq = w.half().float()
+    if transposed:
+        ref = F.conv_transpose2d(x.float(), wq, b, stride=2, padding=1, output_padding=1)
+    else:
+        ref = F.conv2d(x.float(), wq, b, stride=s, padding=pad)
+    r = None
+    if res:
+        r = (torch.randn(ref.shape, generator=g) * 0.5).half()
+        ref = ref + r.float()
+    ref = F.relu(ref).permute(0, 2, 3, 1).contiguous().numpy()
+    out = engine.conv2d_f16(x.permute(0, 2, 3, 1).contiguous().numpy(), w.numpy(), b.numpy(), stride=s, pad=pad,
+                            transposed=transposed, relu=True,
+                            res=None if r is None else r.permute(0, 2, 3, 1).contiguous().numpy())
+    assert out.shape == ref.shape
+    out = out.astype(np.float32)
+    assert np.isfinite(out).all(), "unwritten / non-finite outputs"
+    err = np.abs(out - ref)
+    tol = 2e-2 + 1e-2 * np.abs(ref)
+    assert (err <= tol).all(), f"max err {err.max():.4f} at {np.unravel_index(err.argmax(), err.shape)}; mean {err.mean():.5f}"
+    assert err.mean() < 2e-3
+
+
+def test_conv_no_relu_negative_outputs():
+    from livetalking_b200 import engine
+    engine.set_device(0)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 64, 8, 8, generator=g).half()
+    w = torch.randn(32, 64, 3, 3, generator=g) * 0.05
+    b = torch.randn(32, generator=g)
+    ref = F.conv2d(x.float(), w.half().float(), b, padding=1).permute(0, 2, 3, 1).numpy()
+    out = engine.conv2d_f16(x.permute(0, 2, 3, 1).contiguous().numpy(), w.numpy(), b.numpy(), pad=1, relu=False).astype(np.float32)
+    assert (ref < 0).any()
+    assert np.abs(out - ref).max() < 2e-2
