@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Benchmark of the lip-sync hot path (BASELINE.json metric: lip-sync frames/sec, wav2lip256, 256^2, batch 16).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of 16 frames:
+    mel windows (resident PCM) -> wav2lip256 forward -> paste-back of 16 frames into 720p frames.
+`value`  : device-timed throughput with every input already resident in HBM (CUDA events on the engine's stream).
+`e2e`    : the same metric through the public plugin-level API with HOST buffers: pinned PCM -> H2D -> mel ->
+           forward -> paste -> D2H of the 16 composited frames, every step.
+Under torchrun (N > 1) every rank drives its own GPU with its own session (sessions are independent: weak scaling);
+weights are packed on rank 0 and broadcast once with NCCL (the only collective of the design).
+`--impl reference` times the reference's own CPU implementation of the path (the oracle port: CPU PyTorch fp32 +
+numpy mel + OpenCV-exact paste) on the host cores; rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "lip-sync frames/sec (wav2lip256, 256x256, batch 16, mel + U-Net fwd + paste-back)"
+GFLOP_PER_FRAME = 55.58           # BASELINE.md §2 / SURVEY §8(d): 27.789 GMAC, hooks on the reference module
+BATCH = 16
+SL, SR, FPS = 10, 10, 25   # opt.l, opt.r (20 ms chunks), opt.fps
+FRAME_H, FRAME_W = 720, 1280
+BBOX = (200, 520, 480, 800)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))), "hbm": float(d["hbm_gbs"]),
+                "src": "measured (MEASURED_PEAKS.json, sustained bf16 cuBLAS)"}
+    return {"tflops": 1400.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def step_pcm(audio: np.ndarray, step: int) -> np.ndarray:
+    """The (l + r + 2B) chunk buffer MelASR.run_step would hold at `step` of the 60 s stream (wraps around)."""
+    n = (SL + SR + 2 * BATCH) * 320
+    start = (step * 2 * BATCH * 320) % (audio.size - n)
+    return audio[start:start + n]
+
+
+# ------------------------------------------------------------------------------------------------ reference arm / CPU baseline
+def cpu_path_fps(frames_per_rep: int, reps: int, threads: int):
+    """The reference's own CPU implementation of the path (oracle port, see oracle/__init__.py), timed on host cores."""
+    import torch
+    from livetalking_b200 import synth
+    from oracle import mel_ref, paste_ref
+    from oracle import wav2lip_ref as R
+    torch.set_num_threads(threads)
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in synth.random_state_dict(0).items()}
+    for k in list(sd):
+        if k.endswith("running_var"):
+            sd[k.replace("running_var", "num_batches_tracked")] = torch.tensor(1)
+    faces, frames, coords = synth.synthetic_avatar(n=4, H=FRAME_H, W=FRAME_W, bbox=BBOX)
+    audio = synth.sine_audio(5.0)
+    B = frames_per_rep
+    n = (SL + SR + 2 * B) * 320
+
+    def one(step):
+        pcm = audio[(step * 640) % (audio.size - n):][:n]
+        mel = mel_ref.mel_step(pcm, B, SL, SR, FPS)                                        # MelASR.run_step
+        img = paste_ref.w2l_build_batch(list(faces), step * B, B)                       # inference_batch glue
+        out = R.wav2lip_forward(sd, torch.from_numpy(mel.astype(np.float32)).reshape(B, 1, 80, 16), torch.from_numpy(img))
+        pred = out.numpy().transpose(0, 2, 3, 1) * 255.0
+        for i in range(B):                                                               # paste_back_frame
+            idx = paste_ref.mirror_index(len(faces), step * B + i)
+            paste_ref.w2l_paste_back(pred[i], frames[idx], coords[idx])
+
+    one(0)
+    t0 = time.perf_counter()
+    for r in range(reps):
+        one(r + 1)
+    dt = time.perf_counter() - t0
+    return B * reps / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    fpr = 2
+    fps, dt = cpu_path_fps(fpr, max(1, args.steps), cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(fps, 4), "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": 1, "ms_per_step": round(1000.0 * fpr / fps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "wav2lip256 batch 16, 256x256, 60 s synthetic audio, U-Net fwd + paste-back (configs[1]); "
+                               f"CPU arm: each step = a bounded sample of {fpr} frames of that workload"},
+        "cpu_baseline": {"value": round(fps, 4), "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x {fpr} frames: numpy mel + CPU PyTorch fp32 wav2lip256 + paste-back"},
+        "e2e": {"value": round(fps, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    from livetalking_b200 import engine, synth
+    from livetalking_b200.w2l_pack import pack_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local)
+    engine.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # ---- weights: packed on rank 0, broadcast once over NCCL (NVLink/NVSwitch), adopted in place by every rank
+    if rank == 0:
+        blob = np.frombuffer(pack_state_dict(synth.random_state_dict(0)), dtype=np.uint8)
+        nbytes = torch.tensor([blob.size], dtype=torch.int64, device="cuda")
+    else:
+        blob, nbytes = None, torch.zeros(1, dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.broadcast(nbytes, 0)
+    wdev = torch.empty(int(nbytes.item()), dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        wdev.copy_(torch.from_numpy(blob.copy()))
+    if world > 1:
+        dist.broadcast(wdev, 0)
+    torch.cuda.synchronize()
+    model = engine.W2LModel(device_ptr=wdev.data_ptr(), nbytes=wdev.numel(), keepalive=wdev)
+
+    faces, frames, coords = synth.synthetic_avatar(n=64, H=FRAME_H, W=FRAME_W, bbox=BBOX, seed=rank)
+    av = engine.W2LAvatar(faces, frames, coords)
+    sess = engine.W2LSession(model, av, BATCH, SL, SR, FPS)
+    audio = synth.sine_audio(60.0)
+    stream = torch.cuda.ExternalStream(sess.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: everything resident (PCM window uploaded once, faces/frames resident), device-timed
+    sess.mel_step(step_pcm(audio, 0), want_output=False)
+    sess.sync()
+    idx = 0
+    for _ in range(args.warmup):
+        sess.step_async(idx)
+        idx += BATCH
+    barrier()
+    l0 = sess.launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        sess.step_async(idx)
+        idx += BATCH
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = sess.launch_count - l0
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * BATCH * args.steps / (ms_max / 1000.0)
+
+    # ---- e2e: public API, host buffers, copies inside the timed region
+    pin_pcm = engine.PinnedBuffer(((SL + SR + 2 * BATCH) * 320,), np.float32)
+    pin_out = engine.PinnedBuffer((BATCH, FRAME_H, FRAME_W, 3), np.uint8)
+
+    def e2e_step(k, index):
+        pin_pcm.array[:] = step_pcm(audio, k)                    # "TTS" hands over host PCM
+        sess.mel_step(pin_pcm.array, want_output=False)          # H2D + mel kernels
+        sess.infer(index, None, want_pred=False)                 # forward
+        sess.paste_batch(index, out=pin_out.array)               # composite + D2H of 16 frames
+
+    for k in range(max(3, args.warmup)):
+        e2e_step(k, k * BATCH)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        e2e_step(k, idx + k * BATCH)
+    e1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1000.0
+    te = torch.tensor([max(e0.elapsed_time(e1), wall_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * BATCH * args.steps / (float(te.item()) / 1000.0)
+
+    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv): per-op CUDA-event timing, median of 3 passes
+    roof = None
+    per_op = None
+    if rank == 0:
+        peaks = load_peaks()
+        passes = [sess.profile_ops(idx)[0] for _ in range(3)]
+        ms_ops, flops, kinds = sess.profile_ops(idx)
+        med = np.median(np.stack(passes + [ms_ops]), axis=0)
+        conv = kinds == 0
+        conv_ms = float(med[conv].sum())
+        algo_flops = GFLOP_PER_FRAME * 1e9 * BATCH            # per step (all conv launches of one step)
+        achieved = algo_flops / (conv_ms / 1000.0) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_step")
+            except Exception:
+                traffic = None
+        roof = {"bound": "tensor", "achieved": round(achieved, 2), "peak": peaks["tflops"], "unit": "TFLOP/s",
+                "frac": round(achieved / peaks["tflops"], 4), "traffic": traffic, "peak_source": peaks["src"],
+                "kernel": "conv_gather_umma (tcgen05 implicit GEMM), all conv launches of one step",
+                "conv_ms_per_step": round(conv_ms, 4), "other_ms_per_step": round(float(med[~conv].sum()), 4),
+                "algorithmic_gflop_per_step": round(algo_flops / 1e9, 1)}
+        per_op = [(int(k), round(float(m), 4), float(f)) for k, m, f in zip(kinds, med, flops)]
+        if args.dump_ops:
+            os.makedirs(os.path.dirname(os.path.abspath(args.dump_ops)), exist_ok=True)
+            json.dump({"ops": per_op, "note": "kind(0 conv,1 prep,2 audio_conv0,3 head), median ms, algorithmic flops"},
+                      open(args.dump_ops, "w"))
+
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            fps, dt = cpu_path_fps(2, 4, cores)
+            cpu = {"value": round(fps, 4), "unit": "frames/s", "cores": cores, "kind": "port",
+                   "sample": "4 reps x 2 frames (+1 warm-up): numpy mel + CPU PyTorch fp32 wav2lip256 + paste-back (oracle port)"}
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 (fp32 accumulate); mel f64; paste u8", "data": "synthetic",
+            "config": {"workload": "wav2lip256 batch 16, 256x256, 1xB200 per rank, 60 s synthetic 16 kHz sine audio, "
+                                   "mel + U-Net fwd + paste-back into 720p frames (BASELINE.json configs[1])",
+                       "global_batch": BATCH * world, "sessions_per_gpu": 1, "parallelism": f"session-sharded x{world}",
+                       "l2": "working set per step (activations ~0.9 GB + 107 MB weights) exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": int(pin_pcm.nbytes),
+                    "d2h_bytes_per_step": int(pin_out.nbytes)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    sess.close()
+    av.close()
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-ops", default=None, help="write per-op timings (json)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -76,9 +76,16 @@ int ltb_w2l_paste(ltb_w2l_session* s, int slot, int idx, uint8_t* out_frame);
  * out_frames: uint8 [batch,H,W,3] host buffer (pinned recommended) or NULL to keep them on the device. */
 int ltb_w2l_paste_batch(ltb_w2l_session* s, int index, uint8_t* out_frames);
 
-/* whole step with everything resident: forward (audio windows already on the device) + batched paste-back,
- * enqueued on the session stream WITHOUT synchronising — used for device-timed throughput. */
+/* mel windows from the PCM buffer already resident on the device (uploaded by the last ltb_w2l_mel_step):
+ * the device-resident form of MelASR.run_step's feature extraction.  Asynchronous. */
+int ltb_w2l_mel_resident(ltb_w2l_session* s);
+/* whole step with everything resident in HBM: mel (resident PCM) + forward + batched paste-back, enqueued on the
+ * session stream WITHOUT synchronising — used for device-timed throughput. */
 int ltb_w2l_step_async(ltb_w2l_session* s, int index);
+/* profiling pass: runs the forward eagerly with a CUDA event between every op; returns per-op milliseconds, the
+ * algorithmic FLOPs of each op (2*M*N*K of the conv it implements, 0 for non-conv ops) and op kinds
+ * (0 conv, 1 prep_faces, 2 audio_conv0, 3 head).  Call with ms == NULL to query n_ops. */
+int ltb_w2l_profile_ops(ltb_w2l_session* s, int index, int max_ops, int* n_ops, float* ms, double* flops, int* kinds);
 int ltb_w2l_sync(ltb_w2l_session* s);
 /* the session's cudaStream_t (so a caller can record CUDA events on it) */
 int ltb_w2l_stream(ltb_w2l_session* s, void** cuda_stream);

@@ -26,7 +26,9 @@ int conv_gather_pick_bn(const ConvParams& p);
 
 // wav2lip-specific small kernels (w2l_small.cu)
 // faces u8 [nf,256,256,3] BGR -> padded fp16 [B,262,264,8]: ch0-2 = face/255 with rows >= 128 zeroed, ch3-5 = face/255
-cudaError_t launch_w2l_prep_faces(const uint8_t* faces, int nfaces, int index, int B, __half* img_pad, cudaStream_t st);
+// the first avatar index of the step is read from device memory (*d_index) so that a captured CUDA graph can be replayed
+cudaError_t launch_w2l_prep_faces(const uint8_t* faces, int nfaces, const int* d_index, int B, __half* img_pad, cudaStream_t st);
+cudaError_t launch_set_int(int* p, int v, cudaStream_t st);
 // mel f32 [B,80,16] -> fp16 NHWC [B,80,16,32]: conv3x3 p1 (1->32) + folded BN + ReLU
 cudaError_t launch_w2l_audio_conv0(const float* mel, const float* w9x32, const float* bias, __half* out, int B, cudaStream_t st);
 // x fp16 [npix,32] -> pred f32 [npix,3] = sigmoid(W x + b) * 255 ; optional u8 copy (truncation)

@@ -536,17 +536,33 @@ static int build_plan(ltb_w2l_session* s) {
   return 0;
 }
 
-static int run_ops(ltb_w2l_session* s, int index_for_eager) {
+static const char* op_name(const Op& o) {
+  switch (o.type) {
+    case 0: return "conv";
+    case 1: return "prep_faces";
+    case 2: return "audio_conv0";
+    case 3: return "head";
+  }
+  return "?";
+}
+
+// enqueue the forward plan on the session stream (reads the step's first avatar index from *d_index).
+// events (optional): ops.size()+1 events recorded around every op (profiling pass only).
+static int run_ops(ltb_w2l_session* s, cudaEvent_t* events = nullptr) {
+  size_t i = 0;
   for (const Op& o : s->ops) {
+    if (events) cudaEventRecord(events[i], s->st);
     cudaError_t e = cudaSuccess;
     switch (o.type) {
       case 0: e = launch_conv_gather(o.cp, s->st); break;
-      case 1: e = launch_w2l_prep_faces(s->a->faces, s->a->n, index_for_eager, s->B, s->img_pad, s->st); break;
+      case 1: e = launch_w2l_prep_faces(s->a->faces, s->a->n, s->d_index, s->B, s->img_pad, s->st); break;
       case 2: e = launch_w2l_audio_conv0(s->mel, s->m->w0, s->m->bias[0], o.cp.out, s->B, s->st); break;
       case 3: e = launch_w2l_head(o.cp.in, s->m->head_w, s->m->head_b, s->pred, s->B * 65536, s->st); break;
     }
-    if (e != cudaSuccess) return LTB_FAIL(std::string("kernel launch failed: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) return LTB_FAIL(std::string("kernel launch failed (") + op_name(o) + "): " + cudaGetErrorString(e));
+    ++i;
   }
+  if (events) cudaEventRecord(events[i], s->st);
   return 0;
 }
 
@@ -709,9 +725,24 @@ int ltb_w2l_session_create(ltb_w2l_model* m, ltb_w2l_avatar* a, int batch, int s
   s->d_index = static_cast<int*>(p);
   if (build_plan(s)) return bail(1);
   // warm-up (also the reference's warm_up, wav2lip_avatar.py:90-96): one eager pass
-  if (run_ops(s, 0)) return bail(1);
+  if (launch_set_int(s->d_index, 0, s->st) != cudaSuccess) return bail(LTB_FAIL("set_int launch failed"));
+  if (run_ops(s)) return bail(1);
   cudaError_t e = cudaStreamSynchronize(s->st);
   if (e != cudaSuccess) return bail(LTB_FAIL(std::string("warm-up forward failed: ") + cudaGetErrorString(e)));
+  if (!(flags & (LTB_SESSION_NO_GRAPH | LTB_SESSION_KEEP_LAYERS))) {
+    // capture the whole forward (57 launches) into one CUDA graph; the per-step index lives in device memory
+    e = cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return bail(LTB_FAIL(std::string("graph capture begin: ") + cudaGetErrorString(e)));
+    const int rc = run_ops(s);
+    e = cudaStreamEndCapture(s->st, &s->graph);
+    if (rc) return bail(1);
+    if (e != cudaSuccess) return bail(LTB_FAIL(std::string("graph capture end: ") + cudaGetErrorString(e)));
+    e = cudaGraphInstantiate(&s->gexec, s->graph, 0);
+    if (e != cudaSuccess) return bail(LTB_FAIL(std::string("graph instantiate: ") + cudaGetErrorString(e)));
+    e = cudaGraphLaunch(s->gexec, s->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+    if (e != cudaSuccess) return bail(LTB_FAIL(std::string("graph warm-up: ") + cudaGetErrorString(e)));
+  }
   *out = s;
   return 0;
 }
@@ -733,8 +764,13 @@ int ltb_w2l_mel_step(ltb_w2l_session* s, const float* pcm, int nsamples, float* 
 
 static int forward_enqueue(ltb_w2l_session* s, int index) {
   if (index < 0) return LTB_FAIL("negative index");
-  if (run_ops(s, index)) return 1;
-  s->launches += (long long)s->ops.size();
+  if (launch_set_int(s->d_index, index, s->st) != cudaSuccess) return LTB_FAIL("set_int launch failed");
+  if (s->gexec) {
+    LTB_CUDA(cudaGraphLaunch(s->gexec, s->st));
+  } else {
+    if (run_ops(s)) return 1;
+  }
+  s->launches += 1 + (long long)s->ops.size();
   return 0;
 }
 
@@ -780,10 +816,46 @@ int ltb_w2l_paste_batch(ltb_w2l_session* s, int index, uint8_t* out_frames) {
   return 0;
 }
 
+int ltb_w2l_mel_resident(ltb_w2l_session* s) {
+  if (!s) return LTB_FAIL("null session");
+  cudaError_t e = launch_mel_step(s->pcm, s->pcm_cap, s->B, s->l, s->fps, s->mel_spec, s->mel_mel, s->mel, s->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("mel kernels: ") + cudaGetErrorString(e));
+  s->launches += 3;
+  return 0;
+}
+
 int ltb_w2l_step_async(ltb_w2l_session* s, int index) {
   if (!s) return LTB_FAIL("null session");
+  if (ltb_w2l_mel_resident(s)) return 1;
   if (forward_enqueue(s, index)) return 1;
   return paste_batch_enqueue(s, index);
+}
+
+int ltb_w2l_profile_ops(ltb_w2l_session* s, int index, int max_ops, int* n_ops, float* ms, double* flops, int* kinds) {
+  if (!s || !n_ops) return LTB_FAIL("null argument");
+  const int n = (int)s->ops.size();
+  *n_ops = n;
+  if (!ms) return 0;
+  if (max_ops < n) return LTB_FAIL("profile_ops: buffer too small");
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) LTB_CUDA(cudaEventCreate(&e));
+  if (launch_set_int(s->d_index, index, s->st) != cudaSuccess) return LTB_FAIL("set_int launch failed");
+  int rc = run_ops(s, ev.data());
+  if (!rc && cudaStreamSynchronize(s->st) != cudaSuccess) rc = LTB_FAIL("profile pass failed");
+  for (int i = 0; i < n && !rc; ++i) {
+    cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    const Op& o = s->ops[i];
+    if (kinds) kinds[i] = o.type;
+    if (flops) {
+      double f = 0;
+      if (o.type == 0) {
+        for (int p = 0; p < o.cp.nphases; ++p) f += 2.0 * o.cp.M * o.cp.Cout * (double)o.cp.ph[p].ntaps * o.cp.Cin;
+      }
+      flops[i] = f;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
 }
 
 int ltb_w2l_sync(ltb_w2l_session* s) {

@@ -19,12 +19,13 @@ __device__ __forceinline__ int mirror_index_dev(int size, int index) {
 constexpr int kPadH = 262;  // 256 + 3 + 3
 constexpr int kPadW = 264;  // 256 + 3 + 5 (row pitch multiple of 8 pixels)
 
-__global__ void __launch_bounds__(256) w2l_prep_faces_kernel(const uint8_t* __restrict__ faces, int nfaces, int index,
+__global__ void __launch_bounds__(256) w2l_prep_faces_kernel(const uint8_t* __restrict__ faces, int nfaces,
+                                                             const int* __restrict__ d_index,
                                                              __half* __restrict__ img_pad) {
   const int b = blockIdx.y;
   const int pix = blockIdx.x * 256 + threadIdx.x;  // 0..65535
   const int y = pix >> 8, x = pix & 255;
-  const int fidx = mirror_index_dev(nfaces, index + b);
+  const int fidx = mirror_index_dev(nfaces, __ldg(d_index) + b);
   const uint8_t* src = faces + ((size_t)fidx * 65536 + pix) * 3;
   const float inv = 1.0f / 255.0f;
   const float c0 = src[0] * inv, c1 = src[1] * inv, c2 = src[2] * inv;
@@ -39,9 +40,10 @@ __global__ void __launch_bounds__(256) w2l_prep_faces_kernel(const uint8_t* __re
   *dst = o;
 }
 
-cudaError_t launch_w2l_prep_faces(const uint8_t* faces, int nfaces, int index, int B, __half* img_pad, cudaStream_t st) {
+cudaError_t launch_w2l_prep_faces(const uint8_t* faces, int nfaces, const int* d_index, int B, __half* img_pad,
+                                  cudaStream_t st) {
   dim3 grid(256, B);
-  w2l_prep_faces_kernel<<<grid, 256, 0, st>>>(faces, nfaces, index, img_pad);
+  w2l_prep_faces_kernel<<<grid, 256, 0, st>>>(faces, nfaces, d_index, img_pad);
   return cudaGetLastError();
 }
 
@@ -124,6 +126,12 @@ __global__ void __launch_bounds__(256) w2l_head_kernel(const __half* __restrict_
 
 cudaError_t launch_w2l_head(const __half* x, const float* w3x32, const float* b3, float* pred, int npix, cudaStream_t st) {
   w2l_head_kernel<<<(npix + 255) / 256, 256, 0, st>>>(x, w3x32, b3, pred, npix);
+  return cudaGetLastError();
+}
+
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+cudaError_t launch_set_int(int* p, int v, cudaStream_t st) {
+  set_int_kernel<<<1, 1, 0, st>>>(p, v);
   return cudaGetLastError();
 }
 

@@ -156,6 +156,19 @@ class W2LSession:
         check(lib().ltb_w2l_paste_batch(self._h, int(index), _ptr(out) if to_host else None))
         return out
 
+    def mel_resident(self) -> None:
+        check(lib().ltb_w2l_mel_resident(self._h))
+
+    def profile_ops(self, index: int = 0):
+        """One eager profiling pass: (ms, flops, kinds) per op of the forward plan."""
+        n = C.c_int(0)
+        check(lib().ltb_w2l_profile_ops(self._h, int(index), 0, C.byref(n), None, None, None))
+        ms = np.zeros(n.value, np.float32)
+        fl = np.zeros(n.value, np.float64)
+        kinds = np.zeros(n.value, np.int32)
+        check(lib().ltb_w2l_profile_ops(self._h, int(index), n.value, C.byref(n), _ptr(ms), _ptr(fl), _ptr(kinds)))
+        return ms, fl, kinds
+
     def step_async(self, index: int) -> None:
         check(lib().ltb_w2l_step_async(self._h, int(index)))
 
