@@ -50,6 +50,7 @@ int ltb_w2l_avatar_destroy(ltb_w2l_avatar* a);
 /* ---- session (one avatar stream) -------------------------------------------------------------------- */
 #define LTB_SESSION_KEEP_LAYERS 1 /* keep every layer's activations (debug / per-layer parity tests) */
 #define LTB_SESSION_NO_GRAPH 2    /* launch kernels eagerly instead of replaying a CUDA graph */
+#define LTB_SESSION_NO_HALO 4     /* route every conv to the generic gather kernel (A/B testing of the TMA halo kernel) */
 /* replaces LipReal.__init__ (avatars/wav2lip_avatar.py:101-114) + warm_up (:90-96): allocates the activation
  * arena for `batch` frames, builds the layer plan and (unless NO_GRAPH) captures it into a CUDA graph.
  * stride_left/right = opt.l / opt.r (20 ms chunks), fps = opt.fps. */
@@ -111,6 +112,11 @@ typedef struct ltb_conv_desc {
 } ltb_conv_desc;
 int ltb_conv2d_f16(const ltb_conv_desc* d, const void* in_f16, const float* w_f32, const float* bias_f32,
                    const void* res_f16, void* out_f16);
+
+/* hardware probe (test hook): D[128x64] = A * B^T with A = 16 groups of 8 consecutive 128-byte rows of a swizzled
+ * shared-memory buffer, first group at row `start_row`, groups `sbo_rows` rows apart, descriptor base_offset as given. */
+int ltb_umma_probe(const void* halo_f16, int halo_rows, const void* b_f16, int start_row, int sbo_rows, int base_offset,
+                   float* out_128x64);
 
 #ifdef __cplusplus
 }

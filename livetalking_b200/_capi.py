@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libltb200.so")
 
 LTB_SESSION_KEEP_LAYERS = 1
 LTB_SESSION_NO_GRAPH = 2
+LTB_SESSION_NO_HALO = 4
 
 
 class LtbError(RuntimeError):
@@ -51,6 +52,7 @@ _SIGS = {
     "ltb_w2l_num_layers": (C.c_int, []),
     "ltb_w2l_layer_shape": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ltb_w2l_layer_read": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "ltb_umma_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ltb_conv2d_f16": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

@@ -1,0 +1,425 @@
+// Halo-resident 3x3 convolution / sub-pixel ConvTranspose on tcgen05 (sm_100a) — the fast path for the FLOP-heavy
+// stride-1 layers of the U-Net (reference ops: avatars/wav2lip/models/conv.py:5-19 Conv2d+BN+residual+ReLU and
+// :33-44 ConvTranspose2d+BN+ReLU; the same kernel serves the MuseTalk VAE/UNet 3x3 convs).
+//
+// Idea: the nine im2col operands of a 3x3 conv are nine SHIFTED VIEWS of one input halo tile.  A CTA therefore TMA-loads
+// ONE (16*NSUB+2) x 10 pixel x 64 channel halo per K chunk into shared memory (128-byte rows, SWIZZLE_128B) and addresses
+// all nine views purely through the tcgen05 shared-memory descriptor: start address = halo + (dy*10+dx) rows, 8-row
+// groups 10 rows (1280 B) apart.  The 128B swizzle is a function of the absolute smem address, so unaligned starts and
+// an SBO that is not a multiple of 1024 B are legal (verified on hardware by umma_probe.cu / tests/probe_umma.py).
+// Compared with one tile load per tap this cuts L2->SM operand traffic for A by 6.4x; weights are streamed 3 taps at a
+// time and amortised over NSUB=2 stacked 128-pixel sub-tiles (M = 256 per CTA).
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue
+// (TMEM -> registers -> +bias (+residual) -> ReLU -> fp16 NHWC channel slice).  Persistent CTAs, double-buffered TMEM
+// accumulators: the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "conv_halo.h"
+#include "ptx_sm100.cuh"
+
+namespace ltb {
+
+constexpr int kHaloP = 10;  // halo row pitch in pixels (8 + 2)
+
+template <int BN, int NSUB, int NACC>
+struct HaloCfg {
+  static constexpr int HR = 16 * NSUB + 2;                                  // halo rows
+  static constexpr int A_BYTES_RAW = HR * kHaloP * 128;                     // TMA transaction bytes per A stage
+  static constexpr int A_BYTES = (A_BYTES_RAW + 1023) & ~1023;
+  static constexpr int B_BYTES = 3 * BN * 128;                              // 3 taps x BN rows x 64 k
+  static constexpr int A_STAGES = 2;
+  static constexpr int B_STAGES_MAX = (216 * 1024 - A_STAGES * A_BYTES) / B_BYTES;
+  static constexpr int B_STAGES = B_STAGES_MAX > 6 ? 6 : B_STAGES_MAX;
+  static constexpr int ACC_COLS = NACC * NSUB * BN;                         // fp32 columns per accumulator buffer
+  static constexpr int TCOLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
+                               : (2 * ACC_COLS <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_STAGES * B_BYTES + 1024;
+  static_assert(2 * ACC_COLS <= 512, "TMEM overflow");
+  static_assert(B_STAGES >= 2, "not enough shared memory for the weight ring");
+};
+
+template <int BN, int NSUB, int NACC>
+__global__ void __launch_bounds__(192, 1) conv_halo_umma_kernel(const __grid_constant__ HaloParams p) {
+  using C = HaloCfg<BN, NSUB, NACC>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[C::A_STAGES], a_empty[C::A_STAGES];
+  __shared__ __align__(8) uint64_t b_full[C::B_STAGES], b_empty[C::B_STAGES];
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_smem = smem0;
+  const uint32_t b_smem = smem0 + C::A_STAGES * C::A_BYTES;
+  const int chunks = (p.Cin + 63) / 64;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::A_STAGES; ++s) {
+      mbar_init(smem_u32(&a_full[s]), 1);
+      mbar_init(smem_u32(&a_empty[s]), 1);
+    }
+    for (int s = 0; s < C::B_STAGES; ++s) {
+      mbar_init(smem_u32(&b_full[s]), 1);
+      mbar_init(smem_u32(&b_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&acc_full[s]), 1);
+      mbar_init(smem_u32(&acc_empty[s]), 4);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&p.tm_in);
+    tma_prefetch_desc(&p.tm_w);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_slot), C::TCOLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  const int tiles_m = p.tiles_x * p.tiles_y * p.N;
+
+  if (warp == 0) {
+    // =============================================================== TMA producer
+    if (lane == 0) {
+      uint32_t ai = 0, bi = 0;  // running stage counters
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int nt = t / tiles_m;
+        int mt = t - nt * tiles_m;
+        const int img = mt / (p.tiles_x * p.tiles_y);
+        mt -= img * (p.tiles_x * p.tiles_y);
+        const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+        const int y0 = ty * (16 * NSUB) + p.halo_y0, x0 = tx * 8 + p.halo_x0;
+        for (int c = 0; c < chunks; ++c) {
+          const uint32_t as = ai % C::A_STAGES;
+          mbar_wait(smem_u32(&a_empty[as]), ((ai / C::A_STAGES) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(smem_u32(&a_full[as]), C::A_BYTES_RAW);
+          tma_load_4d(a_smem + as * C::A_BYTES, &p.tm_in, smem_u32(&a_full[as]), c * 64, x0, y0, img);
+          ++ai;
+          for (int j = 0; j < 3; ++j) {
+            const uint32_t bs = bi % C::B_STAGES;
+            mbar_wait(smem_u32(&b_empty[bs]), ((bi / C::B_STAGES) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(smem_u32(&b_full[bs]), C::B_BYTES);
+            tma_load_3d(b_smem + bs * C::B_BYTES, &p.tm_w, smem_u32(&b_full[bs]), c * 64, nt * BN, j * 3);
+            ++bi;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(128, BN);
+      uint32_t ai = 0, bi = 0, it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        const uint32_t buf = it & 1u;
+        mbar_wait(smem_u32(&acc_empty[buf]), ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t dbase = tmem + buf * C::ACC_COLS;
+        for (int c = 0; c < chunks; ++c) {
+          const uint32_t as = ai % C::A_STAGES;
+          mbar_wait(smem_u32(&a_full[as]), (ai / C::A_STAGES) & 1u);
+          const uint32_t a_base = a_smem + as * C::A_BYTES;
+          for (int j = 0; j < 3; ++j) {
+            const uint32_t bs = bi % C::B_STAGES;
+            mbar_wait(smem_u32(&b_full[bs]), (bi / C::B_STAGES) & 1u);
+            tc_fence_after();
+            const uint32_t b_base = b_smem + bs * C::B_BYTES;
+#pragma unroll
+            for (int tt = 0; tt < 3; ++tt) {
+              const int tap = j * 3 + tt;
+              const uint32_t a_tap = a_base + (uint32_t)p.tap_row[tap] * 128u;
+              const uint32_t d_tap = dbase + (uint32_t)p.tap_acc[tap] * (NSUB * BN);
+              const uint32_t fresh = (c == 0 && p.tap_first[tap]) ? 1u : 0u;
+#pragma unroll
+              for (int sub = 0; sub < NSUB; ++sub) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t ad = umma_smem_desc(a_tap + sub * (16 * kHaloP * 128) + k * 32, kHaloP * 128, 2);
+                  const uint64_t bd = umma_smem_desc(b_base + tt * (BN * 128) + k * 32, 1024, 2);
+                  umma_f16(d_tap + sub * BN, ad, bd, idesc, (fresh && k == 0) ? 0u : 1u);
+                }
+              }
+            }
+            umma_commit(smem_u32(&b_empty[bs]));
+            ++bi;
+          }
+          umma_commit(smem_u32(&a_empty[as]));
+          ++ai;
+        }
+        umma_commit(smem_u32(&acc_full[buf]));
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================================================== epilogue (warps 2..5 -> TMEM lane quarter warp%4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;       // 0..127 inside a sub-tile
+    const int ry = row >> 3, rx = row & 7;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int nt = t / tiles_m;
+      int mt = t - nt * tiles_m;
+      const int img = mt / (p.tiles_x * p.tiles_y);
+      mt -= img * (p.tiles_x * p.tiles_y);
+      const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+      const uint32_t buf = it & 1u;
+      mbar_wait(smem_u32(&acc_full[buf]), (it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tbase = tmem + buf * C::ACC_COLS + ((uint32_t)(q * 32) << 16);
+      const int n0 = nt * BN;
+#pragma unroll 1
+      for (int acc = 0; acc < NACC; ++acc) {
+#pragma unroll 1
+        for (int sub = 0; sub < NSUB; ++sub) {
+          const int gy = ty * (16 * NSUB) + sub * 16 + ry, gx = tx * 8 + rx;
+          const size_t opix = ((size_t)img * p.OH + gy * p.osy + p.acc_oy[acc]) * p.OW + gx * p.osx + p.acc_ox[acc];
+          __half* optr = p.out + opix * p.OCtot + p.oc_off + n0;
+          const __half* rptr = p.res ? (p.res + opix * p.RCtot + p.rc_off + n0) : nullptr;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tbase + (acc * NSUB + sub) * BN + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 32; g += 8) {
+              float f[8];
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + g));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + g + 4));
+              f[0] = __uint_as_float(v[g + 0]) + b0.x;
+              f[1] = __uint_as_float(v[g + 1]) + b0.y;
+              f[2] = __uint_as_float(v[g + 2]) + b0.z;
+              f[3] = __uint_as_float(v[g + 3]) + b0.w;
+              f[4] = __uint_as_float(v[g + 4]) + b1.x;
+              f[5] = __uint_as_float(v[g + 5]) + b1.y;
+              f[6] = __uint_as_float(v[g + 6]) + b1.z;
+              f[7] = __uint_as_float(v[g + 7]) + b1.w;
+              if (rptr) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rptr + c0 + g));
+                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float2 rf = __half22float2(rh[u]);
+                  f[2 * u] += rf.x;
+                  f[2 * u + 1] += rf.y;
+                }
+              }
+              uint4 ov;
+              __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                float x = f[2 * u], y = f[2 * u + 1];
+                if (p.relu) {
+                  x = fmaxf(x, 0.f);
+                  y = fmaxf(y, 0.f);
+                }
+                x = fminf(fmaxf(x, -65504.f), 65504.f);
+                y = fminf(fmaxf(y, -65504.f), 65504.f);
+                oh[u] = __floats2half2_rn(x, y);
+              }
+              *reinterpret_cast<uint4*>(optr + c0 + g) = ov;
+            }
+          }
+        }
+      }
+      // this accumulator buffer may be overwritten by the MMAs of tile it+2
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, C::TCOLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static bool encode(CUtensorMap* tm, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                   const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) return false;
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool is_conv3x3(const ConvParams& p) {
+  if (p.nphases != 1 || p.ph[0].ntaps != 9 || p.sy != 1 || p.sx != 1 || p.osy != 1 || p.osx != 1) return false;
+  for (int t = 0; t < 9; ++t)
+    if (p.ph[0].dy[t] != t / 3 - 1 || p.ph[0].dx[t] != t % 3 - 1) return false;
+  return p.IH == p.GH && p.IW == p.GW && p.OH == p.GH && p.OW == p.GW;
+}
+static bool is_convT(const ConvParams& p) {
+  if (p.nphases != 4 || p.osy != 2 || p.osx != 2 || p.sy != 1 || p.sx != 1) return false;
+  const int nt[4] = {1, 2, 2, 4};
+  for (int i = 0; i < 4; ++i)
+    if (p.ph[i].ntaps != nt[i]) return false;
+  return p.IH == p.GH && p.IW == p.GW && p.OH == 2 * p.GH && p.OW == 2 * p.GW;
+}
+
+bool conv_halo_supported(const ConvParams& p) {
+  if (!(is_conv3x3(p) || is_convT(p))) return false;
+  if (p.GH % 16 != 0 || p.GW % 8 != 0) return false;
+  if (p.Cout % 32 != 0 || p.Cin < 16) return false;
+  if ((p.ICtot % 8) || (p.ic_off % 8) || (p.Ktot != 9 * p.Cin)) return false;
+  return get_encode() != nullptr;
+}
+
+// picks (BN, NSUB, NACC) ; returns false if unsupported
+static bool pick_cfg(const ConvParams& p, int* BN, int* NSUB, int* NACC) {
+  const bool tr = is_convT(p);
+  *NACC = tr ? 4 : 1;
+  if (tr) {
+    *NSUB = 1;
+    *BN = (p.Cout % 64 == 0) ? 64 : 32;
+    return true;
+  }
+  *NSUB = (p.GH % 32 == 0) ? 2 : 1;
+  *BN = (p.Cout % 128 == 0) ? 128 : (p.Cout % 64 == 0) ? 64 : 32;
+  // small problems: prefer more tiles over wider tiles so the persistent grid fills the 148 SMs
+  auto tiles = [&](int bn, int nsub) { return (long)p.N * (p.GH / (16 * nsub)) * (p.GW / 8) * (p.Cout / bn); };
+  if (*NSUB == 2 && tiles(*BN, 2) < 148) *NSUB = 1;
+  while (*BN > 32 && tiles(*BN, *NSUB) < 120) *BN >>= 1;
+  return true;
+}
+
+int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan* out) {
+  if (!conv_halo_supported(p)) return 1;
+  HaloParams& h = out->hp;
+  std::memset(&h, 0, sizeof(h));
+  int BN, NSUB, NACC;
+  if (!pick_cfg(p, &BN, &NSUB, &NACC)) return 1;
+  out->BN = BN;
+  out->NSUB = NSUB;
+  out->NACC = NACC;
+  const bool tr = NACC == 4;
+  // input: 4-D (C, W, H, N) view of the NHWC channel slice
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.IW, (cuuint64_t)p.IH, (cuuint64_t)p.N};
+    cuuint64_t strides[3] = {(cuuint64_t)p.ICtot * 2, (cuuint64_t)p.IW * p.ICtot * 2, (cuuint64_t)p.IH * p.IW * p.ICtot * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)kHaloP, (cuuint32_t)(16 * NSUB + 2), 1};
+    if (!encode(&h.tm_in, 4, p.in + p.ic_off, dims, strides, box)) return 2;
+  }
+  // weights: 3-D (k = Cin, n = Cout, tap = 9) view of the tap-major copy [9][Cout][Cin]
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, 9};
+    cuuint64_t strides[2] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Cout * p.Cin * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)BN, 3};
+    if (!encode(&h.tm_w, 3, w_tap_major, dims, strides, box)) return 2;
+  }
+  h.out = p.out;
+  h.res = p.res;
+  h.bias = p.bias;
+  h.N = p.N;
+  h.Cin = p.Cin;
+  h.OCtot = p.OCtot;
+  h.oc_off = p.oc_off;
+  h.RCtot = p.RCtot;
+  h.rc_off = p.rc_off;
+  h.OH = p.OH;
+  h.OW = p.OW;
+  h.osy = p.osy;
+  h.osx = p.osx;
+  h.relu = p.relu;
+  h.halo_y0 = tr ? 0 : -1;
+  h.halo_x0 = tr ? 0 : -1;
+  int t = 0;
+  for (int ph = 0; ph < p.nphases; ++ph) {
+    h.acc_oy[ph] = p.ph[ph].ooy;
+    h.acc_ox[ph] = p.ph[ph].oox;
+    for (int i = 0; i < p.ph[ph].ntaps; ++i, ++t) {
+      const int dy = p.ph[ph].dy[i] - h.halo_y0, dx = p.ph[ph].dx[i] - h.halo_x0;  // position inside the halo
+      h.tap_row[t] = dy * kHaloP + dx;
+      h.tap_acc[t] = ph;
+      h.tap_first[t] = (i == 0) ? 1 : 0;
+    }
+  }
+  h.tiles_x = p.GW / 8;
+  h.tiles_y = p.GH / (16 * NSUB);
+  h.tiles_n = p.Cout / BN;
+  h.total_tiles = h.tiles_x * h.tiles_y * p.N * h.tiles_n;
+  return 0;
+}
+
+template <int BN, int NSUB, int NACC>
+static cudaError_t launch_cfg(const HaloPlan& pl, int sms, cudaStream_t st) {
+  using C = HaloCfg<BN, NSUB, NACC>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_umma_kernel<BN, NSUB, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int grid = pl.hp.total_tiles < sms ? pl.hp.total_tiles : sms;
+  conv_halo_umma_kernel<BN, NSUB, NACC><<<grid, 192, C::SMEM_BYTES, st>>>(pl.hp);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_halo(const HaloPlan& pl, cudaStream_t st) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int key = pl.BN * 100 + pl.NSUB * 10 + pl.NACC;
+  switch (key) {
+    case 12821: return launch_cfg<128, 2, 1>(pl, sms, st);
+    case 12811: return launch_cfg<128, 1, 1>(pl, sms, st);
+    case 6421: return launch_cfg<64, 2, 1>(pl, sms, st);
+    case 6411: return launch_cfg<64, 1, 1>(pl, sms, st);
+    case 3221: return launch_cfg<32, 2, 1>(pl, sms, st);
+    case 3211: return launch_cfg<32, 1, 1>(pl, sms, st);
+    case 6414: return launch_cfg<64, 1, 4>(pl, sms, st);
+    case 3214: return launch_cfg<32, 1, 4>(pl, sms, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// [Cout][9][Cin] -> [9][Cout][Cin] (one-off, at model load)
+__global__ void w_tap_major_kernel(const __half* __restrict__ w, __half* __restrict__ wt, int cout, int cin) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)cout * 9 * cin;
+  if (i >= total) return;
+  const int ci = (int)(i % cin);
+  const int tap = (int)((i / cin) % 9);
+  const int co = (int)(i / ((size_t)cin * 9));
+  wt[((size_t)tap * cout + co) * cin + ci] = w[i];
+}
+
+cudaError_t launch_w_tap_major(const __half* w, __half* wt, int cout, int cin, cudaStream_t st) {
+  const size_t total = (size_t)cout * 9 * cin;
+  w_tap_major_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, wt, cout, cin);
+  return cudaGetLastError();
+}
+
+}  // namespace ltb

@@ -1,0 +1,41 @@
+// Host/device interface of the halo-resident 3x3 conv / sub-pixel ConvT kernel (conv_halo.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstring>
+
+#include "conv_params.h"
+
+namespace ltb {
+
+struct alignas(64) HaloParams {
+  CUtensorMap tm_in;  // 4-D (C, W, H, N) fp16 NHWC channel slice, box (64, 10, 16*NSUB+2, 1), SWIZZLE_128B, OOB -> 0 (= padding)
+  CUtensorMap tm_w;   // 3-D (k, n, tap) over the tap-major weight copy [9][Cout][Cin], box (64, BN, 3)
+  __half* out;
+  const __half* res;
+  const float* bias;
+  int N, Cin;
+  int OCtot, oc_off, RCtot, rc_off;
+  int OH, OW, osy, osx;
+  int relu;
+  int halo_y0, halo_x0;  // halo origin relative to the tile origin (-1 for pad-1 conv, 0 for ConvT phases)
+  int tap_row[9];        // halo row offset (dy*10 + dx) of each of the 9 K-slices
+  int tap_acc[9];        // accumulator (sub-pixel phase) the slice contributes to
+  int tap_first[9];      // 1 = first slice of its accumulator (overwrite instead of accumulate on the first K chunk)
+  int acc_oy[4], acc_ox[4];
+  int tiles_x, tiles_y, tiles_n, total_tiles;
+};
+
+struct HaloPlan {
+  HaloParams hp;
+  int BN, NSUB, NACC;
+};
+
+bool conv_halo_supported(const ConvParams& p);
+// w_tap_major: device pointer to the [9][Cout][Cin] copy of the layer's weights. returns 0 on success.
+int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan* out);
+cudaError_t launch_conv_halo(const HaloPlan& pl, cudaStream_t st);
+cudaError_t launch_w_tap_major(const __half* w, __half* wt, int cout, int cin, cudaStream_t st);
+
+}  // namespace ltb

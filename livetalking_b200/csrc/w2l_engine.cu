@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/ltb200.h"
+#include "conv_halo.h"
 #include "ltb_internal.h"
 
 namespace ltb {
@@ -174,6 +175,7 @@ struct ltb_w2l_model {
   bool owns = false;
   size_t nbytes = 0;
   const __half* w[kNumLayers] = {nullptr};
+  __half* wt[kNumLayers] = {nullptr};  // tap-major [9][Cout][Cin] copies for the halo kernel (3x3 / sub-pixel ConvT layers)
   const float* w0 = nullptr;  // layer 0 weights (f32 [32][9])
   const float* bias[kNumLayers] = {nullptr};
   const float* head_w = nullptr;
@@ -195,8 +197,9 @@ struct Tensor {
   int H = 0, W = 0, C = 0;  // C = pixel pitch (total channels)
 };
 struct Op {
-  int type;  // 0 = conv (gather kernel), 1 = prep, 2 = audio conv0, 3 = head
+  int type;  // 0 = conv (gather kernel), 1 = prep, 2 = audio conv0, 3 = head, 4 = conv (halo kernel)
   ConvParams cp;
+  int halo = -1;  // index into the session's halo plans (type 4)
 };
 struct LayerOut {
   const __half* p;
@@ -220,6 +223,7 @@ struct ltb_w2l_session {
   uint8_t* frames_out = nullptr;
   int* d_index = nullptr;
   std::vector<Op> ops;
+  std::vector<HaloPlan> halo_plans;
   LayerOut louts[kNumLayers];
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
@@ -382,6 +386,21 @@ static int build_plan(ltb_w2l_session* s) {
   auto record = [&](int li, const View& v) {
     s->louts[li] = LayerOut{v.p, v.H, v.W, v.C, v.Ctot, v.c_off};
   };
+  // route a conv to the halo-resident TMA kernel when its geometry allows, else to the generic gather kernel
+  auto push_conv = [&](int li, const ConvParams& p) {
+    Op o;
+    o.type = 0;
+    o.cp = p;
+    if (!(s->flags & LTB_SESSION_NO_HALO) && m->wt[li] && conv_halo_supported(p)) {
+      HaloPlan pl;
+      if (conv_halo_make_plan(p, m->wt[li], &pl) == 0) {
+        o.type = 4;
+        o.halo = (int)s->halo_plans.size();
+        s->halo_plans.push_back(pl);
+      }
+    }
+    s->ops.push_back(o);
+  };
   // regular conv block li: in -> out (+res)
   auto add_conv = [&](int li, const View& in, const View& out, const View* res) -> int {
     const LDef& L = kLayers[li];
@@ -398,7 +417,7 @@ static int build_plan(ltb_w2l_session* s) {
       p.RCtot = res->Ctot;
       p.rc_off = res->c_off;
     }
-    s->ops.push_back(Op{0, p});
+    push_conv(li, p);
     record(li, out);
     return 0;
   };
@@ -412,7 +431,7 @@ static int build_plan(ltb_w2l_session* s) {
     p.M = B * in.H * in.W;
     p.osy = p.osx = 2;
     phases_convT(p, L.cin);
-    s->ops.push_back(Op{0, p});
+    push_conv(li, p);
     record(li, out);
     return 0;
   };
@@ -420,7 +439,7 @@ static int build_plan(ltb_w2l_session* s) {
   // ---- prep (faces -> padded 8-channel fp16 image) and audio conv0
   {
     Op o;
-    std::memset(&o, 0, sizeof(o));
+    std::memset(&o.cp, 0, sizeof(o.cp));
     o.type = 1;
     s->ops.push_back(o);
   }
@@ -428,7 +447,7 @@ static int build_plan(ltb_w2l_session* s) {
   if (new_atmp(80, 16, 32, &a_prev)) return 1;
   {
     Op o;
-    std::memset(&o, 0, sizeof(o));
+    std::memset(&o.cp, 0, sizeof(o.cp));
     o.type = 2;
     o.cp.out = a_prev.p;
     s->ops.push_back(o);
@@ -462,7 +481,7 @@ static int build_plan(ltb_w2l_session* s) {
       p.ph[0].dy[t] = (signed char)t;
       p.ph[0].dx[t] = 0;
     }
-    s->ops.push_back(Op{0, p});
+    push_conv(kStem, p);
     record(kStem, out);
   }
   {
@@ -498,7 +517,7 @@ static int build_plan(ltb_w2l_session* s) {
                                m->bias[kConvT4], true);
       p.ph[0].ntaps = 1;
       p.ph[0].dy[0] = p.ph[0].dx[0] = 0;
-      s->ops.push_back(Op{0, p});
+      push_conv(kConvT4, p);
       record(kConvT4, t);
     }
     if (add_conv(35, t, cat_dec(1), &t)) return 1;
@@ -528,7 +547,7 @@ static int build_plan(ltb_w2l_session* s) {
   if (add_conv(53, cat_all(7), h, nullptr)) return 1;
   {
     Op o;
-    std::memset(&o, 0, sizeof(o));
+    std::memset(&o.cp, 0, sizeof(o.cp));
     o.type = 3;
     o.cp.in = h.p;
     s->ops.push_back(o);
@@ -542,6 +561,7 @@ static const char* op_name(const Op& o) {
     case 1: return "prep_faces";
     case 2: return "audio_conv0";
     case 3: return "head";
+    case 4: return "conv_halo";
   }
   return "?";
 }
@@ -558,6 +578,7 @@ static int run_ops(ltb_w2l_session* s, cudaEvent_t* events = nullptr) {
       case 1: e = launch_w2l_prep_faces(s->a->faces, s->a->n, s->d_index, s->B, s->img_pad, s->st); break;
       case 2: e = launch_w2l_audio_conv0(s->mel, s->m->w0, s->m->bias[0], o.cp.out, s->B, s->st); break;
       case 3: e = launch_w2l_head(o.cp.in, s->m->head_w, s->m->head_b, s->pred, s->B * 65536, s->st); break;
+      case 4: e = launch_conv_halo(s->halo_plans[o.halo], s->st); break;
     }
     if (e != cudaSuccess) return LTB_FAIL(std::string("kernel launch failed (") + op_name(o) + "): " + cudaGetErrorString(e));
     ++i;
@@ -595,11 +616,35 @@ int ltb_host_free(void* p) {
   return 0;
 }
 
+static void model_free(ltb_w2l_model* m) {
+  for (int i = 0; i < kNumLayers; ++i)
+    if (m->wt[i]) cudaFree(m->wt[i]);
+  if (m->owns && m->blob) cudaFree(m->blob);
+  delete m;
+}
+
 static int model_from(ltb_w2l_model* m, const uint8_t* header_host, size_t nbytes, ltb_w2l_model** out) {
   if (parse_blob(m, header_host, nbytes)) {
-    if (m->owns) cudaFree(m->blob);
-    delete m;
+    model_free(m);
     return 1;
+  }
+  // tap-major weight copies for the halo kernel: every 3x3 s1 p1 conv and every k3 s2 ConvT
+  for (int i = 1; i < kNumLayers; ++i) {
+    const LDef& L = kLayers[i];
+    const bool conv3 = L.kind == 'c' && L.k == 3 && L.sy == 1 && L.sx == 1 && L.pad == 1 && L.cin >= 16;
+    const bool convt = L.kind == 't' && L.k == 3;
+    if (!conv3 && !convt) continue;
+    const size_t bytes = (size_t)L.cout * 9 * L.cin * 2;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->wt[i]), bytes);
+    if (e == cudaSuccess) e = launch_w_tap_major(m->w[i], m->wt[i], L.cout, L.cin, nullptr);
+    if (e != cudaSuccess) {
+      model_free(m);
+      return LTB_FAIL(std::string("tap-major weight copy: ") + cudaGetErrorString(e));
+    }
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    model_free(m);
+    return LTB_FAIL("tap-major weight copy failed");
   }
   *out = m;
   return 0;
@@ -638,8 +683,7 @@ int ltb_w2l_model_create_from_device(void* blob_dev, size_t nbytes, ltb_w2l_mode
 
 int ltb_w2l_model_destroy(ltb_w2l_model* m) {
   if (!m) return 0;
-  if (m->owns && m->blob) cudaFree(m->blob);
-  delete m;
+  model_free(m);
   return 0;
 }
 
@@ -848,7 +892,7 @@ int ltb_w2l_profile_ops(ltb_w2l_session* s, int index, int max_ops, int* n_ops, 
     if (kinds) kinds[i] = o.type;
     if (flops) {
       double f = 0;
-      if (o.type == 0) {
+      if (o.type == 0 || o.type == 4) {
         for (int p = 0; p < o.cp.nphases; ++p) f += 2.0 * o.cp.M * o.cp.Cout * (double)o.cp.ph[p].ntaps * o.cp.Cin;
       }
       flops[i] = f;
@@ -919,7 +963,7 @@ int ltb_conv2d_f16(const ltb_conv_desc* d, const void* in_f16, const float* w_f3
   }
   if (OH <= 0 || OW <= 0) return LTB_FAIL("empty output");
   const size_t in_b = (size_t)d->N * d->IH * d->IW * d->Cin * 2, out_b = (size_t)d->N * OH * OW * d->Cout * 2;
-  __half *din = nullptr, *dout = nullptr, *dw = nullptr, *dres = nullptr;
+  __half *din = nullptr, *dout = nullptr, *dw = nullptr, *dres = nullptr, *dwt = nullptr;
   float* dbias = nullptr;
   int rc = 0;
   auto cleanup = [&]() {
@@ -927,6 +971,7 @@ int ltb_conv2d_f16(const ltb_conv_desc* d, const void* in_f16, const float* w_f3
     cudaFree(dout);
     cudaFree(dw);
     cudaFree(dres);
+    cudaFree(dwt);
     cudaFree(dbias);
   };
 #define CK(x)                                                             \
@@ -968,7 +1013,23 @@ int ltb_conv2d_f16(const ltb_conv_desc* d, const void* in_f16, const float* w_f3
     p.RCtot = d->Cout;
     p.rc_off = 0;
   }
-  CK(launch_conv_gather(p, nullptr));
+  const bool can_halo = conv_halo_supported(p);
+  if (d->force_path == 2 && !can_halo) {
+    cleanup();
+    return LTB_FAIL("force_path=2 but this geometry is not supported by the halo kernel");
+  }
+  if (d->force_path != 1 && can_halo) {
+    CK(cudaMalloc(&dwt, wp.size() * 2));
+    CK(launch_w_tap_major(dw, dwt, d->Cout, d->Cin, nullptr));
+    HaloPlan pl;
+    if (conv_halo_make_plan(p, dwt, &pl) != 0) {
+      cleanup();
+      return LTB_FAIL("halo plan / tensor map creation failed");
+    }
+    CK(launch_conv_halo(pl, nullptr));
+  } else {
+    CK(launch_conv_gather(p, nullptr));
+  }
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out_f16, dout, out_b, cudaMemcpyDeviceToHost));
 #undef CK

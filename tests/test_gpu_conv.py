@@ -75,3 +75,58 @@ def test_conv_no_relu_negative_outputs():
     out = engine.conv2d_f16(x.permute(0, 2, 3, 1).contiguous().numpy(), w.numpy(), b.numpy(), pad=1, relu=False).astype(np.float32)
     assert (ref < 0).any()
     assert np.abs(out - ref).max() < 2e-2
+
+
+# ---- halo-resident TMA kernel (conv_halo.cu): 3x3 s1 p1 convs and k3 s2 ConvT with H % 16 == 0, W % 8 == 0
+HALO_CASES = [
+    # N, H, W, Cin, Cout, transposed, res
+    (1, 16, 16, 64, 64, False, True),       # NSUB=1
+    (1, 64, 64, 64, 64, False, True),       # NSUB=2, BN=64
+    (2, 32, 32, 128, 128, False, True),     # 2 chunks
+    (1, 32, 16, 256, 384, False, False),    # 3 N tiles, 4 chunks
+    (1, 32, 32, 80, 32, False, False),      # Cin=80: second chunk zero-filled beyond channel 80
+    (2, 32, 8, 32, 32, False, True),        # Cin=32: half a chunk
+    (16, 16, 16, 512, 512, False, True),    # deep K, many tiles, persistent loop
+    (3, 48, 24, 64, 128, False, False),     # non power-of-two tiling
+    (1, 16, 16, 64, 64, True, False),       # ConvT, 4 accumulators
+    (2, 32, 32, 160, 64, True, False),      # ConvT Cin=160 (2.5 chunks)
+    (1, 16, 8, 128, 32, True, False),       # ConvT BN=32
+    (1, 32, 32, 320, 128, True, False),     # ConvT 320->128
+    (1, 128, 128, 64, 64, False, True),     # many tiles per CTA
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES, ids=[f"h{i}" for i in range(len(HALO_CASES))])
+def test_halo_kernel_matches_torch_fp32(case):
+    from livetalking_b200 import engine
+    engine.set_device(0)
+    N, H, W, Cin, Cout, transposed, res = case
+    g = torch.Generator().manual_seed(1234 + hash(case) % 1000)
+    x = (torch.randn(N, Cin, H, W, generator=g) * 0.7).half()
+    if transposed:
+        w = torch.randn(Cin, Cout, 3, 3, generator=g) * (2.0 / (Cin * 9 / 4)) ** 0.5
+    else:
+        w = torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (Cin * 9)) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.2
+    wq = w.half().float()
+    if transposed:
+        ref = F.conv_transpose2d(x.float(), wq, b, stride=2, padding=1, output_padding=1)
+    else:
+        ref = F.conv2d(x.float(), wq, b, padding=1)
+    r = None
+    if res:
+        r = (torch.randn(ref.shape, generator=g) * 0.5).half()
+        ref = ref + r.float()
+    ref = F.relu(ref).permute(0, 2, 3, 1).contiguous().numpy()
+    xn = x.permute(0, 2, 3, 1).contiguous().numpy()
+    rn = None if r is None else r.permute(0, 2, 3, 1).contiguous().numpy()
+    out = engine.conv2d_f16(xn, w.numpy(), b.numpy(), stride=(1, 1), pad=1, transposed=transposed, relu=True, res=rn,
+                            force_path=2).astype(np.float32)
+    assert np.isfinite(out).all(), "unwritten / non-finite outputs"
+    err = np.abs(out - ref)
+    tol = 2e-2 + 1e-2 * np.abs(ref)
+    assert (err <= tol).all(), f"max err {err.max():.4f} at {np.unravel_index(err.argmax(), err.shape)}; mean {err.mean():.5f}"
+    # both tensor-core paths accumulate the same K order in fp32: they must agree to the last fp16 bit almost everywhere
+    out_g = engine.conv2d_f16(xn, w.numpy(), b.numpy(), stride=(1, 1), pad=1, transposed=transposed, relu=True, res=rn,
+                              force_path=1).astype(np.float32)
+    assert np.abs(out - out_g).max() <= 2e-2
