@@ -30,8 +30,10 @@ struct HaloCfg {
   static constexpr int A_BYTES_RAW = HR * kHaloP * 128;                     // TMA transaction bytes per A stage
   static constexpr int A_BYTES = (A_BYTES_RAW + 1023) & ~1023;
   static constexpr int B_BYTES = 3 * BN * 128;                              // 3 taps x BN rows x 64 k
-  static constexpr int A_STAGES = 2;
-  static constexpr int B_STAGES_MAX = (216 * 1024 - A_STAGES * A_BYTES) / B_BYTES;
+  // stage counts: fill the 227 KB of shared memory
+  static constexpr int BUDGET = 226 * 1024;
+  static constexpr int A_STAGES = (BN <= 32) ? 4 : (BN <= 64 ? 3 : (NSUB == 1 ? 3 : 2));
+  static constexpr int B_STAGES_MAX = (BUDGET - A_STAGES * A_BYTES) / B_BYTES;
   static constexpr int B_STAGES = B_STAGES_MAX > 6 ? 6 : B_STAGES_MAX;
   static constexpr int ACC_COLS = NACC * NSUB * BN;                         // fp32 columns per accumulator buffer
   static constexpr int TCOLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
@@ -115,6 +117,8 @@ __global__ void __launch_bounds__(192, 1) conv_halo_umma_kernel(const __grid_con
     // =============================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(128, BN);
+      constexpr uint32_t kADescHi = ((kHaloP * 128) >> 4) | (1u << 14) | (2u << 29);  // SBO = 1280 B (halo pitch)
+      constexpr uint32_t kBDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);            // SBO = 1024 B
       uint32_t ai = 0, bi = 0, it = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
         const uint32_t buf = it & 1u;
@@ -130,19 +134,21 @@ __global__ void __launch_bounds__(192, 1) conv_halo_umma_kernel(const __grid_con
             mbar_wait(smem_u32(&b_full[bs]), (bi / C::B_STAGES) & 1u);
             tc_fence_after();
             const uint32_t b_base = b_smem + bs * C::B_BYTES;
+            // descriptor words: hi = {SBO, version 1, SWIZZLE_128B} is loop invariant; lo = (addr >> 4) | LBO(1) << 16
+            const uint32_t b_lo0 = ((b_base & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t a_lo0 = ((a_base & 0x3FFFFu) >> 4) | (1u << 16);
 #pragma unroll
             for (int tt = 0; tt < 3; ++tt) {
               const int tap = j * 3 + tt;
-              const uint32_t a_tap = a_base + (uint32_t)p.tap_row[tap] * 128u;
+              const uint32_t a_lo_tap = a_lo0 + (uint32_t)p.tap_row[tap] * 8u;   // 128 B rows -> 8 x 16 B
               const uint32_t d_tap = dbase + (uint32_t)p.tap_acc[tap] * (NSUB * BN);
               const uint32_t fresh = (c == 0 && p.tap_first[tap]) ? 1u : 0u;
 #pragma unroll
               for (int sub = 0; sub < NSUB; ++sub) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  const uint64_t ad = umma_smem_desc(a_tap + sub * (16 * kHaloP * 128) + k * 32, kHaloP * 128, 2);
-                  const uint64_t bd = umma_smem_desc(b_base + tt * (BN * 128) + k * 32, 1024, 2);
-                  umma_f16(d_tap + sub * BN, ad, bd, idesc, (fresh && k == 0) ? 0u : 1u);
+                  umma_f16_lohi(d_tap + sub * BN, a_lo_tap + sub * (16 * kHaloP * 8) + k * 2, kADescHi,
+                                b_lo0 + tt * (BN * 8) + k * 2, kBDescHi, idesc, (fresh && k == 0) ? 0u : 1u);
                 }
               }
             }

@@ -199,7 +199,9 @@ struct Tensor {
 struct Op {
   int type;  // 0 = conv (gather kernel), 1 = prep, 2 = audio conv0, 3 = head, 4 = conv (halo kernel)
   ConvParams cp;
-  int halo = -1;  // index into the session's halo plans (type 4)
+  int halo = -1;    // index into the session's halo plans (type 4)
+  int branch = 0;   // 1 = audio-encoder branch: runs on the side stream, concurrently with the face encoder
+  bool join = false;  // first op that consumes the audio branch's result
 };
 struct LayerOut {
   const __half* p;
@@ -212,6 +214,8 @@ struct ltb_w2l_session {
   ltb_w2l_avatar* a = nullptr;
   int B = 0, l = 10, r = 10, fps = 25, flags = 0;
   cudaStream_t st = nullptr;
+  cudaStream_t st2 = nullptr;  // audio-encoder branch (forked/joined with events; becomes a parallel branch of the graph)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<void*> allocs;
   __half* img_pad = nullptr;
   float* mel = nullptr;
@@ -450,6 +454,7 @@ static int build_plan(ltb_w2l_session* s) {
     std::memset(&o.cp, 0, sizeof(o.cp));
     o.type = 2;
     o.cp.out = a_prev.p;
+    o.branch = 1;
     s->ops.push_back(o);
     record(0, a_prev);
   }
@@ -462,6 +467,7 @@ static int build_plan(ltb_w2l_session* s) {
       View o;
       if (new_atmp(OH, OW, L.cout, &o)) return 1;
       if (add_conv(li, a_prev, o, L.res ? &a_prev : nullptr)) return 1;
+      s->ops.back().branch = 1;
       a_prev = o;
       H = OH;
       W = OW;
@@ -508,6 +514,7 @@ static int build_plan(ltb_w2l_session* s) {
   {
     // block 0: 1x1 conv on the audio embedding -> cat0[0:512]
     if (add_conv(33, audio_emb, cat_dec(0), nullptr)) return 1;
+    s->ops.back().join = true;
     // block 1: ConvT(1024->512, k4, s1, p0) on a 1x1 map == 1x1 conv with 16*512 outputs laid out [4,4,512]
     View t;
     if (new_tmp(4, 4, 512, &t)) return 1;
@@ -570,19 +577,36 @@ static const char* op_name(const Op& o) {
 // events (optional): ops.size()+1 events recorded around every op (profiling pass only).
 static int run_ops(ltb_w2l_session* s, cudaEvent_t* events = nullptr) {
   size_t i = 0;
+  const bool branches = (events == nullptr);  // the profiling pass serialises everything on the main stream
+  bool forked = false;
   for (const Op& o : s->ops) {
     if (events) cudaEventRecord(events[i], s->st);
+    cudaStream_t st = s->st;
+    if (branches && o.branch == 1) {
+      if (!forked) {
+        if (cudaEventRecord(s->ev_fork, s->st) != cudaSuccess || cudaStreamWaitEvent(s->st2, s->ev_fork, 0) != cudaSuccess)
+          return LTB_FAIL("stream fork failed");
+        forked = true;
+      }
+      st = s->st2;
+    }
+    if (branches && o.join && forked) {
+      if (cudaEventRecord(s->ev_join, s->st2) != cudaSuccess || cudaStreamWaitEvent(s->st, s->ev_join, 0) != cudaSuccess)
+        return LTB_FAIL("stream join failed");
+      forked = false;
+    }
     cudaError_t e = cudaSuccess;
     switch (o.type) {
-      case 0: e = launch_conv_gather(o.cp, s->st); break;
-      case 1: e = launch_w2l_prep_faces(s->a->faces, s->a->n, s->d_index, s->B, s->img_pad, s->st); break;
-      case 2: e = launch_w2l_audio_conv0(s->mel, s->m->w0, s->m->bias[0], o.cp.out, s->B, s->st); break;
-      case 3: e = launch_w2l_head(o.cp.in, s->m->head_w, s->m->head_b, s->pred, s->B * 65536, s->st); break;
-      case 4: e = launch_conv_halo(s->halo_plans[o.halo], s->st); break;
+      case 0: e = launch_conv_gather(o.cp, st); break;
+      case 1: e = launch_w2l_prep_faces(s->a->faces, s->a->n, s->d_index, s->B, s->img_pad, st); break;
+      case 2: e = launch_w2l_audio_conv0(s->mel, s->m->w0, s->m->bias[0], o.cp.out, s->B, st); break;
+      case 3: e = launch_w2l_head(o.cp.in, s->m->head_w, s->m->head_b, s->pred, s->B * 65536, st); break;
+      case 4: e = launch_conv_halo(s->halo_plans[o.halo], st); break;
     }
     if (e != cudaSuccess) return LTB_FAIL(std::string("kernel launch failed (") + op_name(o) + "): " + cudaGetErrorString(e));
     ++i;
   }
+  if (forked) return LTB_FAIL("plan error: audio branch never joined");
   if (events) cudaEventRecord(events[i], s->st);
   return 0;
 }
@@ -726,6 +750,9 @@ int ltb_w2l_session_destroy(ltb_w2l_session* s) {
   if (s->gexec) cudaGraphExecDestroy(s->gexec);
   if (s->graph) cudaGraphDestroy(s->graph);
   for (void* p : s->allocs) cudaFree(p);
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+  if (s->ev_join) cudaEventDestroy(s->ev_join);
+  if (s->st2) cudaStreamDestroy(s->st2);
   if (s->st) cudaStreamDestroy(s->st);
   delete s;
   return 0;
@@ -749,6 +776,10 @@ int ltb_w2l_session_create(ltb_w2l_model* m, ltb_w2l_avatar* a, int batch, int s
     return 1;
   };
   if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) return bail(LTB_FAIL("stream create failed"));
+  if (cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking) != cudaSuccess) return bail(LTB_FAIL("stream create failed"));
+  if (cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess)
+    return bail(LTB_FAIL("event create failed"));
   void* p;
   if (dev_alloc(s, (size_t)batch * 262 * 264 * 8 * 2, &p, true)) return bail(1);
   s->img_pad = static_cast<__half*>(p);
