@@ -73,6 +73,9 @@ int ltb_w2l_infer(ltb_w2l_session* s, int index, const float* mel, float* pred_o
 /* replaces LipReal.paste_back_frame(pred_frame, idx), avatars/wav2lip_avatar.py:141-147, for the prediction in
  * `slot` (0..batch-1) of the last infer.  out_frame: uint8 [H,W,3] host buffer.  Synchronous. */
 int ltb_w2l_paste(ltb_w2l_session* s, int slot, int idx, uint8_t* out_frame);
+/* same entry point for a prediction held by the host: pred is the float32 [256,256,3] array inference_batch returned
+ * (the reference's exact paste_back_frame(pred_frame, idx) signature).  Synchronous. */
+int ltb_w2l_paste_pred(ltb_w2l_session* s, const float* pred, int idx, uint8_t* out_frame);
 /* all `batch` frames of the last infer at once (frame i uses mirror_index(n, index+i), utils/image.py:26-32).
  * out_frames: uint8 [batch,H,W,3] host buffer (pinned recommended) or NULL to keep them on the device. */
 int ltb_w2l_paste_batch(ltb_w2l_session* s, int index, uint8_t* out_frames);

@@ -224,6 +224,7 @@ struct ltb_w2l_session {
   double* mel_spec = nullptr;
   double* mel_mel = nullptr;
   float* pred = nullptr;
+  float* pred_scratch = nullptr;  // one host-supplied prediction (ltb_w2l_paste_pred)
   uint8_t* frames_out = nullptr;
   int* d_index = nullptr;
   std::vector<Op> ops;
@@ -794,6 +795,8 @@ int ltb_w2l_session_create(ltb_w2l_model* m, ltb_w2l_avatar* a, int batch, int s
   s->mel_mel = static_cast<double*>(p);
   if (dev_alloc(s, (size_t)batch * 65536 * 3 * 4, &p, true)) return bail(1);
   s->pred = static_cast<float*>(p);
+  if (dev_alloc(s, (size_t)65536 * 3 * 4, &p, true)) return bail(1);
+  s->pred_scratch = static_cast<float*>(p);
   if (dev_alloc(s, (size_t)batch * a->H * a->W * 3, &p, true)) return bail(1);
   s->frames_out = static_cast<uint8_t*>(p);
   if (dev_alloc(s, 256, &p, true)) return bail(1);
@@ -868,6 +871,20 @@ int ltb_w2l_paste(ltb_w2l_session* s, int slot, int idx, uint8_t* out_frame) {
   if (e != cudaSuccess) return LTB_FAIL(std::string("paste kernel: ") + cudaGetErrorString(e));
   s->launches += 1;
   LTB_CUDA(cudaMemcpyAsync(out_frame, s->frames_out + (size_t)slot * fb, fb, cudaMemcpyDeviceToHost, s->st));
+  LTB_CUDA(cudaStreamSynchronize(s->st));
+  return 0;
+}
+
+int ltb_w2l_paste_pred(ltb_w2l_session* s, const float* pred, int idx, uint8_t* out_frame) {
+  if (!s || !pred || !out_frame) return LTB_FAIL("null argument");
+  if (idx < 0 || idx >= s->a->n) return LTB_FAIL("paste: idx out of range");
+  const size_t fb = (size_t)s->a->H * s->a->W * 3;
+  LTB_CUDA(cudaMemcpyAsync(s->pred_scratch, pred, (size_t)65536 * 3 * 4, cudaMemcpyHostToDevice, s->st));
+  cudaError_t e = launch_w2l_paste(s->a->frames, s->a->coords, s->a->n, s->a->H, s->a->W, s->pred_scratch, 0, 0, idx, 1,
+                                   s->frames_out, s->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("paste kernel: ") + cudaGetErrorString(e));
+  s->launches += 1;
+  LTB_CUDA(cudaMemcpyAsync(out_frame, s->frames_out, fb, cudaMemcpyDeviceToHost, s->st));
   LTB_CUDA(cudaStreamSynchronize(s->st));
   return 0;
 }

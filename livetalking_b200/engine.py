@@ -151,6 +151,16 @@ class W2LSession:
         check(lib().ltb_w2l_paste(self._h, int(slot), int(idx), _ptr(out)))
         return out
 
+    def paste_pred(self, pred: np.ndarray, idx: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """paste_back_frame for a host-side prediction (float32 [256,256,3], as inference_batch returns)."""
+        pred = _carr(pred, np.float32)
+        if pred.shape != (256, 256, 3):
+            raise ValueError(f"pred must be (256,256,3), got {pred.shape}")
+        if out is None:
+            out = np.empty((self.avatar.H, self.avatar.W, 3), np.uint8)
+        check(lib().ltb_w2l_paste_pred(self._h, _ptr(pred), int(idx), _ptr(out)))
+        return out
+
     def paste_batch(self, index: int, out: Optional[np.ndarray] = None, to_host: bool = True) -> Optional[np.ndarray]:
         if to_host and out is None:
             out = np.empty((self.batch, self.avatar.H, self.avatar.W, 3), np.uint8)

@@ -1,0 +1,110 @@
+"""Wav2Lip avatar plugin on the B200 engine — drop-in for avatars/wav2lip_avatar.py.
+
+Module surface used by app.py:128-151 (unchanged): ``load_model(path)``, ``load_avatar(avatar_id)``,
+``warm_up(batch_size, model, modelres)`` and the class registered as ``("avatar", "wav2lip")`` constructed with
+``opt, model, avatar``.  ``LipReal`` keeps the reference class's hooks:
+
+    inference_batch(index, audiofeat_batch) -> iterable of B per-frame results      (wav2lip_avatar.py:116-139)
+    paste_back_frame(pred_frame, idx)       -> H x W x 3 uint8 BGR, fresh & writable (wav2lip_avatar.py:141-147)
+
+By default the per-frame result is an opaque ``EngineFrame`` (the reference treats it as opaque,
+base_avatar.py:374-376, 433): the whole batch is composited on the GPU right after the forward pass and copied back
+once; ``paste_back_frame`` then only hands out the finished frame.  With ``opt.ltb_return_pred = True`` the plugin
+returns the reference's exact data instead (float32 (B,256,256,3) predictions; paste on demand).
+"""
+from __future__ import annotations
+
+import glob
+import os
+import pickle
+
+import numpy as np
+
+from .. import engine
+from .mel_asr import MelASR
+
+try:
+    from avatars.base_avatar import BaseAvatar            # the reference's runtime, unchanged
+    from registry import register
+    from utils.image import mirror_index, read_imgs
+    from utils.logger import logger
+except Exception as _e:  # pragma: no cover - only when imported outside LiveTalking without stubs
+    raise ImportError("livetalking_b200.plugin.wav2lip_avatar must be imported inside LiveTalking (or with stubs for "
+                      "avatars.base_avatar / registry / utils): " + repr(_e))
+
+
+class AvatarPayload(tuple):
+    """(frame_list_cycle, face_list_cycle, coord_list_cycle) as the reference returns it, plus the resident copy."""
+    engine_avatar = None
+
+
+class EngineFrame:
+    """One composited frame of a batch, produced on the GPU; opaque to BaseAvatar."""
+    __slots__ = ("frame", "idx")
+
+    def __init__(self, frame, idx):
+        self.frame, self.idx = frame, idx
+
+
+def load_model(path):
+    """wav2lip_avatar.py:59-70 — checkpoint["state_dict"] (optional 'module.' prefixes) -> resident engine weights."""
+    import torch
+    engine.set_device(int(os.environ.get("LTB_DEVICE", "0")))
+    logger.info("Load checkpoint from: {}".format(path))
+    checkpoint = torch.load(path, map_location="cpu")
+    sd = checkpoint["state_dict"] if "state_dict" in checkpoint else checkpoint
+    return engine.W2LModel.from_state_dict({k.replace("module.", ""): v for k, v in sd.items()})
+
+
+def load_avatar(avatar_id):
+    """wav2lip_avatar.py:72-88 — same on-disk format; additionally uploads the assets once."""
+    avatar_path = f"./data/avatars/{avatar_id}"
+    with open(f"{avatar_path}/coords.pkl", "rb") as f:
+        coord_list_cycle = pickle.load(f)
+    key = lambda x: int(os.path.splitext(os.path.basename(x))[0])  # noqa: E731
+    frame_list_cycle = read_imgs(sorted(glob.glob(os.path.join(f"{avatar_path}/full_imgs", "*.[jpJP][pnPN]*[gG]")), key=key))
+    face_list_cycle = read_imgs(sorted(glob.glob(os.path.join(f"{avatar_path}/face_imgs", "*.[jpJP][pnPN]*[gG]")), key=key))
+    return make_avatar(frame_list_cycle, face_list_cycle, coord_list_cycle)
+
+
+def make_avatar(frame_list_cycle, face_list_cycle, coord_list_cycle) -> AvatarPayload:
+    payload = AvatarPayload((frame_list_cycle, face_list_cycle, coord_list_cycle))
+    payload.engine_avatar = engine.W2LAvatar(face_list_cycle, frame_list_cycle, coord_list_cycle)
+    return payload
+
+
+def warm_up(batch_size, model, modelres):
+    """wav2lip_avatar.py:90-96 — the engine warms every session when it is created; nothing to do per model."""
+    logger.info("warmup model... (engine sessions warm up at creation)")
+
+
+@register("avatar", "wav2lip")
+class LipReal(BaseAvatar):
+    def __init__(self, opt, model, avatar):
+        super().__init__(opt)
+        self.model = model
+        self.frame_list_cycle, self.face_list_cycle, self.coord_list_cycle = avatar
+        eng_avatar = getattr(avatar, "engine_avatar", None)
+        if eng_avatar is None:   # a plain tuple from somewhere else: upload now
+            eng_avatar = engine.W2LAvatar(self.face_list_cycle, self.frame_list_cycle, self.coord_list_cycle)
+        self._engine_avatar = eng_avatar
+        self.engine_session = engine.W2LSession(model, eng_avatar, self.batch_size, opt.l, opt.r, opt.fps)
+        self._return_pred = bool(getattr(opt, "ltb_return_pred", False))
+        self.asr = MelASR(opt, self, self.engine_session)
+        self.asr.warm_up()
+
+    def inference_batch(self, index, audiofeat_batch):
+        mel = np.asarray(audiofeat_batch, dtype=np.float32)                      # (B, 80, 16)
+        if self._return_pred:
+            return self.engine_session.infer(index, mel, want_pred=True)        # float32 (B,256,256,3), as the reference
+        self.engine_session.infer(index, mel, want_pred=False)
+        frames = self.engine_session.paste_batch(index)                          # (B,H,W,3) uint8, one D2H
+        length = len(self.face_list_cycle)
+        return [EngineFrame(frames[i], mirror_index(length, index + i)) for i in range(self.batch_size)]
+
+    def paste_back_frame(self, pred_frame, idx: int):
+        if isinstance(pred_frame, EngineFrame):
+            if pred_frame.idx != idx:
+                raise ValueError(f"paste_back_frame: frame was composited for idx {pred_frame.idx}, asked for {idx}")
+            return np.array(pred_frame.frame, copy=True)                          # fresh, writable, owned by Python
+        return self.engine_session.paste_pred(np.asarray(pred_frame, dtype=np.float32), idx)

@@ -1,0 +1,79 @@
+"""GPU: the plugin classes (LipReal / MelASR) driven the way BaseAvatar.inference / process_frames drive them,
+checked against the CPU oracle restatement of the reference pipeline."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.dirname(__file__))
+import stubs  # noqa: E402
+
+
+def _pipeline_oracle(sd, faces, frames, coords, pcm, B, index):
+    from oracle import mel_ref, paste_ref
+    from oracle import wav2lip_ref as R
+    mel = mel_ref.mel_step(pcm, B)
+    img = paste_ref.w2l_build_batch(faces, index, B)
+    out = R.wav2lip_forward(sd, torch.from_numpy(mel.astype(np.float32)).reshape(B, 1, 80, 16), torch.from_numpy(img))
+    pred = out.numpy().transpose(0, 2, 3, 1) * 255.0
+    res = []
+    for i in range(B):
+        idx = paste_ref.mirror_index(len(faces), index + i)
+        res.append(paste_ref.w2l_paste_back(pred[i], frames[idx], coords[idx]))
+    return mel, pred, res
+
+
+@pytest.mark.parametrize("return_pred", [False, True])
+def test_lipreal_session_loop(w2l_state_dict, return_pred):
+    stubs.install()
+    from livetalking_b200 import engine
+    from livetalking_b200.plugin import wav2lip_avatar as W
+    from oracle import wav2lip_ref as R
+    import registry
+    engine.set_device(0)
+    B = 4
+    rng = np.random.default_rng(3)
+    _, img = R.synth_inputs(3, seed=21)
+    faces = list((img[:, 3:6].permute(0, 2, 3, 1).numpy() * 255.0).round().astype(np.uint8))
+    frames = list(rng.integers(0, 256, (3, 240, 320, 3), dtype=np.uint8))
+    coords = [(10, 170, 40, 210), (20, 148, 60, 188), (0, 240, 0, 320)]
+    model = engine.W2LModel.from_state_dict(w2l_state_dict)
+    avatar = W.make_avatar(frames, faces, coords)
+    opt = stubs.Opt(batch_size=B, ltb_return_pred=return_pred)
+    av = registry.create("avatar", "wav2lip", opt=opt, model=model, avatar=avatar)      # app.py:99
+    assert av.get_avatar_length() == 3 and av.asr.feat_queue.maxsize == 2
+    # TTS side: 20 ms chunks of speech (tone + noise, benchmark_asr.py recipe)
+    n_chunks = 2 * B
+    t = np.arange((20 + n_chunks) * 320) / 16000.0
+    audio = (0.3 * np.sin(2 * np.pi * 300 * t) + 0.05 * rng.standard_normal(t.size)).astype(np.float32)
+    # the session warmed up on silence (20 zero chunks); now speech arrives
+    for c in range(n_chunks):
+        av.asr.put_audio_frame(audio[c * 320:(c + 1) * 320], {"c": c})
+    av.asr.run_step()                                                                   # render thread
+    feats = av.asr.feat_queue.get(timeout=1)                                            # inference thread
+    chunks = [av.asr.output_queue.get() for _ in range(10 + 2 * B)][10:]
+    assert all(f.type == 0 for f in chunks)
+    index = 5
+    pred = av.inference_batch(index, feats)
+    outs = [av.paste_back_frame(p, W.mirror_index(3, index + i)) for i, p in enumerate(pred)]   # process_frames thread
+    pcm = np.concatenate([np.zeros(20 * 320, np.float32), audio[:n_chunks * 320]])
+    mel_o, pred_o, res_o = _pipeline_oracle(w2l_state_dict, faces, frames, coords, pcm, B, index)
+    np.testing.assert_allclose(np.stack(feats), mel_o, atol=1e-5)
+    for i in range(B):
+        assert outs[i].dtype == np.uint8 and outs[i].shape == (240, 320, 3) and outs[i].flags.writeable and outs[i].flags.c_contiguous
+        assert R.psnr_u8(outs[i], res_o[i]) >= 40.0, i
+        y1, y2, x1, x2 = coords[W.mirror_index(3, index + i)]
+        mask = np.ones((240, 320), bool)
+        mask[y1:y2, x1:x2] = False
+        assert np.array_equal(outs[i][mask], frames[W.mirror_index(3, index + i)][mask])   # outside the bbox: untouched copy
+    if return_pred:
+        assert isinstance(pred, np.ndarray) and pred.shape == (B, 256, 256, 3) and pred.dtype == np.float32
+        assert R.psnr_u8(pred.astype(np.uint8), pred_o.astype(np.uint8)) >= 40.0
+    else:
+        with pytest.raises(ValueError):
+            av.paste_back_frame(pred[0], (pred[0].idx + 1) % 3)
+    outs[0][:] = 0                                                                       # caller may scribble (cv2.putText)
+    av.engine_session.close()

@@ -1,0 +1,97 @@
+"""CPU: host-side logic of the plugin layer (queues, silence synthesis, warm-up, run_step bookkeeping), and — when the
+reference tree is present (build container) — equivalence with the reference's own BaseASR on the same event sequence."""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(__file__))
+import stubs  # noqa: E402
+
+stubs.install()
+from livetalking_b200.plugin import base_asr as B  # noqa: E402
+
+
+def _feed(asr, n, rng):
+    chunks = [rng.standard_normal(320).astype(np.float32) for _ in range(n)]
+    for i, c in enumerate(chunks):
+        asr.put_audio_frame(c, {"i": i})
+    return chunks
+
+
+def test_silence_synthesis_and_warm_up():
+    opt = stubs.Opt(batch_size=2)
+    a = B.BaseASR(opt)
+    assert a.chunk == 320 and a.feat_queue.maxsize == 2
+    f = a.get_audio_frame()                             # empty queue -> zeros, type 1 (base_asr.py:66-69)
+    assert f.type == 1 and f.data.shape == (320,) and f.data.dtype == np.float32 and not f.data.any()
+    rng = np.random.default_rng(0)
+    chunks = _feed(a, 25, rng)
+    a.warm_up()                                         # l + r = 20 chunks consumed, first l = 10 dropped from output
+    assert len(a.frames) == 20 and a.output_queue.qsize() == 10
+    out = a.get_audio_out()
+    assert out.type == 0 and np.array_equal(out.data, chunks[10]) and out.userdata == {"i": 10}
+    a.flush_talk()
+    assert a.queue.qsize() == 0
+
+
+def test_custom_audio_stream_has_priority():
+    class Parent:
+        custom_audiotype = 2
+
+        def get_custom_audio_stream(self, t):
+            return np.full(320, 0.25, np.float32)
+
+    a = B.BaseASR(stubs.Opt(), Parent())
+    a.put_audio_frame(np.ones(320, np.float32), {})
+    f = a.get_audio_frame()
+    assert f.type == 2 and float(f.data[0]) == 0.25      # base_asr.py:59-62
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/avatars/audio_features/base_asr.py"), reason="reference tree not present")
+def test_same_behaviour_as_reference_base_asr():
+    spec = importlib.util.spec_from_file_location("ref_base_asr", "/root/reference/avatars/audio_features/base_asr.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)                         # imports the stubbed avatars.base_avatar
+    opt = stubs.Opt(batch_size=3)
+    ours, theirs = B.BaseASR(opt), ref.BaseASR(opt)
+    rng1, rng2 = np.random.default_rng(5), np.random.default_rng(5)
+    _feed(ours, 23, rng1)
+    _feed(theirs, 23, rng2)
+    ours.warm_up()
+    theirs.warm_up()
+    for _ in range(8):                                   # drains speech then synthesises silence
+        a, b = ours.get_audio_frame(), theirs.get_audio_frame()
+        assert a.type == b.type and np.array_equal(a.data, b.data) and a.userdata == b.userdata
+    assert ours.output_queue.qsize() == theirs.output_queue.qsize()
+    assert len(ours.frames) == len(theirs.frames) and all(np.array_equal(x, y) for x, y in zip(ours.frames, theirs.frames))
+
+
+def test_mel_asr_run_step_bookkeeping_with_fake_session():
+    """run_step: 2B chunks forwarded, one feature list queued, l+r chunks of context kept (mel.py:36-67, Appendix E)."""
+    from livetalking_b200.plugin.mel_asr import MelASR
+
+    class FakeSession:
+        def __init__(self):
+            self.calls = []
+
+        def mel_step(self, pcm):
+            self.calls.append(pcm.copy())
+            return np.zeros((2, 80, 16), np.float32)
+
+    opt = stubs.Opt(batch_size=2)
+    sess = FakeSession()
+    asr = MelASR(opt, None, sess)
+    rng = np.random.default_rng(1)
+    chunks = _feed(asr, 24, rng)
+    asr.warm_up()
+    asr.run_step()
+    assert asr.feat_queue.qsize() == 1 and asr.output_queue.qsize() == 10 + 4
+    feats = asr.feat_queue.get()
+    assert len(feats) == 2 and feats[0].shape == (80, 16)
+    assert sess.calls[0].size == (10 + 10 + 4) * 320 and np.array_equal(sess.calls[0], np.concatenate(chunks[:24]))
+    assert len(asr.frames) == 20 and np.array_equal(asr.frames[0], chunks[4])
+    with pytest.raises(RuntimeError):
+        MelASR(opt, None, None)                          # no engine session -> loud failure, never a CPU fallback
