@@ -116,6 +116,72 @@ typedef struct ltb_conv_desc {
 int ltb_conv2d_f16(const ltb_conv_desc* d, const void* in_f16, const float* w_f32, const float* bias_f32,
                    const void* res_f16, void* out_f16);
 
+/* ==== generic device-op layer (MuseTalk path) ==========================================================================
+ * The MuseTalk networks are third-party graphs the reference only wraps: diffusers.UNet2DConditionModel
+ * (avatars/musetalk/models/unet.py:29-48), diffusers.AutoencoderKL (avatars/musetalk/models/vae.py:10-38) and
+ * transformers.WhisperModel (avatars/musetalk/whisper/audio2feature.py:15-23).  Host code (Python) assembles them
+ * from the operators below, captures the sequence once into a CUDA graph and replays it per step.  All ops are
+ * asynchronous on the context stream; pointers are device pointers obtained from ltb_dev_alloc. */
+typedef struct ltb_ctx ltb_ctx;
+typedef struct ltb_graph ltb_graph;
+int ltb_ctx_create(ltb_ctx** out);
+int ltb_ctx_destroy(ltb_ctx* c);
+int ltb_ctx_stream(ltb_ctx* c, void** cuda_stream);
+int ltb_ctx_sync(ltb_ctx* c);
+int ltb_ctx_launch_count(ltb_ctx* c, long long* n);
+int ltb_dev_alloc(ltb_ctx* c, size_t bytes, int zero, void** dptr);
+int ltb_dev_free(ltb_ctx* c, void* dptr);
+int ltb_h2d(ltb_ctx* c, void* dst_dev, const void* src_host, size_t bytes, int sync);
+int ltb_d2h(ltb_ctx* c, void* dst_host, const void* src_dev, size_t bytes, int sync);
+int ltb_set_i32(ltb_ctx* c, void* dptr, int value); /* stream-ordered scalar (per-step avatar index read by graph kernels) */
+int ltb_capture_begin(ltb_ctx* c);
+int ltb_capture_end(ltb_ctx* c, ltb_graph** out);
+int ltb_graph_launch(ltb_ctx* c, ltb_graph* g);
+int ltb_graph_destroy(ltb_graph* g);
+
+/* conv / linear / batched GEMM on the tcgen05 kernels (nn.Conv2d, nn.Linear, attention Q.K^T and P.V):
+ * out[pix, co] = act(sum_{tap,ci} in[pix*s + tap - pad, ic_off+ci] * w[co, w_koff + tap*Cin + ci] + bias[co] (+ res[pix, co]))
+ * w: fp16 [Cout][Ktot] (K-major rows); w_tap: optional tap-major copy [9][Cout][Cin] enabling the TMA halo kernel for
+ * 3x3 s1 p1; bias may be NULL (zero).  zbatch > 1 runs zbatch independent GEMMs (z = zo*zdiv + zi) with element
+ * offsets in_z*, w_z*, out_z* added to the base pointers. */
+typedef struct ltb_conv_op {
+  const void* in; const void* w; const void* w_tap; const float* bias; const void* res; void* out;
+  int N, IH, IW, ICtot, ic_off, Cin;
+  int OH, OW, Cout, OCtot, oc_off, RCtot, rc_off;
+  int KH, KW, sy, sx, pad_t, pad_l;
+  int Ktot, w_koff, relu, no_halo;
+  int zbatch, zdiv;
+  long long in_zo, in_zi, w_zo, w_zi, out_zo, out_zi;
+} ltb_conv_op;
+int ltb_op_conv2d(ltb_ctx* c, const ltb_conv_op* d);
+int ltb_op_w_tap_major(ltb_ctx* c, const void* w, void* wt, int cout, int cin);
+/* torch.nn.GroupNorm (+ optional SiLU) on an NHWC channel slice; fp32 statistics */
+int ltb_op_groupnorm(ltb_ctx* c, const void* x, int N, int HW, int C, int Ctot, int c_off, int groups, float eps, const float* gamma,
+                     const float* beta, int silu, void* out, int OCtot, int oc_off);
+/* torch.nn.LayerNorm over the last dim of [rows, C] */
+int ltb_op_layernorm(ltb_ctx* c, const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out);
+/* softmax(scale * x[:, :valid]) per row of a [rows, ld] matrix; columns [valid, cols) are written as 0 */
+int ltb_op_softmax(ltb_ctx* c, const void* x, int rows, int cols, int ld, int valid, float scale, void* out);
+/* diffusers GEGLU: out[rows,H] = h[:, :H] * gelu(h[:, H:]) */
+int ltb_op_geglu(ltb_ctx* c, const void* h, long long rows, int H, void* out);
+/* out = act(x + y[i % period]) ; y may be NULL ; act: 0 none, 1 GELU(erf), 2 SiLU */
+int ltb_op_eltwise(ltb_ctx* c, const void* x, const void* y, long long n, long long period, int act, void* out);
+int ltb_op_upsample2x(ltb_ctx* c, const void* x, int N, int H, int W, int C, void* out);
+int ltb_op_copy_channels(ltb_ctx* c, const void* src, long long rows, int C, int SCtot, int sc_off, void* dst, int DCtot, int dc_off);
+int ltb_op_transpose_heads(ltb_ctx* c, const void* v, int B, int n_keys, int Ctot, int c_off, int heads, int d, int n_pad, void* vt);
+/* VAE.decode_latents post-processing, avatars/musetalk/models/vae.py:104-107 -> uint8 BGR NHWC */
+int ltb_op_vae_post(ltb_ctx* c, const void* x, long long npix, int Ctot, void* out_u8);
+/* VAE.preprocess_img, avatars/musetalk/models/vae.py:51-82 (uint8 BGR -> fp16 RGB [-1,1], 8-channel padded NHWC) */
+int ltb_op_vae_pre(ltb_ctx* c, const void* img_u8, int N, int H, int W, int half_mask, void* out);
+/* out[i] = table[mirror_index(n, *d_index + i)], i < B  (latent gather of MuseReal.inference_batch, musetalk_avatar.py:134-139) */
+int ltb_op_gather_rows(ltb_ctx* c, const void* table, int n, const void* d_index, int B, long long row_elems, void* out);
+/* MuseReal.paste_back_frame + get_image_blending (avatars/musetalk_avatar.py:154-164, avatars/musetalk/myutil.py:4-25) */
+typedef struct ltb_mt_paste_op {
+  const void* frames; const void* coords; const void* crop; const void* masks; const void* mask_off; const void* pred; void* out;
+  int nf, H, W, index, explicit_idx, slot0, count;
+} ltb_mt_paste_op;
+int ltb_op_mt_paste(ltb_ctx* c, const ltb_mt_paste_op* d);
+
 /* hardware probe (test hook): D[128x64] = A * B^T with A = 16 groups of 8 consecutive 128-byte rows of a swizzled
  * shared-memory buffer, first group at row `start_row`, groups `sbo_rows` rows apart, descriptor base_offset as given. */
 int ltb_umma_probe(const void* halo_f16, int halo_rows, const void* b_f16, int start_row, int sbo_rows, int base_offset,

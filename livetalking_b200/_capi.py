@@ -17,6 +17,19 @@ class LtbError(RuntimeError):
     pass
 
 
+class ConvOp(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n in ("in_", "w", "w_tap", "bias", "res", "out")] +
+                [(n, C.c_int) for n in ("N", "IH", "IW", "ICtot", "ic_off", "Cin", "OH", "OW", "Cout", "OCtot", "oc_off", "RCtot",
+                                        "rc_off", "KH", "KW", "sy", "sx", "pad_t", "pad_l", "Ktot", "w_koff", "relu", "no_halo",
+                                        "zbatch", "zdiv")] +
+                [(n, C.c_longlong) for n in ("in_zo", "in_zi", "w_zo", "w_zi", "out_zo", "out_zi")])
+
+
+class MtPasteOp(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n in ("frames", "coords", "crop", "masks", "mask_off", "pred", "out")] +
+                [(n, C.c_int) for n in ("nf", "H", "W", "index", "explicit_idx", "slot0", "count")])
+
+
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in
                 ("N", "IH", "IW", "Cin", "Cout", "KH", "KW", "sy", "sx", "pad", "transposed", "relu", "has_res",
@@ -53,6 +66,36 @@ _SIGS = {
     "ltb_w2l_num_layers": (C.c_int, []),
     "ltb_w2l_layer_shape": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ltb_w2l_layer_read": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "ltb_ctx_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "ltb_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "ltb_ctx_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ltb_ctx_sync": (C.c_int, [C.c_void_p]),
+    "ltb_ctx_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong)]),
+    "ltb_dev_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+    "ltb_dev_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ltb_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "ltb_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "ltb_set_i32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "ltb_capture_begin": (C.c_int, [C.c_void_p]),
+    "ltb_capture_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ltb_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ltb_graph_destroy": (C.c_int, [C.c_void_p]),
+    "ltb_op_conv2d": (C.c_int, [C.c_void_p, C.POINTER(ConvOp)]),
+    "ltb_op_w_tap_major": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "ltb_op_groupnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                   C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
+    "ltb_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ltb_op_softmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "ltb_op_geglu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "ltb_op_eltwise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p]),
+    "ltb_op_upsample2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ltb_op_copy_channels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]),
+    "ltb_op_transpose_heads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p]),
+    "ltb_op_vae_post": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "ltb_op_vae_pre": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ltb_op_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
+    "ltb_op_mt_paste": (C.c_int, [C.c_void_p, C.POINTER(MtPasteOp)]),
     "ltb_umma_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ltb_conv2d_f16": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

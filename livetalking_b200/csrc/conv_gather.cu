@@ -54,7 +54,18 @@ __global__ void __launch_bounds__(160) conv_gather_umma_kernel(const __grid_cons
   const int lane = tid & 31;
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
-  const ConvPhase& ph = p.ph[blockIdx.z];
+  const int zphase = (p.zbatch > 1) ? (int)(blockIdx.z % p.nphases) : (int)blockIdx.z;
+  const ConvPhase& ph = p.ph[zphase];
+  const __half* in_base = p.in;
+  const __half* w_base = p.w;
+  __half* out_base = p.out;
+  if (p.zbatch > 1) {
+    const int zb = blockIdx.z / p.nphases;
+    const int zo = zb / p.zdiv, zi = zb - zo * p.zdiv;
+    in_base += zo * p.in_zo + zi * p.in_zi;
+    w_base += zo * p.w_zo + zi * p.w_zi;
+    out_base += zo * p.out_zo + zi * p.out_zi;
+  }
   const int m0 = blockIdx.x * 128;
   const int n0 = blockIdx.y * BN;
   const int cpt = p.Cin / KB;  // K chunks per tap
@@ -113,7 +124,7 @@ __global__ void __launch_bounds__(160) conv_gather_umma_kernel(const __grid_cons
         const int iy = riy[i] + dy, ix = rix[i] + dx;
         const bool inb = ((unsigned)iy < (unsigned)p.IH) && ((unsigned)ix < (unsigned)p.IW);
         const size_t off = ((size_t)(rb[i] * p.IH + iy) * p.IW + ix) * p.ICtot + p.ic_off + cc * KB + j * 8;
-        const __half* src = inb ? (p.in + off) : p.in;
+        const __half* src = inb ? (in_base + off) : in_base;
         cp_async16(a_base + row * C::ROWB + swz_chunk<KB>(row, j) * 16, src, inb ? 16u : 0u);
       }
       const size_t wk = (size_t)ph.koff + (size_t)tap * p.Cin + cc * KB + j * 8;
@@ -121,7 +132,7 @@ __global__ void __launch_bounds__(160) conv_gather_umma_kernel(const __grid_cons
       for (int i = 0; i < C::CH; ++i) {
         const int n = r0 + i * C::RSTEP;
         if (n < BN) {
-          cp_async16(b_base + n * C::ROWB + swz_chunk<KB>(n, j) * 16, p.w + (size_t)(n0 + n) * p.Ktot + wk, 16u);
+          cp_async16(b_base + n * C::ROWB + swz_chunk<KB>(n, j) * 16, w_base + (size_t)(n0 + n) * p.Ktot + wk, 16u);
         }
       }
       cp_async_commit();
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__(160) conv_gather_umma_kernel(const __grid_cons
       const int gx = rem - gy * p.GW;
       opix = (size_t)(b * p.OH + gy * p.osy + ph.ooy) * p.OW + gx * p.osx + ph.oox;
     }
-    __half* optr = p.out + opix * p.OCtot + p.oc_off + n0;
+    __half* optr = out_base + opix * p.OCtot + p.oc_off + n0;
     const __half* rptr = p.res ? (p.res + opix * p.RCtot + p.rc_off + n0) : nullptr;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     constexpr int CW = (BN >= 32) ? 32 : 16;
@@ -247,7 +258,7 @@ static cudaError_t launch_one(const ConvParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid((p.M + 127) / 128, p.Cout / BN, p.nphases);
+  dim3 grid((p.M + 127) / 128, p.Cout / BN, p.nphases * (p.zbatch > 1 ? p.zbatch : 1));
   conv_gather_umma_kernel<BN, KB><<<grid, 160, C::SMEM_BYTES, st>>>(p);
   return cudaGetLastError();
 }
@@ -273,7 +284,8 @@ int conv_gather_pick_bn(const ConvParams& p) {
   if (!bn) return 0;
   // small-M layers are weight-bandwidth bound: prefer more, narrower CTAs until the grid fills the 148 SMs
   const long mt = (p.M + 127) / 128;
-  while (bn > 32 && mt * (p.Cout / bn) * p.nphases < 148) bn >>= 1;
+  const long zb = p.zbatch > 1 ? p.zbatch : 1;
+  while (bn > 32 && mt * (p.Cout / bn) * p.nphases * zb < 148) bn >>= 1;
   return bn;
 }
 

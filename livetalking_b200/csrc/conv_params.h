@@ -43,6 +43,10 @@ struct ConvParams {
   int M;  // N*GH*GW rows per phase
   int nphases;
   ConvPhase ph[kMaxPhases];
+  // optional batching over grid.z (attention: one GEMM per (batch, head)): z = zo * zdiv + zi, element offsets added to
+  // the in / w / out (/ res) base pointers.  zbatch <= 1 disables.
+  int zbatch, zdiv;
+  long long in_zo, in_zi, w_zo, w_zi, out_zo, out_zi;
 };
 
 }  // namespace ltb

@@ -1,0 +1,40 @@
+// Launchers of the bandwidth-bound operators (ops.cu) and the MuseTalk blend composite (mt_paste.cu).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace ltb {
+
+cudaError_t launch_groupnorm(const __half* x, int N, int HW, int C, int Ctot, int c_off, int groups, float eps, const float* gamma,
+                             const float* beta, int silu, __half* out, int OCtot, int oc_off, float* stats_ws, cudaStream_t st);
+cudaError_t launch_layernorm(const __half* x, int rows, int C, float eps, const float* gamma, const float* beta, __half* out,
+                             cudaStream_t st);
+cudaError_t launch_softmax(const __half* x, int rows, int cols, int ld, int valid, float scale, __half* out, cudaStream_t st);
+cudaError_t launch_geglu(const __half* h, size_t rows, int H, __half* out, cudaStream_t st);
+cudaError_t launch_eltwise(const __half* x, const __half* y, size_t n, size_t period, int act, __half* out, cudaStream_t st);
+cudaError_t launch_upsample2x(const __half* x, int N, int H, int W, int C, __half* out, cudaStream_t st);
+cudaError_t launch_copy_channels(const __half* src, size_t rows, int C, int SCtot, int sc_off, __half* dst, int DCtot, int dc_off,
+                                 cudaStream_t st);
+cudaError_t launch_transpose_heads(const __half* v, int B, int n_keys, int Ctot, int c_off, int heads, int d, int n_pad, __half* vt,
+                                   cudaStream_t st);
+cudaError_t launch_vae_post(const __half* x, size_t npix, int Ctot, uint8_t* out, cudaStream_t st);
+cudaError_t launch_vae_pre(const uint8_t* img, int N, int H, int W, int half_mask, __half* out, cudaStream_t st);
+cudaError_t launch_gather_rows(const __half* table, int n, const int* d_index, int B, size_t row_elems, __half* out, cudaStream_t st);
+
+// MuseTalk paste-back (mt_paste.cu): resize + insert + blendLinear, `count` frames per launch
+struct MtPasteArgs {
+  const uint8_t* frames;     // [nf,H,W,3]
+  const int* coords;         // [nf,4] = (x1,y1,x2,y2)           (musetalk_avatar.py:157)
+  const int* crop;           // [nf,4] = (x_s,y_s,x_e,y_e)       (myutil.py:7)
+  const uint8_t* masks;      // concatenated 3-channel masks, frame i at mask_off[i], size (y_e-y_s) x (x_e-x_s) x 3
+  const long long* mask_off;
+  const uint8_t* pred;       // [B,256,256,3] u8 BGR (VAE decode output)
+  uint8_t* out;              // [count,H,W,3]
+  int nf, H, W;
+  int index, explicit_idx, slot0;
+};
+cudaError_t launch_mt_paste(const MtPasteArgs& a, int count, cudaStream_t st);
+
+}  // namespace ltb

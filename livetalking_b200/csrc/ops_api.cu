@@ -1,0 +1,334 @@
+// Generic device-op layer of the C ABI (include/ltb200.h, "ltb_ctx / ltb_op_*"): the MuseTalk networks (diffusers
+// UNet2DConditionModel / AutoencoderKL and the Whisper encoder — third-party graphs the reference only wraps,
+// avatars/musetalk/models/{unet,vae}.py, avatars/musetalk/whisper/audio2feature.py) are assembled by the Python host
+// code out of these operators, captured ONCE into a CUDA graph and replayed per step.  Every op is asynchronous on the
+// context's stream; device memory is owned by the context.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ltb200.h"
+#include "conv_halo.h"
+#include "ltb_internal.h"
+#include "ops.h"
+
+using namespace ltb;
+
+struct ltb_ctx {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  std::vector<void*> allocs;
+  float* zero_bias = nullptr;   // 16384 zeros (bias of bias-free GEMMs)
+  float* gn_ws = nullptr;       // GroupNorm statistics workspace
+  long long launches = 0;
+  bool capturing = false;
+  long long capture_launches = 0;
+};
+struct ltb_graph {
+  cudaGraph_t g = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  long long launches = 0;
+};
+
+static const int kZeroBias = 16384;
+static const int kGnWsFloats = 64 * 64 * 2;
+
+extern "C" {
+
+int ltb_ctx_create(ltb_ctx** out) {
+  if (!out) return LTB_FAIL("null argument");
+  auto* c = new ltb_ctx();
+  cudaError_t e = cudaGetDevice(&c->device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->zero_bias), kZeroBias * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(c->zero_bias, 0, kZeroBias * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->gn_ws), kGnWsFloats * sizeof(float));
+  if (e != cudaSuccess) {
+    delete c;
+    return LTB_FAIL(std::string("ctx create: ") + cudaGetErrorString(e));
+  }
+  *out = c;
+  return 0;
+}
+
+int ltb_ctx_destroy(ltb_ctx* c) {
+  if (!c) return 0;
+  cudaStreamSynchronize(c->st);
+  for (void* p : c->allocs) cudaFree(p);
+  cudaFree(c->zero_bias);
+  cudaFree(c->gn_ws);
+  cudaStreamDestroy(c->st);
+  delete c;
+  return 0;
+}
+
+int ltb_ctx_stream(ltb_ctx* c, void** stream) {
+  if (!c || !stream) return LTB_FAIL("null argument");
+  *stream = static_cast<void*>(c->st);
+  return 0;
+}
+int ltb_ctx_sync(ltb_ctx* c) {
+  if (!c) return LTB_FAIL("null ctx");
+  LTB_CUDA(cudaStreamSynchronize(c->st));
+  return 0;
+}
+int ltb_ctx_launch_count(ltb_ctx* c, long long* n) {
+  if (!c || !n) return LTB_FAIL("null argument");
+  *n = c->launches;
+  return 0;
+}
+
+int ltb_dev_alloc(ltb_ctx* c, size_t bytes, int zero, void** dptr) {
+  if (!c || !dptr) return LTB_FAIL("null argument");
+  void* p = nullptr;
+  LTB_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
+  if (zero) LTB_CUDA(cudaMemset(p, 0, bytes ? bytes : 16));
+  c->allocs.push_back(p);
+  *dptr = p;
+  return 0;
+}
+int ltb_dev_free(ltb_ctx* c, void* dptr) {
+  if (!c || !dptr) return 0;
+  for (size_t i = 0; i < c->allocs.size(); ++i)
+    if (c->allocs[i] == dptr) {
+      cudaFree(dptr);
+      c->allocs.erase(c->allocs.begin() + i);
+      return 0;
+    }
+  return LTB_FAIL("dev_free: pointer not owned by this context");
+}
+int ltb_h2d(ltb_ctx* c, void* dst_dev, const void* src_host, size_t bytes, int sync) {
+  if (!c) return LTB_FAIL("null ctx");
+  LTB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, c->st));
+  if (sync) LTB_CUDA(cudaStreamSynchronize(c->st));
+  return 0;
+}
+int ltb_d2h(ltb_ctx* c, void* dst_host, const void* src_dev, size_t bytes, int sync) {
+  if (!c) return LTB_FAIL("null ctx");
+  LTB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, c->st));
+  if (sync) LTB_CUDA(cudaStreamSynchronize(c->st));
+  return 0;
+}
+int ltb_set_i32(ltb_ctx* c, void* dptr, int value) {
+  if (!c || !dptr) return LTB_FAIL("null argument");
+  LTB_CUDA(launch_set_int(static_cast<int*>(dptr), value, c->st));
+  c->launches += 1;
+  return 0;
+}
+
+// ---- graph capture ------------------------------------------------------------------------------
+int ltb_capture_begin(ltb_ctx* c) {
+  if (!c) return LTB_FAIL("null ctx");
+  if (c->capturing) return LTB_FAIL("already capturing");
+  LTB_CUDA(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
+  c->capturing = true;
+  c->capture_launches = c->launches;
+  return 0;
+}
+int ltb_capture_end(ltb_ctx* c, ltb_graph** out) {
+  if (!c || !out) return LTB_FAIL("null argument");
+  if (!c->capturing) return LTB_FAIL("not capturing");
+  c->capturing = false;
+  auto* g = new ltb_graph();
+  cudaError_t e = cudaStreamEndCapture(c->st, &g->g);
+  if (e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, g->g, 0);
+  if (e != cudaSuccess) {
+    if (g->g) cudaGraphDestroy(g->g);
+    delete g;
+    return LTB_FAIL(std::string("graph capture/instantiate: ") + cudaGetErrorString(e));
+  }
+  g->launches = c->launches - c->capture_launches;
+  c->launches = c->capture_launches;  // captured launches did not execute
+  *out = g;
+  return 0;
+}
+int ltb_graph_launch(ltb_ctx* c, ltb_graph* g) {
+  if (!c || !g) return LTB_FAIL("null argument");
+  LTB_CUDA(cudaGraphLaunch(g->exec, c->st));
+  c->launches += g->launches;
+  return 0;
+}
+int ltb_graph_destroy(ltb_graph* g) {
+  if (!g) return 0;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->g) cudaGraphDestroy(g->g);
+  delete g;
+  return 0;
+}
+
+// ---- ops ----------------------------------------------------------------------------------------
+int ltb_op_conv2d(ltb_ctx* c, const ltb_conv_op* d) {
+  if (!c || !d || !d->in || !d->w || !d->out) return LTB_FAIL("conv2d: null argument");
+  if (d->KH * d->KW > kMaxTaps) return LTB_FAIL("conv2d: kernel too large");
+  if (d->Cout > kZeroBias && !d->bias) return LTB_FAIL("conv2d: Cout too large for the implicit zero bias");
+  ConvParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.in = static_cast<const __half*>(d->in);
+  p.N = d->N;
+  p.IH = d->IH;
+  p.IW = d->IW;
+  p.ICtot = d->ICtot;
+  p.ic_off = d->ic_off;
+  p.Cin = d->Cin;
+  p.sy = d->sy;
+  p.sx = d->sx;
+  p.GH = d->OH;
+  p.GW = d->OW;
+  p.out = static_cast<__half*>(d->out);
+  p.OH = d->OH;
+  p.OW = d->OW;
+  p.OCtot = d->OCtot;
+  p.oc_off = d->oc_off;
+  p.osy = p.osx = 1;
+  p.Cout = d->Cout;
+  p.res = static_cast<const __half*>(d->res);
+  p.RCtot = d->RCtot;
+  p.rc_off = d->rc_off;
+  p.w = static_cast<const __half*>(d->w);
+  p.Ktot = d->Ktot;
+  p.bias = d->bias ? d->bias : c->zero_bias;
+  p.relu = d->relu;
+  p.M = d->N * d->OH * d->OW;
+  p.nphases = 1;
+  p.ph[0].ntaps = d->KH * d->KW;
+  p.ph[0].koff = d->w_koff;
+  for (int kh = 0; kh < d->KH; ++kh)
+    for (int kw = 0; kw < d->KW; ++kw) {
+      p.ph[0].dy[kh * d->KW + kw] = (signed char)(kh - d->pad_t);
+      p.ph[0].dx[kh * d->KW + kw] = (signed char)(kw - d->pad_l);
+    }
+  p.zbatch = d->zbatch;
+  p.zdiv = d->zdiv > 0 ? d->zdiv : 1;
+  p.in_zo = d->in_zo;
+  p.in_zi = d->in_zi;
+  p.w_zo = d->w_zo;
+  p.w_zi = d->w_zi;
+  p.out_zo = d->out_zo;
+  p.out_zi = d->out_zi;
+  cudaError_t e;
+  if (d->w_tap && d->zbatch <= 1 && d->w_koff == 0 && !d->no_halo && conv_halo_supported(p)) {
+    HaloPlan pl;
+    if (conv_halo_make_plan(p, static_cast<const __half*>(d->w_tap), &pl) != 0) return LTB_FAIL("conv2d: tensor map creation failed");
+    e = launch_conv_halo(pl, c->st);
+  } else {
+    e = launch_conv_gather(p, c->st);
+  }
+  if (e != cudaSuccess) return LTB_FAIL(std::string("conv2d launch: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
+
+int ltb_op_w_tap_major(ltb_ctx* c, const void* w, void* wt, int cout, int cin) {
+  if (!c || !w || !wt) return LTB_FAIL("null argument");
+  LTB_CUDA(launch_w_tap_major(static_cast<const __half*>(w), static_cast<__half*>(wt), cout, cin, c->st));
+  c->launches += 1;
+  return 0;
+}
+
+int ltb_op_groupnorm(ltb_ctx* c, const void* x, int N, int HW, int C, int Ctot, int c_off, int groups, float eps, const float* gamma,
+                     const float* beta, int silu, void* out, int OCtot, int oc_off) {
+  if (!c || !x || !out || !gamma || !beta) return LTB_FAIL("groupnorm: null argument");
+  if ((size_t)N * groups * 2 > (size_t)kGnWsFloats) return LTB_FAIL("groupnorm: batch too large for the statistics workspace");
+  cudaError_t e = launch_groupnorm(static_cast<const __half*>(x), N, HW, C, Ctot, c_off, groups, eps, gamma, beta, silu,
+                                   static_cast<__half*>(out), OCtot, oc_off, c->gn_ws, c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("groupnorm: ") + cudaGetErrorString(e));
+  c->launches += 2;
+  return 0;
+}
+int ltb_op_layernorm(ltb_ctx* c, const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out) {
+  if (!c || !x || !out) return LTB_FAIL("layernorm: null argument");
+  cudaError_t e = launch_layernorm(static_cast<const __half*>(x), rows, C, eps, gamma, beta, static_cast<__half*>(out), c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("layernorm: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
+int ltb_op_softmax(ltb_ctx* c, const void* x, int rows, int cols, int ld, int valid, float scale, void* out) {
+  if (!c || !x || !out) return LTB_FAIL("softmax: null argument");
+  cudaError_t e = launch_softmax(static_cast<const __half*>(x), rows, cols, ld, valid, scale, static_cast<__half*>(out), c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("softmax: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
+int ltb_op_geglu(ltb_ctx* c, const void* h, long long rows, int H, void* out) {
+  if (!c || !h || !out) return LTB_FAIL("geglu: null argument");
+  cudaError_t e = launch_geglu(static_cast<const __half*>(h), (size_t)rows, H, static_cast<__half*>(out), c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("geglu: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
+int ltb_op_eltwise(ltb_ctx* c, const void* x, const void* y, long long n, long long period, int act, void* out) {
+  if (!c || !x || !out) return LTB_FAIL("eltwise: null argument");
+  cudaError_t e = launch_eltwise(static_cast<const __half*>(x), static_cast<const __half*>(y), (size_t)n, (size_t)period, act,
+                                 static_cast<__half*>(out), c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("eltwise: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
+int ltb_op_upsample2x(ltb_ctx* c, const void* x, int N, int H, int W, int C, void* out) {
+  if (!c || !x || !out) return LTB_FAIL("upsample2x: null argument");
+  cudaError_t e = launch_upsample2x(static_cast<const __half*>(x), N, H, W, C, static_cast<__half*>(out), c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("upsample2x: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
+int ltb_op_copy_channels(ltb_ctx* c, const void* src, long long rows, int C, int SCtot, int sc_off, void* dst, int DCtot, int dc_off) {
+  if (!c || !src || !dst) return LTB_FAIL("copy_channels: null argument");
+  cudaError_t e = launch_copy_channels(static_cast<const __half*>(src), (size_t)rows, C, SCtot, sc_off, static_cast<__half*>(dst), DCtot,
+                                       dc_off, c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("copy_channels: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
+int ltb_op_transpose_heads(ltb_ctx* c, const void* v, int B, int n_keys, int Ctot, int c_off, int heads, int d, int n_pad, void* vt) {
+  if (!c || !v || !vt) return LTB_FAIL("transpose_heads: null argument");
+  cudaError_t e = launch_transpose_heads(static_cast<const __half*>(v), B, n_keys, Ctot, c_off, heads, d, n_pad, static_cast<__half*>(vt),
+                                         c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("transpose_heads: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
+int ltb_op_vae_post(ltb_ctx* c, const void* x, long long npix, int Ctot, void* out_u8) {
+  if (!c || !x || !out_u8) return LTB_FAIL("vae_post: null argument");
+  cudaError_t e = launch_vae_post(static_cast<const __half*>(x), (size_t)npix, Ctot, static_cast<uint8_t*>(out_u8), c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("vae_post: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
+int ltb_op_vae_pre(ltb_ctx* c, const void* img_u8, int N, int H, int W, int half_mask, void* out) {
+  if (!c || !img_u8 || !out) return LTB_FAIL("vae_pre: null argument");
+  cudaError_t e = launch_vae_pre(static_cast<const uint8_t*>(img_u8), N, H, W, half_mask, static_cast<__half*>(out), c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("vae_pre: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
+int ltb_op_gather_rows(ltb_ctx* c, const void* table, int n, const void* d_index, int B, long long row_elems, void* out) {
+  if (!c || !table || !d_index || !out) return LTB_FAIL("gather_rows: null argument");
+  cudaError_t e = launch_gather_rows(static_cast<const __half*>(table), n, static_cast<const int*>(d_index), B, (size_t)row_elems,
+                                     static_cast<__half*>(out), c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("gather_rows: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
+int ltb_op_mt_paste(ltb_ctx* c, const ltb_mt_paste_op* d) {
+  if (!c || !d) return LTB_FAIL("mt_paste: null argument");
+  MtPasteArgs a;
+  a.frames = static_cast<const uint8_t*>(d->frames);
+  a.coords = static_cast<const int*>(d->coords);
+  a.crop = static_cast<const int*>(d->crop);
+  a.masks = static_cast<const uint8_t*>(d->masks);
+  a.mask_off = static_cast<const long long*>(d->mask_off);
+  a.pred = static_cast<const uint8_t*>(d->pred);
+  a.out = static_cast<uint8_t*>(d->out);
+  a.nf = d->nf;
+  a.H = d->H;
+  a.W = d->W;
+  a.index = d->index;
+  a.explicit_idx = d->explicit_idx;
+  a.slot0 = d->slot0;
+  cudaError_t e = launch_mt_paste(a, d->count, c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("mt_paste: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,574 @@
+"""MuseTalk on the B200 engine: VAE-encode -> audio-conditioned UNet -> VAE-decode -> blend paste-back.
+
+The reference only *wraps* these networks (diffusers ``UNet2DConditionModel`` / ``AutoencoderKL``:
+avatars/musetalk/models/unet.py:29-48, vae.py:10-38) and drives them from ``MuseReal.inference_batch``
+(avatars/musetalk_avatar.py:130-152).  Here the host code (this file) assembles the same graphs out of the engine's
+device operators — tcgen05 implicit-GEMM convs / linears / attention GEMMs, GroupNorm, LayerNorm, softmax, GEGLU ... —
+captures them ONCE into a CUDA graph per batch size and replays the graph per step.  Weights are taken from state_dicts
+with the diffusers key scheme (so a real ``unet.pth`` / ``sd-vae`` loads by name).
+
+Load-time rewrites (exact up to fp16 rounding):
+  * timestep is the constant 0 (musetalk_avatar.py:61): ``time_emb_proj(silu(time_embedding(t=0)))`` is folded into the
+    bias of every ResnetBlock's conv1;
+  * ``latents / scaling_factor`` (vae.py:102) is folded into ``post_quant_conv``; ``scaling_factor * mean`` (vae.py:93)
+    into ``quant_conv``;
+  * q/k/v projections are fused and every head is zero-padded to a multiple of 16 channels (head_dim 40 -> 48) so the
+    attention GEMMs meet the tensor-core K granularity; ``to_out`` gets the matching zero columns.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _capi
+from .ops import ConvWeight, Ctx, DevTensor
+
+KEY_PAD = 64  # cross-attention keys (50 audio tokens) padded to a multiple of 16
+
+
+def _np(t) -> np.ndarray:
+    if hasattr(t, "detach"):
+        t = t.detach().cpu().float().numpy()
+    return np.asarray(t, dtype=np.float32)
+
+
+def _ceil16(x: int) -> int:
+    return (x + 15) // 16 * 16
+
+
+def _silu(x):
+    return x / (1.0 + np.exp(-x))
+
+
+class _Norm:
+    def __init__(self, ctx: Ctx, sd, p):
+        self.gamma = ctx.upload(_np(sd[p + ".weight"]))
+        self.beta = ctx.upload(_np(sd[p + ".bias"]))
+
+
+def _pad_heads_rows(w: np.ndarray, heads: int, d: int, dp: int) -> np.ndarray:
+    """[heads*d, cin] -> [heads*dp, cin] with zero rows after each head."""
+    out = np.zeros((heads * dp, w.shape[1]), np.float32)
+    for h in range(heads):
+        out[h * dp:h * dp + d] = w[h * d:(h + 1) * d]
+    return out
+
+
+def _pad_heads_vec(b: np.ndarray, heads: int, d: int, dp: int) -> np.ndarray:
+    out = np.zeros(heads * dp, np.float32)
+    for h in range(heads):
+        out[h * dp:h * dp + d] = b[h * d:(h + 1) * d]
+    return out
+
+
+def _pad_heads_cols(w: np.ndarray, heads: int, d: int, dp: int) -> np.ndarray:
+    """[cout, heads*d] -> [cout, heads*dp] with zero columns after each head."""
+    out = np.zeros((w.shape[0], heads * dp), np.float32)
+    for h in range(heads):
+        out[:, h * dp:h * dp + d] = w[:, h * d:(h + 1) * d]
+    return out
+
+
+class _Attn:
+    """One diffusers ``Attention`` block (self or cross) in engine layout."""
+
+    def __init__(self, ctx: Ctx, sd, p: str, C: int, heads: int, kv_dim: Optional[int]):
+        d = C // heads
+        dp = _ceil16(d)
+        self.C, self.heads, self.d, self.dp = C, heads, d, dp
+        self.self_attn = kv_dim is None
+        bias = (p + ".to_q.bias") in sd
+        wq, wk, wv = (_pad_heads_rows(_np(sd[f"{p}.{n}.weight"]), heads, d, dp) for n in ("to_q", "to_k", "to_v"))
+        bq = bk = bv = None
+        if bias:
+            bq, bk, bv = (_pad_heads_vec(_np(sd[f"{p}.{n}.bias"]), heads, d, dp) for n in ("to_q", "to_k", "to_v"))
+        if self.self_attn:
+            self.qkv = ConvWeight(ctx, np.concatenate([wq, wk, wv], 0), np.concatenate([bq, bk, bv]) if bias else None, tap_major=False)
+        else:
+            self.q = ConvWeight(ctx, wq, bq, tap_major=False)
+            self.kv = ConvWeight(ctx, np.concatenate([wk, wv], 0), np.concatenate([bk, bv]) if bias else None, tap_major=False)
+        self.out = ConvWeight(ctx, _pad_heads_cols(_np(sd[p + ".to_out.0.weight"]), heads, d, dp), _np(sd[p + ".to_out.0.bias"]),
+                              tap_major=False)
+
+
+class _Resnet:
+    def __init__(self, ctx: Ctx, sd, p: str, temb_act: Optional[np.ndarray]):
+        w1 = _np(sd[p + ".conv1.weight"])
+        b1 = _np(sd[p + ".conv1.bias"]).copy()
+        if temb_act is not None:   # constant timestep: time_emb_proj(silu(emb)) is a per-channel bias after conv1
+            b1 += _np(sd[p + ".time_emb_proj.weight"]) @ temb_act + _np(sd[p + ".time_emb_proj.bias"])
+        self.cin, self.cout = w1.shape[1], w1.shape[0]
+        self.norm1, self.norm2 = _Norm(ctx, sd, p + ".norm1"), _Norm(ctx, sd, p + ".norm2")
+        self.conv1 = ConvWeight(ctx, w1, b1)
+        self.conv2 = ConvWeight(ctx, _np(sd[p + ".conv2.weight"]), _np(sd[p + ".conv2.bias"]))
+        self.shortcut = None
+        if (p + ".conv_shortcut.weight") in sd:
+            self.shortcut = ConvWeight(ctx, _np(sd[p + ".conv_shortcut.weight"]), _np(sd[p + ".conv_shortcut.bias"]), tap_major=False)
+
+
+class _Transformer:
+    def __init__(self, ctx: Ctx, sd, p: str, C: int, heads: int, ctx_dim: int):
+        self.C = C
+        self.norm = _Norm(ctx, sd, p + ".norm")
+        self.proj_in = ConvWeight(ctx, _np(sd[p + ".proj_in.weight"]), _np(sd[p + ".proj_in.bias"]), tap_major=False)
+        self.proj_out = ConvWeight(ctx, _np(sd[p + ".proj_out.weight"]), _np(sd[p + ".proj_out.bias"]), tap_major=False)
+        b = p + ".transformer_blocks.0"
+        self.ln1, self.ln2, self.ln3 = (_Norm(ctx, sd, f"{b}.norm{i}") for i in (1, 2, 3))
+        self.attn1 = _Attn(ctx, sd, b + ".attn1", C, heads, None)
+        self.attn2 = _Attn(ctx, sd, b + ".attn2", C, heads, ctx_dim)
+        self.ff1 = ConvWeight(ctx, _np(sd[b + ".ff.net.0.proj.weight"]), _np(sd[b + ".ff.net.0.proj.bias"]), tap_major=False)
+        self.ff2 = ConvWeight(ctx, _np(sd[b + ".ff.net.2.weight"]), _np(sd[b + ".ff.net.2.bias"]), tap_major=False)
+
+
+class Builder:
+    """Emits engine ops for the diffusers building blocks.  Tensors are NHWC fp16 ``DevTensor``s of shape (N,H,W,C)."""
+
+    def __init__(self, ctx: Ctx):
+        self.ctx = ctx
+        self.temps: List[DevTensor] = []
+
+    def new(self, *shape) -> DevTensor:
+        t = self.ctx.alloc(shape, np.float16, zero=True)
+        self.temps.append(t)
+        return t
+
+    # -- primitives
+    def conv3(self, x: DevTensor, w: ConvWeight, res: Optional[DevTensor] = None, stride: int = 1, pad=(1, 1), out: Optional[DevTensor] = None):
+        N, H, W, _ = x.shape
+        OH = (H + (2 if pad == (1, 1) else 1) - 3) // stride + 1
+        OW = (W + (2 if pad == (1, 1) else 1) - 3) // stride + 1
+        if out is None:
+            out = self.new(N, OH, OW, w.cout)
+        self.ctx.conv(x, w, out, N=N, IH=H, IW=W, OH=OH, OW=OW, stride=(stride, stride), pad=pad, res=res)
+        return out
+
+    def linear(self, x: DevTensor, w: ConvWeight, res: Optional[DevTensor] = None, out: Optional[DevTensor] = None):
+        """x (..., Cin) -> (..., Cout) ; also 1x1 convs."""
+        rows = x.rows
+        if out is None:
+            out = self.new(*x.shape[:-1], w.cout)
+        self.ctx.conv(x, w, out, N=1, IH=1, IW=rows, OH=1, OW=rows, res=res)
+        return out
+
+    def groupnorm(self, x: DevTensor, n: _Norm, groups: int, eps: float, silu: bool):
+        N, H, W, C = x.shape
+        out = self.new(N, H, W, C)
+        self.ctx.groupnorm(x, N, H * W, groups, eps, n.gamma, n.beta, silu, out)
+        return out
+
+    def layernorm(self, x: DevTensor, n: _Norm, eps: float = 1e-5):
+        out = self.new(*x.shape)
+        self.ctx.layernorm(x, x.rows, x.C, eps, n.gamma, n.beta, out)
+        return out
+
+    # -- blocks
+    def resnet(self, x: DevTensor, r: _Resnet, groups: int, eps: float):
+        h = self.conv3(self.groupnorm(x, r.norm1, groups, eps, True), r.conv1)
+        h = self.groupnorm(h, r.norm2, groups, eps, True)
+        skip = self.linear(x, r.shortcut) if r.shortcut is not None else x
+        return self.conv3(h, r.conv2, res=skip)
+
+    def attention(self, a: _Attn, xq: DevTensor, B: int, nq: int, res: DevTensor, kv_src: Optional[DevTensor] = None, n_keys: Optional[int] = None,
+                  n_valid: Optional[int] = None):
+        """xq: (B*nq, C) normalised tokens.  Self-attention when kv_src is None, else keys/values from kv_src (B*n_keys, kv_dim)."""
+        ctx, H, dp, d = self.ctx, a.heads, a.dp, a.d
+        Hdp = H * dp
+        if a.self_attn:
+            qkv = self.linear(xq, a.qkv)                                  # (B*nq, 3*Hdp)
+            q_ptr, q_pitch = qkv.ptr, 3 * Hdp
+            k_ptr, v_ptr, kv_pitch = qkv.offset(Hdp), qkv.offset(2 * Hdp), 3 * Hdp
+            nk = nq
+            valid = nq
+        else:
+            q = self.linear(xq, a.q)                                      # (B*nq, Hdp)
+            kv = self.linear(kv_src, a.kv)                                # (B*n_keys, 2*Hdp)
+            q_ptr, q_pitch = q.ptr, Hdp
+            k_ptr, v_ptr, kv_pitch = kv.ptr, kv.offset(Hdp), 2 * Hdp
+            nk, valid = n_keys, n_valid
+        S = self.new(B * H, nq, nk)
+        qv = DevTensor(q_ptr, (nq, dp), pitch=q_pitch)
+        sv = DevTensor(S.ptr, (nq, nk), pitch=nk)
+        ctx.conv(qv, None, sv, N=1, IH=1, IW=nq, OH=1, OW=nq, cin=dp, cout=nk, w_ptr=k_ptr, ktot=kv_pitch,
+                 zbatch=B * H, zdiv=H, in_z=(nq * q_pitch, dp), w_z=(nk * kv_pitch, dp), out_z=(H * nq * nk, nq * nk))
+        ctx.softmax(S, B * H * nq, nk, valid, float(d) ** -0.5)
+        VT = self.new(B * H, dp, nk)
+        ctx.transpose_heads(v_ptr, B, nk, kv_pitch, H, dp, nk, VT)
+        O = self.new(B * nq, Hdp)
+        ov = DevTensor(O.ptr, (nq, dp), pitch=Hdp)
+        ctx.conv(sv, None, ov, N=1, IH=1, IW=nq, OH=1, OW=nq, cin=nk, cout=dp, w_ptr=VT.ptr, ktot=nk,
+                 zbatch=B * H, zdiv=H, in_z=(H * nq * nk, nq * nk), w_z=(H * dp * nk, dp * nk), out_z=(nq * Hdp, dp))
+        return self.linear(O, a.out, res=res)
+
+    def transformer(self, x: DevTensor, t: _Transformer, audio: DevTensor, groups: int):
+        N, H, W, C = x.shape
+        tok = self.linear(self.groupnorm(x, t.norm, groups, 1e-6, False), t.proj_in)       # (N,H,W,C) == tokens (N*HW, C)
+        tok = self.attention(t.attn1, self.layernorm(tok, t.ln1), N, H * W, res=tok)
+        tok = self.attention(t.attn2, self.layernorm(tok, t.ln2), N, H * W, res=tok, kv_src=audio, n_keys=KEY_PAD, n_valid=50)
+        g = self.linear(self.layernorm(tok, t.ln3), t.ff1)                                 # (.., 8C)
+        gg = self.new(N, H, W, 4 * C)
+        self.ctx.geglu(g, N * H * W, 4 * C, gg)
+        tok = self.linear(gg, t.ff2, res=tok)
+        return self.linear(tok, t.proj_out, res=x)
+
+    def upsample(self, x: DevTensor, w: ConvWeight):
+        N, H, W, C = x.shape
+        up = self.new(N, 2 * H, 2 * W, C)
+        self.ctx.upsample2x(x, N, H, W, up)
+        return self.conv3(up, w)
+
+    def concat(self, a: DevTensor, b: DevTensor):
+        N, H, W, _ = a.shape
+        out = self.new(N, H, W, a.C + b.C)
+        self.ctx.copy_channels(a, DevTensor(out.ptr, (N, H, W, a.C), pitch=out.C, c_off=0))
+        self.ctx.copy_channels(b, DevTensor(out.ptr, (N, H, W, b.C), pitch=out.C, c_off=a.C))
+        return out
+
+
+class MuseTalkModel:
+    """Device-resident UNet + VAE weights (replaces load_model()'s vae/unet/pe, musetalk_avatar.py:57-67)."""
+
+    def __init__(self, ctx: Ctx, unet_sd: Dict, vae_sd: Dict, ucfg, vcfg, with_encoder: bool = True):
+        self.ctx, self.ucfg, self.vcfg = ctx, ucfg, vcfg
+        sd = unet_sd
+        boc = ucfg.block_out_channels
+        heads = ucfg.num_heads
+        # constant timestep embedding (t = 0): [cos(0)..., sin(0)...] = [1]*half + [0]*half
+        half = boc[0] // 2
+        temb = np.concatenate([np.ones(half, np.float32), np.zeros(half, np.float32)])
+        temb = _np(sd["time_embedding.linear_1.weight"]) @ temb + _np(sd["time_embedding.linear_1.bias"])
+        temb = _np(sd["time_embedding.linear_2.weight"]) @ _silu(temb) + _np(sd["time_embedding.linear_2.bias"])
+        ta = _silu(temb)
+        self.u_conv_in = ConvWeight(ctx, _np(sd["conv_in.weight"]), _np(sd["conv_in.bias"]), pad_cin=16)
+        self.u_down = []
+        for i in range(len(boc)):
+            blk = {"res": [], "attn": [], "down": None}
+            for j in range(ucfg.layers_per_block):
+                blk["res"].append(_Resnet(ctx, sd, f"down_blocks.{i}.resnets.{j}", ta))
+                if ucfg.down_has_attn[i]:
+                    blk["attn"].append(_Transformer(ctx, sd, f"down_blocks.{i}.attentions.{j}", boc[i], heads, ucfg.cross_attention_dim))
+            if i < len(boc) - 1:
+                p = f"down_blocks.{i}.downsamplers.0.conv"
+                blk["down"] = ConvWeight(ctx, _np(sd[p + ".weight"]), _np(sd[p + ".bias"]), tap_major=False)
+            self.u_down.append(blk)
+        self.u_mid = (_Resnet(ctx, sd, "mid_block.resnets.0", ta),
+                      _Transformer(ctx, sd, "mid_block.attentions.0", boc[-1], heads, ucfg.cross_attention_dim),
+                      _Resnet(ctx, sd, "mid_block.resnets.1", ta))
+        rev = list(reversed(boc))
+        self.u_up = []
+        for i in range(len(boc)):
+            blk = {"res": [], "attn": [], "up": None}
+            for j in range(ucfg.layers_per_block + 1):
+                blk["res"].append(_Resnet(ctx, sd, f"up_blocks.{i}.resnets.{j}", ta))
+                if ucfg.up_has_attn[i]:
+                    blk["attn"].append(_Transformer(ctx, sd, f"up_blocks.{i}.attentions.{j}", rev[i], heads, ucfg.cross_attention_dim))
+            if i < len(boc) - 1:
+                p = f"up_blocks.{i}.upsamplers.0.conv"
+                blk["up"] = ConvWeight(ctx, _np(sd[p + ".weight"]), _np(sd[p + ".bias"]))
+            self.u_up.append(blk)
+        self.u_norm_out = _Norm(ctx, sd, "conv_norm_out")
+        self.u_conv_out = ConvWeight(ctx, _np(sd["conv_out.weight"]), _np(sd["conv_out.bias"]), pad_cout=16)
+
+        # ---- VAE decoder
+        sd = vae_sd
+        sf = vcfg.scaling_factor
+        self.v_post_quant = ConvWeight(ctx, _np(sd["post_quant_conv.weight"]) / sf, _np(sd["post_quant_conv.bias"]), pad_cin=16, pad_cout=16,
+                                       tap_major=False)
+        self.v_dec_in = ConvWeight(ctx, _np(sd["decoder.conv_in.weight"]), _np(sd["decoder.conv_in.bias"]), pad_cin=16)
+        self.v_dec_mid = self._vae_mid(ctx, sd, "decoder.mid_block")
+        vrev = list(reversed(vcfg.block_out_channels))
+        self.v_dec_up = []
+        for i in range(len(vrev)):
+            blk = {"res": [_Resnet(ctx, sd, f"decoder.up_blocks.{i}.resnets.{j}", None) for j in range(vcfg.layers_per_block + 1)], "up": None}
+            if i < len(vrev) - 1:
+                p = f"decoder.up_blocks.{i}.upsamplers.0.conv"
+                blk["up"] = ConvWeight(ctx, _np(sd[p + ".weight"]), _np(sd[p + ".bias"]))
+            self.v_dec_up.append(blk)
+        self.v_dec_norm_out = _Norm(ctx, sd, "decoder.conv_norm_out")
+        self.v_dec_out = ConvWeight(ctx, _np(sd["decoder.conv_out.weight"]), _np(sd["decoder.conv_out.bias"]), pad_cout=16)
+        # ---- VAE encoder (BASELINE config 3; offline in the reference: avatars/musetalk/genavatar.py:126-128)
+        self.with_encoder = with_encoder
+        if with_encoder:
+            vb = vcfg.block_out_channels
+            self.v_enc_in = ConvWeight(ctx, _np(sd["encoder.conv_in.weight"]), _np(sd["encoder.conv_in.bias"]), pad_cin=16)
+            self.v_enc_down = []
+            for i in range(len(vb)):
+                blk = {"res": [_Resnet(ctx, sd, f"encoder.down_blocks.{i}.resnets.{j}", None) for j in range(vcfg.layers_per_block)], "down": None}
+                if i < len(vb) - 1:
+                    p = f"encoder.down_blocks.{i}.downsamplers.0.conv"
+                    blk["down"] = ConvWeight(ctx, _np(sd[p + ".weight"]), _np(sd[p + ".bias"]), tap_major=False)
+                self.v_enc_down.append(blk)
+            self.v_enc_mid = self._vae_mid(ctx, sd, "encoder.mid_block")
+            self.v_enc_norm_out = _Norm(ctx, sd, "encoder.conv_norm_out")
+            self.v_enc_out = ConvWeight(ctx, _np(sd["encoder.conv_out.weight"]), _np(sd["encoder.conv_out.bias"]), pad_cout=16)
+            L = vcfg.latent_channels
+            qw, qb = _np(sd["quant_conv.weight"])[:L, :, 0, 0] * sf, _np(sd["quant_conv.bias"])[:L] * sf   # mean rows, x scaling_factor
+            w_lo = np.zeros((16, 16), np.float32)
+            b_lo = np.zeros(16, np.float32)
+            w_lo[:L, :2 * L] = qw
+            b_lo[:L] = qb
+            w_hi = np.zeros((16, 16), np.float32)
+            b_hi = np.zeros(16, np.float32)
+            w_hi[L:2 * L, :2 * L] = qw
+            b_hi[L:2 * L] = qb
+            self.v_quant_masked = ConvWeight(ctx, w_lo, b_lo, tap_major=False)    # masked latents -> channels [0, L)
+            self.v_quant_ref = ConvWeight(ctx, w_hi, b_hi, tap_major=False)       # reference latents -> channels [L, 2L)
+        # positional encoding table (unet.py:12-27), rows >= 50 zero (key padding)
+        pe = np.zeros((KEY_PAD, ucfg.cross_attention_dim), np.float32)
+        pos = np.arange(50, dtype=np.float32)[:, None]
+        D = ucfg.cross_attention_dim
+        div = np.exp(np.arange(0, D, 2, dtype=np.float32) * np.float32(-math.log(10000.0) / D))
+        pe[:50, 0::2] = np.sin(pos * div)
+        pe[:50, 1::2] = np.cos(pos * div)
+        self.pe = ctx.upload(pe.astype(np.float16))
+        ctx.sync()
+
+    @staticmethod
+    def _vae_mid(ctx, sd, p):
+        a = p + ".attentions.0"
+        C = _np(sd[a + ".to_q.weight"]).shape[0]
+        return (_Resnet(ctx, sd, p + ".resnets.0", None), _Norm(ctx, sd, a + ".group_norm"), _Attn(ctx, sd, a, C, 1, None),
+                _Resnet(ctx, sd, p + ".resnets.1", None))
+
+    # ------------------------------------------------------------------------------------------ graph emitters
+    def emit_unet(self, b: Builder, latents16: DevTensor, audio_pe: DevTensor, taps: Optional[dict] = None) -> DevTensor:
+        """latents16 (B,h,w,16) [8 real channels], audio_pe (B*64, 384) -> predicted latents (B,h,w,16) [4 real channels]."""
+        cfg = self.ucfg
+        G, eps = cfg.norm_groups, cfg.norm_eps
+        h = b.conv3(latents16, self.u_conv_in)
+        skips = [h]
+        for i, blk in enumerate(self.u_down):
+            for j, r in enumerate(blk["res"]):
+                h = b.resnet(h, r, G, eps)
+                if blk["attn"]:
+                    h = b.transformer(h, blk["attn"][j], audio_pe, G)
+                skips.append(h)
+            if blk["down"] is not None:
+                h = b.conv3(h, blk["down"], stride=2)
+                skips.append(h)
+            if taps is not None:
+                taps[f"down{i}"] = h
+        h = b.resnet(h, self.u_mid[0], G, eps)
+        h = b.transformer(h, self.u_mid[1], audio_pe, G)
+        h = b.resnet(h, self.u_mid[2], G, eps)
+        if taps is not None:
+            taps["mid"] = h
+        for i, blk in enumerate(self.u_up):
+            for j, r in enumerate(blk["res"]):
+                h = b.resnet(b.concat(h, skips.pop()), r, G, eps)
+                if blk["attn"]:
+                    h = b.transformer(h, blk["attn"][j], audio_pe, G)
+            if blk["up"] is not None:
+                h = b.upsample(h, blk["up"])
+            if taps is not None:
+                taps[f"up{i}"] = h
+        return b.conv3(b.groupnorm(h, self.u_norm_out, G, eps, True), self.u_conv_out)
+
+    def _emit_vae_mid(self, b: Builder, h: DevTensor, mid, G, eps):
+        r0, gn, attn, r1 = mid
+        h = b.resnet(h, r0, G, eps)
+        N, H, W, C = h.shape
+        h = b.attention(attn, b.groupnorm(h, gn, G, eps, False), N, H * W, res=h)
+        h = DevTensor(h.ptr, (N, H, W, C))
+        return b.resnet(h, r1, G, eps)
+
+    def emit_vae_decode(self, b: Builder, pred16: DevTensor, out_u8: DevTensor, taps: Optional[dict] = None) -> DevTensor:
+        """pred16 (B,h,w,16) latents [4 real channels] -> uint8 BGR image written to out_u8 (B,8h,8w,3)."""
+        cfg = self.vcfg
+        G, eps = cfg.norm_groups, cfg.norm_eps
+        h = b.conv3(b.linear(pred16, self.v_post_quant), self.v_dec_in)
+        h = self._emit_vae_mid(b, h, self.v_dec_mid, G, eps)
+        if taps is not None:
+            taps["dec_mid"] = h
+        for i, blk in enumerate(self.v_dec_up):
+            for r in blk["res"]:
+                h = b.resnet(h, r, G, eps)
+            if blk["up"] is not None:
+                h = b.upsample(h, blk["up"])
+            if taps is not None:
+                taps[f"dec_up{i}"] = h
+        img = b.conv3(b.groupnorm(h, self.v_dec_norm_out, G, eps, True), self.v_dec_out)   # (B,H,W,16), RGB in channels 0..2
+        N, H, W, _ = img.shape
+        self.ctx.vae_post(img, N * H * W, out_u8)
+        return img
+
+    def emit_vae_encode(self, b: Builder, img_u8: DevTensor, out_latents16: DevTensor):
+        """img_u8 (B,H,W,3) uint8 BGR -> get_latents_for_unet (vae.py:110-122, latent_dist.mode()): (B,H/8,W/8,16) [8 real]."""
+        assert self.with_encoder
+        cfg = self.vcfg
+        G, eps = cfg.norm_groups, cfg.norm_eps
+        B, H, W, _ = img_u8.shape
+        x = b.new(2 * B, H, W, 16)
+        self.ctx.vae_pre(img_u8, B, H, W, True, DevTensor(x.ptr, (B, H, W, 16)))                                  # masked copies
+        self.ctx.vae_pre(img_u8, B, H, W, False, DevTensor(x.offset(B * H * W * 16), (B, H, W, 16)))              # reference copies
+        h = b.conv3(x, self.v_enc_in)
+        for blk in self.v_enc_down:
+            for r in blk["res"]:
+                h = b.resnet(h, r, G, eps)
+            if blk["down"] is not None:
+                h = b.conv3(h, blk["down"], stride=2, pad=(0, 0))     # F.pad(x,(0,1,0,1)) + conv s2 p0
+        h = self._emit_vae_mid(b, h, self.v_enc_mid, G, eps)
+        m = b.conv3(b.groupnorm(h, self.v_enc_norm_out, G, eps, True), self.v_enc_out)   # (2B,h,w,16): moments in 0..7
+        _, lh, lw, _ = m.shape
+        half = B * lh * lw * 16
+        tmp = b.linear(DevTensor(m.ptr, (B, lh, lw, 16)), self.v_quant_masked)
+        b.linear(DevTensor(m.offset(half), (B, lh, lw, 16)), self.v_quant_ref, res=tmp, out=out_latents16)
+        return out_latents16
+
+
+class MuseTalkAvatar:
+    """Avatar assets resident in HBM (replaces load_avatar's lists, musetalk_avatar.py:69-91): full frames, bbox
+    (x1,y1,x2,y2), mask crop boxes (x_s,y_s,x_e,y_e), 3-channel blend masks and the pre-computed UNet input latents."""
+
+    def __init__(self, ctx: Ctx, frames, masks, coords, crop_boxes, latents):
+        self.ctx = ctx
+        frames = np.ascontiguousarray(np.asarray(frames), np.uint8)
+        self.n, self.H, self.W = frames.shape[0], frames.shape[1], frames.shape[2]
+        self.frames_host = frames
+        self.coords_host = np.ascontiguousarray(np.asarray(coords), np.int32).reshape(self.n, 4)
+        self.crop_host = np.ascontiguousarray(np.asarray(crop_boxes), np.int32).reshape(self.n, 4)
+        offs, blobs, o = [], [], 0
+        for i in range(self.n):
+            xs, ys, xe, ye = self.crop_host[i]
+            x1, y1, x2, y2 = self.coords_host[i]
+            m = np.ascontiguousarray(masks[i], np.uint8)
+            if m.shape != (ye - ys, xe - xs, 3):
+                raise ValueError(f"mask {i} has shape {m.shape}, crop box needs {(ye - ys, xe - xs, 3)}")
+            if not (0 <= xs <= x1 < x2 <= xe <= self.W and 0 <= ys <= y1 < y2 <= ye <= self.H):
+                raise ValueError(f"avatar frame {i}: bbox / crop box outside the frame")
+            offs.append(o)
+            blobs.append(m.reshape(-1))
+            o += m.size
+        self.masks_host = [np.asarray(m, np.uint8) for m in masks]
+        self.frames = ctx.upload(frames)
+        self.coords = ctx.upload(self.coords_host)
+        self.crop = ctx.upload(self.crop_host)
+        self.masks = ctx.upload(np.concatenate(blobs))
+        self.mask_off = ctx.upload(np.asarray(offs, np.int64))
+        # latents: list of (1,8,h,w) arrays (latents.pt) -> NHWC fp16 padded to 16 channels
+        lat = np.concatenate([_np(l) for l in latents], 0)
+        self.lat_hw = lat.shape[2]
+        lat16 = np.zeros((lat.shape[0], lat.shape[2], lat.shape[3], 16), np.float16)
+        lat16[..., :8] = lat.transpose(0, 2, 3, 1)
+        self.latents = ctx.upload(lat16)
+
+
+class MuseTalkSession:
+    """One avatar stream at a fixed batch size: the captured UNet + VAE-decode graph and the paste-back buffers."""
+
+    def __init__(self, model: MuseTalkModel, avatar: MuseTalkAvatar, batch: int, keep_taps: bool = False):
+        self.model, self.avatar, self.B = model, avatar, int(batch)
+        ctx = self.ctx = model.ctx
+        B, hw = self.B, avatar.lat_hw
+        self.builder = Builder(ctx)
+        self.d_index = ctx.alloc((4,), np.int32, zero=True)
+        self.audio_in = ctx.alloc((B, KEY_PAD, model.ucfg.cross_attention_dim), np.float16, zero=True)
+        self.audio_pe = ctx.alloc((B * KEY_PAD, model.ucfg.cross_attention_dim), np.float16, zero=True)
+        self.latents16 = ctx.alloc((B, hw, hw, 16), np.float16, zero=True)
+        self.image_u8 = ctx.alloc((B, hw * 8, hw * 8, 3), np.uint8, zero=True)
+        self.frames_out = ctx.alloc((B, avatar.H, avatar.W, 3), np.uint8, zero=True)
+        self.taps = {} if keep_taps else None
+        self._audio_host = np.zeros((B, KEY_PAD, model.ucfg.cross_attention_dim), np.float16)
+
+        def emit():
+            ctx.gather_rows(avatar.latents, avatar.latents.shape[0], self.d_index, B, hw * hw * 16, self.latents16)
+            ctx.eltwise(self.audio_in, model.pe, self.audio_in.rows * self.audio_in.C, KEY_PAD * self.audio_in.C, 0, self.audio_pe)
+            self.pred16 = model.emit_unet(self.builder, self.latents16, self.audio_pe, self.taps)
+            self.image16 = model.emit_vae_decode(self.builder, self.pred16, self.image_u8, self.taps)
+
+        emit()                       # eager pass: allocates every intermediate and warms the kernels up
+        ctx.sync()
+        temps, self.builder.temps = self.builder.temps, []
+        self.builder.new = _Replay(temps)   # the captured pass reuses exactly the same buffers, in the same order
+        with ctx.capture() as cap:
+            emit()
+        self.graph = cap.graph
+        self.graph_launches = None
+
+    # ---- MuseReal.inference_batch (musetalk_avatar.py:130-152)
+    def infer_async(self, index: int, audio_feats: Optional[np.ndarray] = None):
+        if audio_feats is not None:
+            a = np.asarray(audio_feats)
+            if a.shape != (self.B, 50, self._audio_host.shape[2]):
+                raise ValueError(f"audio features must be ({self.B},50,{self._audio_host.shape[2]}), got {a.shape}")
+            self._audio_host[:, :50] = a.astype(np.float16)
+            self.ctx.h2d(self.audio_in, self._audio_host, sync=False)
+        self.ctx.set_i32(self.d_index, index)
+        self.graph.launch()
+
+    def infer(self, index: int, audio_feats: Optional[np.ndarray] = None, want_pred: bool = True):
+        self.infer_async(index, audio_feats)
+        if want_pred:
+            return self.ctx.download(self.image_u8)          # uint8 (B,256,256,3) BGR, as vae.decode_latents returns
+        self.ctx.sync()
+        return None
+
+    # ---- MuseReal.paste_back_frame (musetalk_avatar.py:154-164)
+    def _paste_op(self, pred: DevTensor, slot0: int, index: int, explicit_idx: int, count: int):
+        a = self.avatar
+        op = _capi.MtPasteOp()
+        op.frames, op.coords, op.crop, op.masks, op.mask_off = a.frames.ptr, a.coords.ptr, a.crop.ptr, a.masks.ptr, a.mask_off.ptr
+        op.pred, op.out = pred.ptr, self.frames_out.ptr
+        op.nf, op.H, op.W = a.n, a.H, a.W
+        op.index, op.explicit_idx, op.slot0, op.count = index, explicit_idx, slot0, count
+        self.ctx.mt_paste(op)
+
+    def paste(self, slot: int, idx: int) -> np.ndarray:
+        if not (0 <= slot < self.B and 0 <= idx < self.avatar.n):
+            raise ValueError("paste: slot / idx out of range")
+        self._paste_op(self.image_u8, slot, 0, idx, 1)
+        one = DevTensor(self.frames_out.ptr, (self.avatar.H, self.avatar.W, 3), np.uint8)
+        return self.ctx.download(one)
+
+    def paste_pred(self, pred_u8: np.ndarray, idx: int) -> np.ndarray:
+        """paste_back_frame for a host prediction (256,256,3) uint8 — the reference's exact argument."""
+        if not hasattr(self, "_pred_scratch"):
+            self._pred_scratch = self.ctx.alloc((1, 256, 256, 3), np.uint8)
+        self.ctx.h2d(self._pred_scratch, np.ascontiguousarray(pred_u8, np.uint8), sync=False)
+        self._paste_op(self._pred_scratch, 0, 0, idx, 1)
+        one = DevTensor(self.frames_out.ptr, (self.avatar.H, self.avatar.W, 3), np.uint8)
+        return self.ctx.download(one)
+
+    def paste_batch_async(self, index: int):
+        self._paste_op(self.image_u8, 0, index, -1, self.B)
+
+    def paste_batch(self, index: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        self.paste_batch_async(index)
+        return self.ctx.download(self.frames_out, out)
+
+    def step_async(self, index: int):
+        """Everything resident (audio features already on the device): UNet + VAE decode + blend paste-back."""
+        self.infer_async(index, None)
+        self.paste_batch_async(index)
+
+
+class _Replay:
+    """Hands back the buffers of the eager pass, in order, while the same op sequence is being captured."""
+
+    def __init__(self, temps):
+        self.temps, self.i = temps, 0
+
+    def __call__(self, *shape):
+        t = self.temps[self.i]
+        self.i += 1
+        assert t.shape == tuple(shape), (t.shape, shape)
+        return t
+
+
+def encode_avatar_latents(model: MuseTalkModel, images_u8: np.ndarray) -> np.ndarray:
+    """GPU get_latents_for_unet for a stack of (n,256,256,3) uint8 BGR crops -> (n,8,h,w) float16 (latents.pt content,
+    avatars/musetalk/genavatar.py:126-128 with the deterministic latent_dist.mode())."""
+    ctx = model.ctx
+    imgs = np.ascontiguousarray(images_u8, np.uint8)
+    n, H, W, _ = imgs.shape
+    d_img = ctx.upload(imgs)
+    out = ctx.alloc((n, H // 8, W // 8, 16), np.float16, zero=True)
+    b = Builder(ctx)
+    model.emit_vae_encode(b, d_img, out)
+    lat = ctx.download(out)
+    for t in b.temps:
+        ctx.free(t)
+    ctx.free(d_img)
+    ctx.free(out)
+    return np.ascontiguousarray(lat[..., :8].transpose(0, 3, 1, 2))

@@ -1,0 +1,252 @@
+"""Python handle over the generic device-op layer of the C ABI (``ltb_ctx`` / ``ltb_op_*``, include/ltb200.h).
+
+A ``Ctx`` owns a CUDA stream and device memory; ``DevTensor`` is a (pointer, shape) view — NHWC fp16 activations or raw
+byte buffers.  Ops enqueue kernels asynchronously; ``capture()`` records a sequence of ops into a CUDA graph that is
+replayed with ``Graph.launch()``.  No computation happens in Python."""
+from __future__ import annotations
+
+import contextlib
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import ConvOp, MtPasteOp, check, lib
+
+
+class DevTensor:
+    __slots__ = ("ptr", "shape", "dtype", "nbytes", "pitch", "c_off")
+
+    def __init__(self, ptr: int, shape: Sequence[int], dtype=np.float16, pitch: Optional[int] = None, c_off: int = 0):
+        self.ptr = int(ptr)
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.pitch = int(pitch) if pitch is not None else self.shape[-1]   # elements between consecutive pixels / rows
+        self.c_off = int(c_off)                                            # first channel inside the pitch
+
+    @property
+    def C(self) -> int:
+        return self.shape[-1]
+
+    @property
+    def rows(self) -> int:
+        return int(np.prod(self.shape[:-1]))
+
+    def offset(self, elems: int) -> int:
+        return self.ptr + elems * self.dtype.itemsize
+
+
+class Graph:
+    def __init__(self, ctx: "Ctx", handle):
+        self.ctx, self._h = ctx, handle
+
+    def launch(self):
+        check(lib().ltb_graph_launch(self.ctx._h, self._h))
+
+    def close(self):
+        if self._h:
+            lib().ltb_graph_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Ctx:
+    def __init__(self):
+        self._h = C.c_void_p()
+        check(lib().ltb_ctx_create(C.byref(self._h)))
+
+    # ---- memory
+    def alloc(self, shape, dtype=np.float16, zero: bool = False) -> DevTensor:
+        t = DevTensor(0, shape, dtype)
+        p = C.c_void_p()
+        check(lib().ltb_dev_alloc(self._h, t.nbytes, int(zero), C.byref(p)))
+        t.ptr = p.value
+        return t
+
+    def free(self, t: DevTensor):
+        check(lib().ltb_dev_free(self._h, C.c_void_p(t.ptr)))
+
+    def upload(self, arr: np.ndarray, dtype=None) -> DevTensor:
+        arr = np.ascontiguousarray(arr, dtype=dtype)
+        t = self.alloc(arr.shape, arr.dtype)
+        check(lib().ltb_h2d(self._h, C.c_void_p(t.ptr), arr.ctypes.data_as(C.c_void_p), arr.nbytes, 1))
+        return t
+
+    def h2d(self, t: DevTensor, arr: np.ndarray, sync: bool = True):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= t.nbytes, (arr.nbytes, t.nbytes)
+        check(lib().ltb_h2d(self._h, C.c_void_p(t.ptr), arr.ctypes.data_as(C.c_void_p), arr.nbytes, int(sync)))
+
+    def download(self, t: DevTensor, out: Optional[np.ndarray] = None, sync: bool = True) -> np.ndarray:
+        if out is None:
+            out = np.empty(t.shape, t.dtype)
+        check(lib().ltb_d2h(self._h, out.ctypes.data_as(C.c_void_p), C.c_void_p(t.ptr), t.nbytes, int(sync)))
+        return out
+
+    def download_slice(self, t: DevTensor) -> np.ndarray:
+        """Dense copy of a channel-sliced view (pitch > C): gathers through a temporary."""
+        if t.pitch == t.C and t.c_off == 0:
+            return self.download(t)
+        tmp = self.alloc(t.shape, t.dtype)
+        self.copy_channels(t, tmp)
+        out = self.download(tmp)
+        self.free(tmp)
+        return out
+
+    def set_i32(self, t: DevTensor, value: int):
+        check(lib().ltb_set_i32(self._h, C.c_void_p(t.ptr), int(value)))
+
+    def sync(self):
+        check(lib().ltb_ctx_sync(self._h))
+
+    @property
+    def cuda_stream(self) -> int:
+        p = C.c_void_p()
+        check(lib().ltb_ctx_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    @property
+    def launch_count(self) -> int:
+        n = C.c_longlong(0)
+        check(lib().ltb_ctx_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    @contextlib.contextmanager
+    def capture(self):
+        """with ctx.capture() as g: <ops> ; afterwards g.graph is the instantiated CUDA graph."""
+        holder = type("Capture", (), {"graph": None})()
+        check(lib().ltb_capture_begin(self._h))
+        try:
+            yield holder
+        except Exception:
+            h = C.c_void_p()
+            lib().ltb_capture_end(self._h, C.byref(h))
+            if h:
+                lib().ltb_graph_destroy(h)
+            raise
+        h = C.c_void_p()
+        check(lib().ltb_capture_end(self._h, C.byref(h)))
+        holder.graph = Graph(self, h)
+
+    # ---- ops
+    def conv(self, x: DevTensor, w: "ConvWeight", out: DevTensor, *, N: int, IH: int, IW: int, OH: int, OW: int, stride=(1, 1),
+             pad=(0, 0), res: Optional[DevTensor] = None, relu: bool = False, cin: Optional[int] = None, no_halo: bool = False,
+             zbatch: int = 0, zdiv: int = 1, in_z=(0, 0), w_z=(0, 0), out_z=(0, 0), w_ptr: Optional[int] = None,
+             ktot: Optional[int] = None, cout: Optional[int] = None, in_ptr: Optional[int] = None, out_ptr: Optional[int] = None):
+        d = ConvOp()
+        d.in_ = in_ptr if in_ptr is not None else x.ptr
+        d.w = w_ptr if w_ptr is not None else w.w.ptr
+        d.w_tap = (w.w_tap.ptr if (w is not None and w.w_tap is not None and w_ptr is None) else None)
+        d.bias = (w.bias.ptr if (w is not None and w.bias is not None) else None)
+        d.res = res.ptr if res is not None else None
+        d.out = out_ptr if out_ptr is not None else out.ptr
+        d.N, d.IH, d.IW = N, IH, IW
+        d.ICtot, d.ic_off = x.pitch, x.c_off
+        d.Cin = cin if cin is not None else w.cin
+        d.OH, d.OW = OH, OW
+        d.Cout = cout if cout is not None else w.cout
+        d.OCtot, d.oc_off = out.pitch, out.c_off
+        d.RCtot, d.rc_off = (res.pitch, res.c_off) if res is not None else (0, 0)
+        d.KH, d.KW = (w.kh, w.kw) if w is not None else (1, 1)
+        d.sy, d.sx = stride
+        d.pad_t, d.pad_l = pad
+        d.Ktot = ktot if ktot is not None else w.ktot
+        d.w_koff = 0
+        d.relu = int(relu)
+        d.no_halo = int(no_halo)
+        d.zbatch, d.zdiv = zbatch, zdiv
+        d.in_zo, d.in_zi = in_z
+        d.w_zo, d.w_zi = w_z
+        d.out_zo, d.out_zi = out_z
+        check(lib().ltb_op_conv2d(self._h, C.byref(d)))
+
+    def groupnorm(self, x: DevTensor, N: int, HW: int, groups: int, eps: float, gamma: DevTensor, beta: DevTensor, silu: bool,
+                  out: DevTensor):
+        check(lib().ltb_op_groupnorm(self._h, C.c_void_p(x.ptr), N, HW, x.C, x.pitch, x.c_off, groups, eps, C.c_void_p(gamma.ptr),
+                                     C.c_void_p(beta.ptr), int(silu), C.c_void_p(out.ptr), out.pitch, out.c_off))
+
+    def layernorm(self, x: DevTensor, rows: int, Cc: int, eps: float, gamma: DevTensor, beta: DevTensor, out: DevTensor):
+        check(lib().ltb_op_layernorm(self._h, C.c_void_p(x.ptr), rows, Cc, eps, C.c_void_p(gamma.ptr), C.c_void_p(beta.ptr),
+                                     C.c_void_p(out.ptr)))
+
+    def softmax(self, x: DevTensor, rows: int, cols: int, valid: int, scale: float):
+        check(lib().ltb_op_softmax(self._h, C.c_void_p(x.ptr), rows, cols, cols, valid, scale, C.c_void_p(x.ptr)))
+
+    def geglu(self, h: DevTensor, rows: int, H: int, out: DevTensor):
+        check(lib().ltb_op_geglu(self._h, C.c_void_p(h.ptr), rows, H, C.c_void_p(out.ptr)))
+
+    def eltwise(self, x: DevTensor, y: Optional[DevTensor], n: int, period: int, act: int, out: DevTensor):
+        check(lib().ltb_op_eltwise(self._h, C.c_void_p(x.ptr), C.c_void_p(y.ptr) if y is not None else None, n, period, act,
+                                   C.c_void_p(out.ptr)))
+
+    def upsample2x(self, x: DevTensor, N: int, H: int, W: int, out: DevTensor):
+        check(lib().ltb_op_upsample2x(self._h, C.c_void_p(x.ptr), N, H, W, x.C, C.c_void_p(out.ptr)))
+
+    def copy_channels(self, src: DevTensor, dst: DevTensor, rows: Optional[int] = None):
+        check(lib().ltb_op_copy_channels(self._h, C.c_void_p(src.ptr), rows if rows is not None else src.rows, src.C, src.pitch,
+                                         src.c_off, C.c_void_p(dst.ptr), dst.pitch, dst.c_off))
+
+    def transpose_heads(self, v_ptr: int, B: int, n_keys: int, Ctot: int, heads: int, d: int, n_pad: int, vt: DevTensor):
+        check(lib().ltb_op_transpose_heads(self._h, C.c_void_p(v_ptr), B, n_keys, Ctot, 0, heads, d, n_pad, C.c_void_p(vt.ptr)))
+
+    def vae_post(self, x: DevTensor, npix: int, out_u8: DevTensor):
+        check(lib().ltb_op_vae_post(self._h, C.c_void_p(x.ptr), npix, x.pitch, C.c_void_p(out_u8.ptr)))
+
+    def vae_pre(self, img_u8: DevTensor, N: int, H: int, W: int, half_mask: bool, out: DevTensor):
+        check(lib().ltb_op_vae_pre(self._h, C.c_void_p(img_u8.ptr), N, H, W, int(half_mask), C.c_void_p(out.ptr)))
+
+    def gather_rows(self, table: DevTensor, n: int, d_index: DevTensor, B: int, row_elems: int, out: DevTensor):
+        check(lib().ltb_op_gather_rows(self._h, C.c_void_p(table.ptr), n, C.c_void_p(d_index.ptr), B, row_elems, C.c_void_p(out.ptr)))
+
+    def w_tap_major(self, w: DevTensor, wt: DevTensor, cout: int, cin: int):
+        check(lib().ltb_op_w_tap_major(self._h, C.c_void_p(w.ptr), C.c_void_p(wt.ptr), cout, cin))
+
+    def mt_paste(self, op: MtPasteOp):
+        check(lib().ltb_op_mt_paste(self._h, C.byref(op)))
+
+    def close(self):
+        if self._h:
+            lib().ltb_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ConvWeight:
+    """Device-resident conv / linear weights in the kernels' layout: fp16 [Cout][KH*KW*Cin] (+ tap-major copy for 3x3)."""
+
+    def __init__(self, ctx: Ctx, w: np.ndarray, bias: Optional[np.ndarray], *, pad_cin: Optional[int] = None,
+                 pad_cout: Optional[int] = None, tap_major: bool = True):
+        w = np.asarray(w, dtype=np.float32)
+        if w.ndim == 2:
+            w = w[:, :, None, None]
+        cout, cin, kh, kw = w.shape
+        cin_p = pad_cin or cin
+        cout_p = pad_cout or cout
+        if cin_p != cin or cout_p != cout:
+            wp = np.zeros((cout_p, cin_p, kh, kw), np.float32)
+            wp[:cout, :cin] = w
+            w = wp
+        self.cout, self.cin, self.kh, self.kw = cout_p, cin_p, kh, kw
+        self.ktot = kh * kw * cin_p
+        packed = np.ascontiguousarray(w.transpose(0, 2, 3, 1)).reshape(cout_p, self.ktot).astype(np.float16)
+        self.w = ctx.upload(packed)
+        b = np.zeros(cout_p, np.float32)
+        if bias is not None:
+            b[:cout] = np.asarray(bias, np.float32)
+        self.bias = ctx.upload(b)
+        self.w_tap = None
+        if tap_major and kh == 3 and kw == 3 and cin_p >= 16:
+            self.w_tap = ctx.alloc((9, cout_p, cin_p), np.float16)
+            ctx.w_tap_major(self.w, self.w_tap, cout_p, cin_p)

@@ -101,3 +101,35 @@ def w2l_build_batch(face_list, index: int, batch: int):
     masked[:, faces.shape[1] // 2:] = 0
     img = np.concatenate((masked, faces), axis=3) / 255.0
     return np.transpose(img, (0, 3, 1, 2)).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# MuseTalk blend paste-back
+# --------------------------------------------------------------------------------------------------------------------
+def bgr2gray_u8(img: np.ndarray) -> np.ndarray:
+    """cv2.cvtColor(img, cv2.COLOR_BGR2GRAY) for uint8: 15-bit fixed point, pinned against the installed cv2."""
+    b, g, r = (img[..., i].astype(np.int64) for i in range(3))
+    return ((b * 3735 + g * 19235 + r * 9798 + 16384) >> 15).astype(np.uint8)
+
+
+def blend_linear_u8(src1: np.ndarray, src2: np.ndarray, w1: np.ndarray, w2: np.ndarray) -> np.ndarray:
+    """cv2.blendLinear for uint8 images / float32 weights: sat_u8(rint((s1*w1 + s2*w2) / (w1 + w2 + 1e-5))) in float32."""
+    w1 = w1.astype(np.float32)[..., None]
+    w2 = w2.astype(np.float32)[..., None]
+    den = (w1 + w2 + np.float32(1e-5)).astype(np.float32)
+    num = (src1.astype(np.float32) * w1).astype(np.float32) + (src2.astype(np.float32) * w2).astype(np.float32)
+    return np.clip(np.rint((num / den).astype(np.float32)), 0, 255).astype(np.uint8)
+
+
+def mt_paste_back(pred_u8: np.ndarray, frame_u8: np.ndarray, bbox, mask_u8: np.ndarray, crop_box) -> np.ndarray:
+    """MuseReal.paste_back_frame (avatars/musetalk_avatar.py:154-164) + get_image_blending (avatars/musetalk/myutil.py:4-25).
+    bbox = (x1,y1,x2,y2); crop_box = (x_s,y_s,x_e,y_e); mask: (y_e-y_s, x_e-x_s, 3) uint8."""
+    x1, y1, x2, y2 = [int(v) for v in bbox]
+    xs, ys, xe, ye = [int(v) for v in crop_box]
+    body = frame_u8.copy()
+    res = resize_linear_u8(np.asarray(pred_u8).astype(np.uint8), x2 - x1, y2 - y1)
+    face_large = body[ys:ye, xs:xe].copy()
+    face_large[y1 - ys:y2 - ys, x1 - xs:x2 - xs] = res
+    m = (bgr2gray_u8(mask_u8) / 255).astype(np.float32)
+    body[ys:ye, xs:xe] = blend_linear_u8(face_large, body[ys:ye, xs:xe], m, (1 - m).astype(np.float32))
+    return body

@@ -1,0 +1,136 @@
+"""GPU: the MuseTalk path (UNet + VAE decode / encode + blend paste-back, assembled from engine ops through the C ABI)
+against the CPU fp32 oracle restatement.  NB oracle/musetalk_ref.py: the diffusers architecture is not in the reference
+tree — parity here is against our restatement of the published layout ("parity unpinned")."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _avatar(ctx, lat, n, H=300, W=400, seed=0):
+    from livetalking_b200.musetalk import MuseTalkAvatar
+    rng = np.random.default_rng(seed)
+    frames = rng.integers(0, 256, (n, H, W, 3), dtype=np.uint8)
+    coords = [(120 + 3 * i, 60 + 2 * i, 120 + 3 * i + 150 + 7 * i, 60 + 2 * i + 170 + 5 * i) for i in range(n)]   # x1,y1,x2,y2
+    crops, masks = [], []
+    for (x1, y1, x2, y2) in coords:
+        xs, ys, xe, ye = max(0, x1 - 40), max(0, y1 - 30), min(W, x2 + 40), min(H, y2 + 30)
+        crops.append((xs, ys, xe, ye))
+        mh, mw = ye - ys, xe - xs
+        yy = np.linspace(0, 1, mh)[:, None] * np.ones((1, mw))
+        soft = (np.clip((yy - 0.35) * 4, 0, 1) * 255).astype(np.uint8)
+        masks.append(np.stack([soft, soft, soft], -1))
+    return MuseTalkAvatar(ctx, frames, masks, coords, crops, [lat[i:i + 1] for i in range(n)]), frames, coords, crops, masks
+
+
+def _cmp_taps(ctx, taps, otaps, tol_max=4e-2, tol_mean=1e-2):
+    bad = []
+    for k, ot in otaps.items():
+        got = ctx.download(taps[k]).astype(np.float32)
+        want = ot.permute(0, 2, 3, 1).numpy()
+        assert got.shape == want.shape, (k, got.shape, want.shape)
+        assert np.isfinite(got).all(), k
+        rel = np.abs(got - want).max() / max(1e-6, np.abs(want).max())
+        mrel = np.abs(got - want).mean() / max(1e-6, np.abs(want).mean())
+        if rel > tol_max or mrel > tol_mean:
+            bad.append(f"{k}:{rel:.4f}:{mrel:.5f}")
+    assert not bad, "taps out of tolerance (name:max-rel:mean-rel): " + "; ".join(bad)
+
+
+@pytest.fixture(scope="module")
+def small_nets():
+    from oracle import musetalk_ref as M
+    return M.UNET_SMALL, M.VAE_SMALL, M.synth_unet_state_dict(M.UNET_SMALL), M.synth_vae_state_dict(M.VAE_SMALL)
+
+
+def test_small_unet_vae_decode_parity_and_blend(small_nets):
+    from livetalking_b200 import engine
+    from livetalking_b200.musetalk import MuseTalkModel, MuseTalkSession
+    from livetalking_b200.ops import Ctx
+    from oracle import musetalk_ref as M
+    from oracle import paste_ref as P
+    from oracle.wav2lip_ref import psnr_u8
+    ucfg, vcfg, us, vs = small_nets
+    engine.set_device(0)
+    B = 2
+    lat, aud = M.synth_latents_and_audio(B, seed=4)
+    otaps = {}
+    pred = M.unet_forward(us, ucfg, lat, M.positional_encoding(aud), taps=otaps)
+    vt = {}
+    M.vae_decode(vs, vcfg, pred / vcfg.scaling_factor, taps=vt)
+    otaps.update(vt)
+    want_u8 = M.decode_latents_u8(vs, vcfg, pred)
+    ctx = Ctx()
+    model = MuseTalkModel(ctx, us, vs, ucfg, vcfg)
+    av, frames, coords, crops, masks = _avatar(ctx, lat.numpy(), B)
+    s = MuseTalkSession(model, av, B, keep_taps=True)
+    got_u8 = s.infer(0, aud.numpy())
+    _cmp_taps(ctx, s.taps, otaps)
+    got_lat = ctx.download(s.pred16).astype(np.float32)[..., :4]
+    np.testing.assert_allclose(got_lat, pred.permute(0, 2, 3, 1).numpy(), atol=6e-2)
+    assert got_u8.shape == (B, 256, 256, 3) and got_u8.dtype == np.uint8
+    assert psnr_u8(got_u8, want_u8) >= 40.0, psnr_u8(got_u8, want_u8)
+    # replay determinism + mirror index gather (index 1 -> latents [1, 1 mirrored -> 0]... with n=2: idx 1, then 1 (turn 1: 2-0-1))
+    again = s.infer(0, aud.numpy())           # graph replay; GroupNorm statistics use float atomics -> last-bit jitter only
+    assert np.abs(again.astype(int) - got_u8.astype(int)).max() <= 2 and psnr_u8(again, got_u8) >= 55.0
+    # paste-back: bit-exact blend of the engine's own prediction
+    for slot in range(B):
+        idx = P.mirror_index(B, slot)
+        got = s.paste(slot, idx)
+        want = P.mt_paste_back(got_u8[slot], frames[idx], coords[idx], masks[idx], crops[idx])
+        assert np.array_equal(got, want), (slot, int(np.abs(got.astype(int) - want).max()))
+    allf = s.paste_batch(0)
+    for slot in range(B):
+        idx = P.mirror_index(B, slot)
+        assert np.array_equal(allf[slot], P.mt_paste_back(got_u8[slot], frames[idx], coords[idx], masks[idx], crops[idx]))
+    host_pred = np.random.default_rng(1).integers(0, 256, (256, 256, 3), dtype=np.uint8)
+    assert np.array_equal(s.paste_pred(host_pred, 1), P.mt_paste_back(host_pred, frames[1], coords[1], masks[1], crops[1]))
+    ctx.close()
+
+
+def test_small_vae_encode_parity(small_nets):
+    from livetalking_b200 import engine
+    from livetalking_b200.musetalk import MuseTalkModel, encode_avatar_latents
+    from livetalking_b200.ops import Ctx
+    from oracle import musetalk_ref as M
+    ucfg, vcfg, us, vs = small_nets
+    engine.set_device(0)
+    rng = np.random.default_rng(2)
+    low = rng.integers(0, 256, (2, 32, 32, 3)).astype(np.float32)
+    imgs = np.clip(np.kron(low, np.ones((1, 8, 8, 1), np.float32)) + rng.integers(-6, 7, (2, 256, 256, 3)), 0, 255).astype(np.uint8)
+    ctx = Ctx()
+    model = MuseTalkModel(ctx, us, vs, ucfg, vcfg)
+    got = encode_avatar_latents(model, imgs).astype(np.float32)
+    want = np.concatenate([M.latents_for_unet(vs, vcfg, imgs[i]).numpy() for i in range(2)], 0)
+    assert got.shape == want.shape == (2, 8, 32, 32)
+    err = np.abs(got - want)
+    assert err.max() <= 0.02 + 0.04 * np.abs(want).max(), (err.max(), np.abs(want).max())
+    assert err.mean() <= 0.01 * max(1e-3, np.abs(want).mean()) + 2e-3
+    ctx.close()
+
+
+def test_full_width_networks_once():
+    """The real MuseTalk widths (UNet 320/640/1280/1280 with head_dim 40 -> padded 48, sd-vae 128/256/512/512), B = 1."""
+    from livetalking_b200 import engine
+    from livetalking_b200.musetalk import MuseTalkModel, MuseTalkSession
+    from livetalking_b200.ops import Ctx
+    from oracle import musetalk_ref as M
+    from oracle.wav2lip_ref import psnr_u8
+    engine.set_device(0)
+    us = M.synth_unet_state_dict(M.UNET_FULL, fast=True)
+    vs = M.synth_vae_state_dict(M.VAE_FULL, fast=True)
+    assert M.count_params(us) == 849_947_844 and M.count_params(vs) == 83_653_863     # published parameter counts
+    lat, aud = M.synth_latents_and_audio(1, seed=9)
+    pred = M.unet_forward(us, M.UNET_FULL, lat, M.positional_encoding(aud))
+    want_u8 = M.decode_latents_u8(vs, M.VAE_FULL, pred)
+    ctx = Ctx()
+    model = MuseTalkModel(ctx, us, vs, M.UNET_FULL, M.VAE_FULL, with_encoder=False)
+    av, *_ = _avatar(ctx, lat.numpy(), 1)
+    s = MuseTalkSession(model, av, 1)
+    got_u8 = s.infer(0, aud.numpy())
+    got_lat = ctx.download(s.pred16).astype(np.float32)[..., :4]
+    want_lat = pred.permute(0, 2, 3, 1).numpy()
+    assert np.abs(got_lat - want_lat).max() <= 0.08 * max(1.0, np.abs(want_lat).max())
+    assert psnr_u8(got_u8, want_u8) >= 40.0, psnr_u8(got_u8, want_u8)
+    ctx.close()
