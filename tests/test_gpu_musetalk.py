@@ -74,7 +74,8 @@ def test_small_unet_vae_decode_parity_and_blend(small_nets):
     # replay determinism + mirror index gather (index 1 -> latents [1, 1 mirrored -> 0]... with n=2: idx 1, then 1 (turn 1: 2-0-1))
     again = s.infer(0, aud.numpy())           # graph replay; GroupNorm statistics use float atomics -> last-bit jitter only
     assert np.abs(again.astype(int) - got_u8.astype(int)).max() <= 2 and psnr_u8(again, got_u8) >= 55.0
-    # paste-back: bit-exact blend of the engine's own prediction
+    # paste-back: bit-exact blend of the engine's own (latest) prediction
+    got_u8 = again
     for slot in range(B):
         idx = P.mirror_index(B, slot)
         got = s.paste(slot, idx)
