@@ -175,6 +175,15 @@ int ltb_op_vae_post(ltb_ctx* c, const void* x, long long npix, int Ctot, void* o
 int ltb_op_vae_pre(ltb_ctx* c, const void* img_u8, int N, int H, int W, int half_mask, void* out);
 /* out[i] = table[mirror_index(n, *d_index + i)], i < B  (latent gather of MuseReal.inference_batch, musetalk_avatar.py:134-139) */
 int ltb_op_gather_rows(ltb_ctx* c, const void* table, int n, const void* d_index, int B, long long row_elems, void* out);
+/* transformers.WhisperFeatureExtractor as used by Audio2Feature.audio2feat (avatars/musetalk/whisper/audio2feature.py:106-111):
+ * float32 PCM [n <= 480000] -> log-mel features; out_f16 = fp16 [3000][80] (conv1 input), out_f32 (optional) = float [80][3000].
+ * fb_f32: the 80 x 201 Slaney mel filterbank; logspec_ws: >= 80*3000 floats; gmax_ws: one int. */
+int ltb_op_whisper_logmel(ltb_ctx* c, const void* pcm_f32, int n, const void* fb_f32, void* logspec_ws, void* gmax_ws, void* out_f16,
+                          void* out_f32);
+/* WhisperASR._feature2chunks / BaseASR._get_sliced_feature (avatars/audio_features/whisper.py:35-56, base_asr.py:91-133):
+ * frame i <- encoder steps int((i+start)*mult) + 0..9 (clamped) of the 5 hidden states -> out[i][50 rows][D]. */
+int ltb_op_whisper_slice(ltb_ctx* c, const void* const* hidden5, int T, int D, int B, float start, float mult, void* out,
+                         int out_rows_per_frame);
 /* MuseReal.paste_back_frame + get_image_blending (avatars/musetalk_avatar.py:154-164, avatars/musetalk/myutil.py:4-25) */
 typedef struct ltb_mt_paste_op {
   const void* frames; const void* coords; const void* crop; const void* masks; const void* mask_off; const void* pred; void* out;

@@ -23,6 +23,12 @@ cudaError_t launch_vae_post(const __half* x, size_t npix, int Ctot, uint8_t* out
 cudaError_t launch_vae_pre(const uint8_t* img, int N, int H, int W, int half_mask, __half* out, cudaStream_t st);
 cudaError_t launch_gather_rows(const __half* table, int n, const int* d_index, int B, size_t row_elems, __half* out, cudaStream_t st);
 
+// Whisper front-end (whisper.cu)
+cudaError_t launch_whisper_logmel(const float* pcm, int n, const float* fb, float* logspec_ws, int* gmax, __half* out16, float* out32,
+                                  cudaStream_t st);
+cudaError_t launch_whisper_slice(const __half* const* hidden5, int T, int D, int B, float start, float mult, __half* out,
+                                 int out_rows_per_frame, cudaStream_t st);
+
 // MuseTalk paste-back (mt_paste.cu): resize + insert + blendLinear, `count` frames per launch
 struct MtPasteArgs {
   const uint8_t* frames;     // [nf,H,W,3]

@@ -170,31 +170,36 @@ class Builder:
         skip = self.linear(x, r.shortcut) if r.shortcut is not None else x
         return self.conv3(h, r.conv2, res=skip)
 
-    def attention(self, a: _Attn, xq: DevTensor, B: int, nq: int, res: DevTensor, kv_src: Optional[DevTensor] = None, n_keys: Optional[int] = None,
+    def attention(self, a, xq: DevTensor, B: int, nq: int, res: DevTensor, kv_src: Optional[DevTensor] = None, n_keys: Optional[int] = None,
                   n_valid: Optional[int] = None):
-        """xq: (B*nq, C) normalised tokens.  Self-attention when kv_src is None, else keys/values from kv_src (B*n_keys, kv_dim)."""
+        """xq: (B*nq, C) normalised tokens.  Self-attention when kv_src is None, else keys/values from kv_src (B*n_keys, kv_dim).
+        Key counts are padded to a multiple of 16 (tensor-core N / K granularity); padded keys get probability 0."""
         ctx, H, dp, d = self.ctx, a.heads, a.dp, a.d
         Hdp = H * dp
         if a.self_attn:
-            qkv = self.linear(xq, a.qkv)                                  # (B*nq, 3*Hdp)
+            nk = _ceil16(nq)
+            valid = nq
+            if nk != nq:
+                assert B == 1, "key padding of self-attention needs per-batch row padding"
+            qkv = self.new(B * nq + (nk - nq), 3 * Hdp)                   # padded key rows stay zero
+            self.linear(xq, a.qkv, out=DevTensor(qkv.ptr, (B * nq, 3 * Hdp)))
             q_ptr, q_pitch = qkv.ptr, 3 * Hdp
             k_ptr, v_ptr, kv_pitch = qkv.offset(Hdp), qkv.offset(2 * Hdp), 3 * Hdp
-            nk = nq
-            valid = nq
+            kv_rows = nq
         else:
             q = self.linear(xq, a.q)                                      # (B*nq, Hdp)
             kv = self.linear(kv_src, a.kv)                                # (B*n_keys, 2*Hdp)
             q_ptr, q_pitch = q.ptr, Hdp
             k_ptr, v_ptr, kv_pitch = kv.ptr, kv.offset(Hdp), 2 * Hdp
-            nk, valid = n_keys, n_valid
+            nk, valid, kv_rows = n_keys, n_valid, n_keys
         S = self.new(B * H, nq, nk)
         qv = DevTensor(q_ptr, (nq, dp), pitch=q_pitch)
         sv = DevTensor(S.ptr, (nq, nk), pitch=nk)
         ctx.conv(qv, None, sv, N=1, IH=1, IW=nq, OH=1, OW=nq, cin=dp, cout=nk, w_ptr=k_ptr, ktot=kv_pitch,
-                 zbatch=B * H, zdiv=H, in_z=(nq * q_pitch, dp), w_z=(nk * kv_pitch, dp), out_z=(H * nq * nk, nq * nk))
+                 zbatch=B * H, zdiv=H, in_z=(nq * q_pitch, dp), w_z=(kv_rows * kv_pitch, dp), out_z=(H * nq * nk, nq * nk))
         ctx.softmax(S, B * H * nq, nk, valid, float(d) ** -0.5)
         VT = self.new(B * H, dp, nk)
-        ctx.transpose_heads(v_ptr, B, nk, kv_pitch, H, dp, nk, VT)
+        ctx.transpose_heads(v_ptr, B, kv_rows, kv_pitch, H, dp, nk, VT)
         O = self.new(B * nq, Hdp)
         ov = DevTensor(O.ptr, (nq, dp), pitch=Hdp)
         ctx.conv(sv, None, ov, N=1, IH=1, IW=nq, OH=1, OW=nq, cin=nk, cout=dp, w_ptr=VT.ptr, ktot=nk,
