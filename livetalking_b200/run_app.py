@@ -14,7 +14,9 @@ import sys
 def install_aliases():
     import avatars.base_avatar  # noqa: F401  (reference runtime must be importable: we are inside LiveTalking)
     for ours, theirs in (("livetalking_b200.plugin.wav2lip_avatar", "avatars.wav2lip_avatar"),
-                         ("livetalking_b200.plugin.mel_asr", "avatars.audio_features.mel")):
+                         ("livetalking_b200.plugin.mel_asr", "avatars.audio_features.mel"),
+                         ("livetalking_b200.plugin.musetalk_avatar", "avatars.musetalk_avatar"),
+                         ("livetalking_b200.plugin.whisper_asr", "avatars.audio_features.whisper")):
         sys.modules[theirs] = importlib.import_module(ours)
 
 

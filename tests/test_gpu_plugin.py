@@ -77,3 +77,48 @@ def test_lipreal_session_loop(w2l_state_dict, return_pred):
             av.paste_back_frame(pred[0], (pred[0].idx + 1) % 3)
     outs[0][:] = 0                                                                       # caller may scribble (cv2.putText)
     av.engine_session.close()
+
+
+def test_musereal_session_loop():
+    """MuseReal + WhisperASR driven like BaseAvatar's threads, small networks, vs the CPU oracle chain."""
+    stubs.install()
+    from transformers import WhisperConfig, WhisperModel
+    from livetalking_b200.plugin import musetalk_avatar as MT
+    from oracle import musetalk_ref as M
+    from oracle import paste_ref as P
+    from oracle.wav2lip_ref import psnr_u8
+    import registry
+    torch.manual_seed(1)
+    wm = WhisperModel(WhisperConfig(d_model=384, encoder_layers=4, encoder_attention_heads=6, encoder_ffn_dim=1536, decoder_layers=1,
+                                    decoder_attention_heads=6, decoder_ffn_dim=64)).eval()
+    us, vs = M.synth_unet_state_dict(M.UNET_SMALL), M.synth_vae_state_dict(M.VAE_SMALL)
+    model = MT.make_model(us, vs, wm.state_dict(), M.UNET_SMALL, M.VAE_SMALL)
+    assert len(tuple(model)) == 5                                    # the reference unpacks 5 objects from load_model()
+    B, n = 2, 3
+    rng = np.random.default_rng(8)
+    lat, _ = M.synth_latents_and_audio(n, seed=11)
+    frames = list(rng.integers(0, 256, (n, 200, 260, 3), dtype=np.uint8))
+    coords = [(60, 30, 190, 170), (50, 20, 200, 180), (70, 40, 180, 160)]
+    crops = [(30, 10, 230, 195), (20, 5, 240, 198), (40, 20, 220, 190)]
+    masks = [np.repeat((np.linspace(0, 255, (c[3] - c[1]))[:, None] * np.ones((1, c[2] - c[0]))).astype(np.uint8)[..., None], 3, 2) for c in crops]
+    avatar = MT.make_avatar(frames, masks, coords, crops, [lat[i:i + 1] for i in range(n)], model)
+    av = registry.create("avatar", "musetalk", opt=stubs.Opt(batch_size=B), model=model, avatar=avatar)
+    t = np.arange((20 + 2 * B) * 320) / 16000.0
+    audio = (0.3 * np.sin(2 * np.pi * 300 * t) + 0.05 * rng.standard_normal(t.size)).astype(np.float32)
+    for c in range(2 * B):
+        av.asr.put_audio_frame(audio[c * 320:(c + 1) * 320], {})
+    av.asr.run_step()
+    feats = av.asr.feat_queue.get(timeout=1)
+    assert len(feats) == B and feats[0].shape == (50, 384)
+    index = 1
+    pred = av.inference_batch(index, feats)
+    assert pred.shape == (B, 256, 256, 3) and pred.dtype == np.uint8
+    # oracle chain on the engine's own whisper features (the whisper path has its own parity test)
+    aud = torch.from_numpy(np.stack(feats).astype(np.float32))
+    idxs = [P.mirror_index(n, index + i) for i in range(B)]
+    want = M.decode_latents_u8(vs, M.VAE_SMALL, M.unet_forward(us, M.UNET_SMALL, lat[idxs], M.positional_encoding(aud)))
+    assert psnr_u8(pred, want) >= 40.0, psnr_u8(pred, want)
+    for i in range(B):
+        out = av.paste_back_frame(pred[i], idxs[i])
+        assert np.array_equal(out, P.mt_paste_back(pred[i], frames[idxs[i]], coords[idxs[i]], masks[idxs[i]], crops[idxs[i]]))
+        assert out.flags.writeable and out.flags.c_contiguous
