@@ -24,40 +24,66 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x))
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
-// pass 1: per (image, group) sum and sum of squares.  grid (splits, N), block 256.
-constexpr int kGNMaxPerThread = 12;  // supports C <= 3072
-__global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict__ x, int HW, int C, int Ctot, int c_off, int groups,
+// pass 1: per (image, group) sum and sum of squares.  A block is R pixel-rows x VPR 16-byte vectors (VPR = C/8): thread
+// (r, v) owns channel vector v and walks pixels r, r+R, ... of its slab, so every warp load is a contiguous run of the
+// NHWC row and the 8 per-channel partial sums stay in registers; groups are resolved once per thread at the end.
+__global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict__ x, int HW, int C, int Ctot, int c_off, int groups, int R,
                                                        float* __restrict__ stats) {
   __shared__ float s_sum[64], s_sq[64];
   const int n = blockIdx.y;
   const int cpg = C / groups;
+  const int vpr = C / 8;
   if (threadIdx.x < 64) s_sum[threadIdx.x] = s_sq[threadIdx.x] = 0.f;
   __syncthreads();
   const int per = (HW + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
-  float a[kGNMaxPerThread], b[kGNMaxPerThread];
+  const int v = threadIdx.x % vpr, r = threadIdx.x / vpr;
+  float a[8], b[8];
 #pragma unroll
-  for (int k = 0; k < kGNMaxPerThread; ++k) a[k] = b[k] = 0.f;
-  const __half* base = x + ((size_t)n * HW) * Ctot + c_off;
-  for (int p = p0; p < p1; ++p) {
-    const __half* row = base + (size_t)p * Ctot;
+  for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+  if (r < R) {
+    const __half* base = x + ((size_t)n * HW) * Ctot + c_off + v * 8;
+    int p = p0 + r;
+    // two loads in flight per thread
+    for (; p + R < p1; p += 2 * R) {
+      const uint4 u0 = *reinterpret_cast<const uint4*>(base + (size_t)p * Ctot);
+      const uint4 u1 = *reinterpret_cast<const uint4*>(base + (size_t)(p + R) * Ctot);
+      const __half* h0 = reinterpret_cast<const __half*>(&u0);
+      const __half* h1 = reinterpret_cast<const __half*>(&u1);
 #pragma unroll
-    for (int k = 0; k < kGNMaxPerThread; ++k) {
-      const int c = threadIdx.x + k * 256;
-      if (c < C) {
-        const float v = __half2float(row[c]);
-        a[k] += v;
-        b[k] += v * v;
+      for (int j = 0; j < 8; ++j) {
+        const float f0 = __half2float(h0[j]), f1 = __half2float(h1[j]);
+        a[j] += f0 + f1;
+        b[j] += f0 * f0 + f1 * f1;
       }
     }
-  }
+    for (; p < p1; p += R) {
+      const uint4 u0 = *reinterpret_cast<const uint4*>(base + (size_t)p * Ctot);
+      const __half* h0 = reinterpret_cast<const __half*>(&u0);
 #pragma unroll
-  for (int k = 0; k < kGNMaxPerThread; ++k) {
-    const int c = threadIdx.x + k * 256;
-    if (c < C) {
-      atomicAdd(&s_sum[c / cpg], a[k]);
-      atomicAdd(&s_sq[c / cpg], b[k]);
+      for (int j = 0; j < 8; ++j) {
+        const float f0 = __half2float(h0[j]);
+        a[j] += f0;
+        b[j] += f0 * f0;
+      }
     }
+    // fold the 8 channels into their groups (consecutive channels mostly share a group)
+    int g = (v * 8) / cpg;
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gj = (v * 8 + j) / cpg;
+      if (gj != g) {
+        atomicAdd(&s_sum[g], sa);
+        atomicAdd(&s_sq[g], sb);
+        sa = sb = 0.f;
+        g = gj;
+      }
+      sa += a[j];
+      sb += b[j];
+    }
+    atomicAdd(&s_sum[g], sa);
+    atomicAdd(&s_sq[g], sb);
   }
   __syncthreads();
   if (threadIdx.x < groups) {
@@ -102,16 +128,23 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
 
 cudaError_t launch_groupnorm(const __half* x, int N, int HW, int C, int Ctot, int c_off, int groups, float eps, const float* gamma,
                              const float* beta, int silu, __half* out, int OCtot, int oc_off, float* stats_ws, cudaStream_t st) {
-  if (C % groups != 0 || C % 8 != 0 || groups > 64 || C > 256 * kGNMaxPerThread) return cudaErrorInvalidValue;
+  if (C % groups != 0 || C % 8 != 0 || groups > 64 || C / 8 > 512 || (Ctot % 8) || (c_off % 8)) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(stats_ws, 0, (size_t)N * groups * 2 * sizeof(float), st);
   if (e != cudaSuccess) return e;
-  int splits = (HW * C) / (64 * 1024);
-  splits = splits < 1 ? 1 : (splits > 64 ? 64 : splits);
-  if (splits > HW) splits = HW;
-  gn_stats_kernel<<<dim3(splits, N), 256, 0, st>>>(x, HW, C, Ctot, c_off, groups, stats_ws);
+  const int vpr = C / 8;
+  int R = 512 / vpr;
+  if (R > HW) R = HW;
+  const int threads = ((R * vpr + 31) / 32) * 32;
+  // enough blocks to fill the chip, but keep >= 4 pixels per thread-row
+  int splits = (592 + N - 1) / N;
+  const int max_splits = (HW + 4 * R - 1) / (4 * R);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  gn_stats_kernel<<<dim3(splits, N), threads, 0, st>>>(x, HW, C, Ctot, c_off, groups, R, stats_ws);
   const size_t total_vec = (size_t)HW * (C / 8);
   int blocks = (int)((total_vec + 255) / 256);
-  if (blocks > 296) blocks = 296;
+  const int cap = (1184 + N - 1) / N;
+  if (blocks > cap) blocks = cap;
   gn_apply_kernel<<<dim3(blocks, N), 256, 0, st>>>(x, HW, C, Ctot, c_off, groups, eps, stats_ws, gamma, beta, silu, out, OCtot, oc_off,
                                                    total_vec);
   return cudaGetLastError();
