@@ -257,7 +257,7 @@ def run_ours(args):
         passes = [sess.profile_ops(idx)[0] for _ in range(3)]
         ms_ops, flops, kinds = sess.profile_ops(idx)
         med = np.median(np.stack(passes + [ms_ops]), axis=0)
-        conv = (kinds == 0) | (kinds == 4)
+        conv = (kinds == 0) | (kinds == 4) | (kinds == 5)
         conv_ms = float(med[conv].sum())
         algo_flops = GFLOP_PER_FRAME * 1e9 * BATCH            # per step (all conv launches of one step)
         achieved = algo_flops / (conv_ms / 1000.0) / 1e12

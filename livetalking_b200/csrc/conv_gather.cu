@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(160) conv_gather_umma_kernel(const __grid_cons
   const int lane = tid & 31;
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
-  const int zphase = (p.zbatch > 1) ? (int)(blockIdx.z % p.nphases) : (int)blockIdx.z;
+  const int zphase = (p.ksplit > 1) ? 0 : ((p.zbatch > 1) ? (int)(blockIdx.z % p.nphases) : (int)blockIdx.z);
   const ConvPhase& ph = p.ph[zphase];
   const __half* in_base = p.in;
   const __half* w_base = p.w;
@@ -69,7 +69,12 @@ __global__ void __launch_bounds__(160) conv_gather_umma_kernel(const __grid_cons
   const int m0 = blockIdx.x * 128;
   const int n0 = blockIdx.y * BN;
   const int cpt = p.Cin / KB;  // K chunks per tap
-  const int kiters = ph.ntaps * cpt;
+  int it_begin = 0, kiters = ph.ntaps * cpt;
+  if (p.ksplit > 1) {  // split-K: this CTA owns K iterations [it_begin, it_begin + kiters)
+    const int per = (kiters + p.ksplit - 1) / p.ksplit;
+    it_begin = (int)blockIdx.z * per;
+    kiters = min(per, kiters - it_begin);
+  }
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(160) conv_gather_umma_kernel(const __grid_cons
         rix[i] = 0;
       }
     }
-    int tap = 0, cc = 0;
+    int tap = it_begin / cpt, cc = it_begin % cpt;
     for (int it = 0; it < kiters; ++it) {
       const int stage = it % C::STAGES;
       mbar_wait(smem_u32(&bar_empty[stage]), (((uint32_t)it / C::STAGES) & 1u) ^ 1u);
@@ -176,7 +181,14 @@ __global__ void __launch_bounds__(160) conv_gather_umma_kernel(const __grid_cons
         tmem_ld16(trow + c0, reinterpret_cast<uint32_t(&)[16]>(v));
       }
       tmem_ld_wait();
-      if (valid) {
+      if (valid && p.ksplit > 1) {
+        // split-K: this CTA's fp32 partial goes to its own slice ws[split][m][co] (plain 16-byte stores, no atomics)
+        float4* wrow = reinterpret_cast<float4*>(p.ws + ((size_t)blockIdx.z * p.M + m) * p.Cout + n0 + c0);
+#pragma unroll
+        for (int g = 0; g < CW / 4; ++g)
+          wrow[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                                __uint_as_float(v[4 * g + 3]));
+      } else if (valid) {
 #pragma unroll
         for (int g = 0; g < CW; g += 8) {
           float f[8];
@@ -258,7 +270,7 @@ static cudaError_t launch_one(const ConvParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid((p.M + 127) / 128, p.Cout / BN, p.nphases * (p.zbatch > 1 ? p.zbatch : 1));
+  dim3 grid((p.M + 127) / 128, p.Cout / BN, p.ksplit > 1 ? p.ksplit : p.nphases * (p.zbatch > 1 ? p.zbatch : 1));
   conv_gather_umma_kernel<BN, KB><<<grid, 160, C::SMEM_BYTES, st>>>(p);
   return cudaGetLastError();
 }
@@ -289,16 +301,90 @@ int conv_gather_pick_bn(const ConvParams& p) {
   return bn;
 }
 
-cudaError_t launch_conv_gather(const ConvParams& p, cudaStream_t st) {
+// out[m, co] = act(sum_s ws[s][m][co] + bias[co] (+ res))
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __restrict__ ws, int ksplit, int M, int Cout,
+                                                              const float* __restrict__ bias, const __half* __restrict__ res, int RCtot,
+                                                              int rc_off, int relu, __half* __restrict__ out, int OCtot, int oc_off) {
+  const int vpr = Cout / 8;
+  const size_t total = (size_t)M * vpr;
+  const size_t slice = (size_t)M * Cout;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const size_t m = i / vpr;
+    const int c = (int)(i % vpr) * 8;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = __ldg(bias + c + j);
+    for (int s = 0; s < ksplit; ++s) {
+      const float4* w4 = reinterpret_cast<const float4*>(ws + s * slice + m * Cout + c);
+      const float4 a = w4[0], b = w4[1];
+      f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w;
+      f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+    }
+    if (res) {
+      const uint4 rv = *reinterpret_cast<const uint4*>(res + m * RCtot + rc_off + c);
+      const __half* rh = reinterpret_cast<const __half*>(&rv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += __half2float(rh[j]);
+    }
+    uint4 ov;
+    __half* oh = reinterpret_cast<__half*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float x = relu ? fmaxf(f[j], 0.f) : f[j];
+      oh[j] = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+    }
+    *reinterpret_cast<uint4*>(out + m * OCtot + oc_off + c) = ov;
+  }
+}
+
+cudaError_t launch_conv_gather(const ConvParams& p_in, cudaStream_t st, float* splitk_ws, size_t splitk_ws_floats) {
+  ConvParams p = p_in;
   if (p.Cout % 16 != 0 || p.Cin % 16 != 0 || (p.ICtot % 8) || (p.OCtot % 8) || (p.ic_off % 8) || (p.oc_off % 8) ||
       (p.Ktot % 8) || p.nphases < 1 || p.nphases > kMaxPhases)
     return cudaErrorInvalidValue;
   if (p.res && ((p.RCtot % 8) || (p.rc_off % 8))) return cudaErrorInvalidValue;
-  const int bn = conv_gather_pick_bn(p);
+  int bn = conv_gather_pick_bn(p);
   if (!bn) return cudaErrorInvalidValue;
-  if (p.Cin % 64 == 0) return launch_kb<64>(p, bn, st);
-  if (p.Cin % 32 == 0) return launch_kb<32>(p, bn, st);
-  return launch_kb<16>(p, bn, st);
+  const int kb = (p.Cin % 64 == 0) ? 64 : (p.Cin % 32 == 0) ? 32 : 16;
+  // split-K for small-M, deep-K layers (1x1..8x8 maps with 512..2560 channels): they are weight-streaming bound and a
+  // handful of CTAs walking thousands of K blocks serially is latency-bound.
+  p.ksplit = 0;
+  p.ws = nullptr;
+  const int kiters = p.ph[0].ntaps * (p.Cin / kb);
+  const long mt = (p.M + 127) / 128;
+  if (splitk_ws && p.nphases == 1 && p.zbatch <= 1 && p.osy == 1 && p.osx == 1 && p.GH == p.OH && p.GW == p.OW && kiters >= 32 && mt <= 8) {
+    int bn2 = 0;
+    for (int c : {128, 64, 32, 16})
+      if (p.Cout % c == 0) {
+        bn2 = c;
+        break;
+      }
+    const long tiles = mt * (p.Cout / bn2);
+    if (tiles < 64) {
+      int ks = (int)((296 + tiles - 1) / tiles);
+      if (ks > kiters / 8) ks = kiters / 8;   // >= 8 K blocks per split
+      if (ks > 32) ks = 32;
+      while (ks >= 2 && (size_t)ks * p.M * p.Cout > splitk_ws_floats) --ks;
+      if (ks >= 2) {
+        const int per = (kiters + ks - 1) / ks;
+        ks = (kiters + per - 1) / per;  // no empty splits
+        p.ksplit = ks;
+        p.ws = splitk_ws;
+        bn = bn2;
+      }
+    }
+  }
+  cudaError_t e;
+  if (kb == 64) e = launch_kb<64>(p, bn, st);
+  else if (kb == 32) e = launch_kb<32>(p, bn, st);
+  else e = launch_kb<16>(p, bn, st);
+  if (e != cudaSuccess || p.ksplit <= 1) return e;
+  const size_t total = (size_t)p.M * (p.Cout / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 592) blocks = 592;
+  splitk_finalize_kernel<<<blocks, 256, 0, st>>>(p.ws, p.ksplit, p.M, p.Cout, p.bias, p.res, p.RCtot, p.rc_off, p.relu, p.out, p.OCtot,
+                                                 p.oc_off);
+  return cudaGetLastError();
 }
 
 }  // namespace ltb

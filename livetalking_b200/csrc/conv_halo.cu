@@ -10,7 +10,7 @@
 // Compared with one tile load per tap this cuts L2->SM operand traffic for A by 6.4x; weights are streamed 3 taps at a
 // time and amortised over NSUB=2 stacked 128-pixel sub-tiles (M = 256 per CTA).
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue
 // (TMEM -> registers -> +bias (+residual) -> ReLU -> fp16 NHWC channel slice).  Persistent CTAs, double-buffered TMEM
 // accumulators: the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
@@ -44,7 +44,7 @@ struct HaloCfg {
 };
 
 template <int BN, int NSUB, int NACC>
-__global__ void __launch_bounds__(192, 1) conv_halo_umma_kernel(const __grid_constant__ HaloParams p) {
+__global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_constant__ HaloParams p) {
   using C = HaloCfg<BN, NSUB, NACC>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[C::A_STAGES], a_empty[C::A_STAGES];
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(192, 1) conv_halo_umma_kernel(const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&acc_full[s]), 1);
-      mbar_init(smem_u32(&acc_empty[s]), 4);
+      mbar_init(smem_u32(&acc_empty[s]), 8);
     }
     mbar_fence_init();
     tma_prefetch_desc(&p.tm_in);
@@ -163,8 +163,11 @@ __global__ void __launch_bounds__(192, 1) conv_halo_umma_kernel(const __grid_con
     }
     __syncwarp();
   } else {
-    // =============================================================== epilogue (warps 2..5 -> TMEM lane quarter warp%4)
+    // =============================================================== epilogue (warps 2..9 -> TMEM lane quarter warp%4).
+    // Two warps per quarter (one per 32-column chunk parity): with a single warp per scheduler the epilogue was
+    // issue-latency bound on the narrow HBM-bound layers (ncu: 32 % tensor, 22 % DRAM, IPC 0.2 per warp).
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
     const int row = q * 32 + lane;       // 0..127 inside a sub-tile
     const int ry = row >> 3, rx = row & 7;
     uint32_t it = 0;
@@ -189,45 +192,32 @@ __global__ void __launch_bounds__(192, 1) conv_halo_umma_kernel(const __grid_con
           const __half* rptr = p.res ? (p.res + opix * p.RCtot + p.rc_off + n0) : nullptr;
 #pragma unroll 1
           for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (((((acc * NSUB + sub) * BN + c0) >> 5) & 1) != grp) continue;
             uint32_t v[32];
             tmem_ld32(tbase + (acc * NSUB + sub) * BN + c0, v);
             tmem_ld_wait();
 #pragma unroll
             for (int g = 0; g < 32; g += 8) {
-              float f[8];
+              // packed-half epilogue (the narrow layers are epilogue-issue bound): fp32 accumulator + fp32 bias -> half2,
+              // then residual add / ReLU / saturation as half2 ops (3 instructions per element instead of 8)
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + g));
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + g + 4));
-              f[0] = __uint_as_float(v[g + 0]) + b0.x;
-              f[1] = __uint_as_float(v[g + 1]) + b0.y;
-              f[2] = __uint_as_float(v[g + 2]) + b0.z;
-              f[3] = __uint_as_float(v[g + 3]) + b0.w;
-              f[4] = __uint_as_float(v[g + 4]) + b1.x;
-              f[5] = __uint_as_float(v[g + 5]) + b1.y;
-              f[6] = __uint_as_float(v[g + 6]) + b1.z;
-              f[7] = __uint_as_float(v[g + 7]) + b1.w;
+              uint4 ov;
+              __half2* oh = reinterpret_cast<__half2*>(&ov);
+              oh[0] = __floats2half2_rn(__uint_as_float(v[g + 0]) + b0.x, __uint_as_float(v[g + 1]) + b0.y);
+              oh[1] = __floats2half2_rn(__uint_as_float(v[g + 2]) + b0.z, __uint_as_float(v[g + 3]) + b0.w);
+              oh[2] = __floats2half2_rn(__uint_as_float(v[g + 4]) + b1.x, __uint_as_float(v[g + 5]) + b1.y);
+              oh[3] = __floats2half2_rn(__uint_as_float(v[g + 6]) + b1.z, __uint_as_float(v[g + 7]) + b1.w);
               if (rptr) {
                 const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rptr + c0 + g));
                 const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float2 rf = __half22float2(rh[u]);
-                  f[2 * u] += rf.x;
-                  f[2 * u + 1] += rf.y;
-                }
+                for (int u = 0; u < 4; ++u) oh[u] = __hadd2(oh[u], rh[u]);
               }
-              uint4 ov;
-              __half2* oh = reinterpret_cast<__half2*>(&ov);
+              const __half2 hmax = __floats2half2_rn(65504.f, 65504.f);
+              const __half2 lo = p.relu ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(-65504.f, -65504.f);
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                float x = f[2 * u], y = f[2 * u + 1];
-                if (p.relu) {
-                  x = fmaxf(x, 0.f);
-                  y = fmaxf(y, 0.f);
-                }
-                x = fminf(fmaxf(x, -65504.f), 65504.f);
-                y = fminf(fmaxf(y, -65504.f), 65504.f);
-                oh[u] = __floats2half2_rn(x, y);
-              }
+              for (int u = 0; u < 4; ++u) oh[u] = __hmin2(__hmax2(oh[u], lo), hmax);
               *reinterpret_cast<uint4*>(optr + c0 + g) = ov;
             }
           }
@@ -385,7 +375,7 @@ static cudaError_t launch_cfg(const HaloPlan& pl, int sms, cudaStream_t st) {
     configured = true;
   }
   const int grid = pl.hp.total_tiles < sms ? pl.hp.total_tiles : sms;
-  conv_halo_umma_kernel<BN, NSUB, NACC><<<grid, 192, C::SMEM_BYTES, st>>>(pl.hp);
+  conv_halo_umma_kernel<BN, NSUB, NACC><<<grid, 320, C::SMEM_BYTES, st>>>(pl.hp);
   return cudaGetLastError();
 }
 
@@ -411,20 +401,20 @@ cudaError_t launch_conv_halo(const HaloPlan& pl, cudaStream_t st) {
   return cudaErrorInvalidValue;
 }
 
-// [Cout][9][Cin] -> [9][Cout][Cin] (one-off, at model load)
-__global__ void w_tap_major_kernel(const __half* __restrict__ w, __half* __restrict__ wt, int cout, int cin) {
+// [Cout][ntaps][Cin] -> [ntaps][Cout][Cin] (one-off, at model load)
+__global__ void w_tap_major_kernel(const __half* __restrict__ w, __half* __restrict__ wt, int cout, int cin, int ntaps) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)cout * 9 * cin;
+  const size_t total = (size_t)cout * ntaps * cin;
   if (i >= total) return;
   const int ci = (int)(i % cin);
-  const int tap = (int)((i / cin) % 9);
-  const int co = (int)(i / ((size_t)cin * 9));
+  const int tap = (int)((i / cin) % ntaps);
+  const int co = (int)(i / ((size_t)cin * ntaps));
   wt[((size_t)tap * cout + co) * cin + ci] = w[i];
 }
 
-cudaError_t launch_w_tap_major(const __half* w, __half* wt, int cout, int cin, cudaStream_t st) {
-  const size_t total = (size_t)cout * 9 * cin;
-  w_tap_major_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, wt, cout, cin);
+cudaError_t launch_w_tap_major(const __half* w, __half* wt, int cout, int cin, cudaStream_t st, int ntaps) {
+  const size_t total = (size_t)cout * ntaps * cin;
+  w_tap_major_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, wt, cout, cin, ntaps);
   return cudaGetLastError();
 }
 

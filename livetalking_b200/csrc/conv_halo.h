@@ -36,6 +36,6 @@ bool conv_halo_supported(const ConvParams& p);
 // w_tap_major: device pointer to the [9][Cout][Cin] copy of the layer's weights. returns 0 on success.
 int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan* out);
 cudaError_t launch_conv_halo(const HaloPlan& pl, cudaStream_t st);
-cudaError_t launch_w_tap_major(const __half* w, __half* wt, int cout, int cin, cudaStream_t st);
+cudaError_t launch_w_tap_major(const __half* w, __half* wt, int cout, int cin, cudaStream_t st, int ntaps = 9);
 
 }  // namespace ltb

@@ -47,6 +47,10 @@ struct ConvParams {
   // the in / w / out (/ res) base pointers.  zbatch <= 1 disables.
   int zbatch, zdiv;
   long long in_zo, in_zi, w_zo, w_zi, out_zo, out_zi;
+  // optional split-K (small-M, weight-heavy layers): grid.z = ksplit CTAs each reduce a slice of the K loop and store
+  // their fp32 partial tile to ws[split][M][Cout]; splitk_finalize sums the slices and applies bias/residual/activation.
+  int ksplit;
+  float* ws;
 };
 
 }  // namespace ltb

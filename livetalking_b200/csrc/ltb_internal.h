@@ -21,7 +21,8 @@ int fail(const char* file, int line, const std::string& msg);
   } while (0)
 
 // ---- kernel launchers ----
-cudaError_t launch_conv_gather(const ConvParams& p, cudaStream_t st);
+// splitk_ws: optional zero-initialised fp32 workspace (one per stream) enabling split-K for small-M deep-K layers
+cudaError_t launch_conv_gather(const ConvParams& p, cudaStream_t st, float* splitk_ws = nullptr, size_t splitk_ws_floats = 0);
 int conv_gather_pick_bn(const ConvParams& p);
 
 // wav2lip-specific small kernels (w2l_small.cu)

@@ -92,11 +92,13 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict_
   }
 }
 
-// pass 2: normalise + affine (+SiLU); one thread = 8 channels of one pixel.
+// pass 2: y = x * a[c] + b[c] (+SiLU) with a = rstd*gamma, b = beta - mean*rstd*gamma staged per image in shared memory;
+// one thread = 8 channels of one pixel (16-byte loads/stores), channel vector fixed per thread.
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, int HW, int C, int Ctot, int c_off, int groups,
                                                        float eps, const float* __restrict__ stats, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, int silu, __half* __restrict__ out, int OCtot,
                                                        int oc_off, size_t total_vec) {
+  extern __shared__ float s_ab[];  // [2][C]
   __shared__ float s_mean[64], s_rstd[64];
   const int n = blockIdx.y;
   const int cpg = C / groups;
@@ -108,20 +110,34 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
     s_rstd[threadIdx.x] = rsqrtf(v + eps);
   }
   __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int g = c / cpg;
+    const float a = s_rstd[g] * gamma[c];
+    s_ab[c] = a;
+    s_ab[C + c] = beta[c] - s_mean[g] * a;
+  }
+  __syncthreads();
   const int vpr = C / 8;  // vectors per pixel
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * 256) {
-    const int p = (int)(i / vpr), cv = (int)(i % vpr) * 8;
+    const int p = (int)(i / vpr), cv = (int)(i - (size_t)p * vpr) * 8;
     const uint4 v = *reinterpret_cast<const uint4*>(x + ((size_t)n * HW + p) * Ctot + c_off + cv);
-    const __half* h = reinterpret_cast<const __half*>(&v);
-    uint4 o;
-    __half* oh = reinterpret_cast<__half*>(&o);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+    const float4 a0 = *reinterpret_cast<const float4*>(s_ab + cv), a1 = *reinterpret_cast<const float4*>(s_ab + cv + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(s_ab + C + cv), b1 = *reinterpret_cast<const float4*>(s_ab + C + cv + 4);
+    float y[8];
+    float2 t;
+    t = __half22float2(h[0]); y[0] = fmaf(t.x, a0.x, b0.x); y[1] = fmaf(t.y, a0.y, b0.y);
+    t = __half22float2(h[1]); y[2] = fmaf(t.x, a0.z, b0.z); y[3] = fmaf(t.y, a0.w, b0.w);
+    t = __half22float2(h[2]); y[4] = fmaf(t.x, a1.x, b1.x); y[5] = fmaf(t.y, a1.y, b1.y);
+    t = __half22float2(h[3]); y[6] = fmaf(t.x, a1.z, b1.z); y[7] = fmaf(t.y, a1.w, b1.w);
+    if (silu) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = cv + j, g = c / cpg;
-      float y = (__half2float(h[j]) - s_mean[g]) * s_rstd[g] * __ldg(gamma + c) + __ldg(beta + c);
-      if (silu) y = silu_f(y);
-      oh[j] = __float2half_rn(y);
+      for (int j = 0; j < 8; ++j) y[j] = silu_f(y[j]);
     }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
     *reinterpret_cast<uint4*>(out + ((size_t)n * HW + p) * OCtot + oc_off + cv) = o;
   }
 }
@@ -145,8 +161,8 @@ cudaError_t launch_groupnorm(const __half* x, int N, int HW, int C, int Ctot, in
   int blocks = (int)((total_vec + 255) / 256);
   const int cap = (1184 + N - 1) / N;
   if (blocks > cap) blocks = cap;
-  gn_apply_kernel<<<dim3(blocks, N), 256, 0, st>>>(x, HW, C, Ctot, c_off, groups, eps, stats_ws, gamma, beta, silu, out, OCtot, oc_off,
-                                                   total_vec);
+  gn_apply_kernel<<<dim3(blocks, N), 256, 2 * C * sizeof(float), st>>>(x, HW, C, Ctot, c_off, groups, eps, stats_ws, gamma, beta, silu, out,
+                                                                        OCtot, oc_off, total_vec);
   return cudaGetLastError();
 }
 

@@ -20,6 +20,7 @@ struct ltb_ctx {
   std::vector<void*> allocs;
   float* zero_bias = nullptr;   // 16384 zeros (bias of bias-free GEMMs)
   float* gn_ws = nullptr;       // GroupNorm statistics workspace
+  float* splitk_ws = nullptr;   // fp32 split-K workspace (zero between uses)
   long long launches = 0;
   bool capturing = false;
   long long capture_launches = 0;
@@ -32,6 +33,7 @@ struct ltb_graph {
 
 static const int kZeroBias = 16384;
 static const int kGnWsFloats = 64 * 64 * 2;
+static const size_t kSplitKWsFloats = (size_t)16 << 20;  // ksplit * M * Cout floats
 
 extern "C" {
 
@@ -43,6 +45,8 @@ int ltb_ctx_create(ltb_ctx** out) {
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->zero_bias), kZeroBias * sizeof(float));
   if (e == cudaSuccess) e = cudaMemset(c->zero_bias, 0, kZeroBias * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->gn_ws), kGnWsFloats * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->splitk_ws), kSplitKWsFloats * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(c->splitk_ws, 0, kSplitKWsFloats * sizeof(float));
   if (e != cudaSuccess) {
     delete c;
     return LTB_FAIL(std::string("ctx create: ") + cudaGetErrorString(e));
@@ -57,6 +61,7 @@ int ltb_ctx_destroy(ltb_ctx* c) {
   for (void* p : c->allocs) cudaFree(p);
   cudaFree(c->zero_bias);
   cudaFree(c->gn_ws);
+  cudaFree(c->splitk_ws);
   cudaStreamDestroy(c->st);
   delete c;
   return 0;
@@ -211,7 +216,7 @@ int ltb_op_conv2d(ltb_ctx* c, const ltb_conv_op* d) {
     if (conv_halo_make_plan(p, static_cast<const __half*>(d->w_tap), &pl) != 0) return LTB_FAIL("conv2d: tensor map creation failed");
     e = launch_conv_halo(pl, c->st);
   } else {
-    e = launch_conv_gather(p, c->st);
+    e = launch_conv_gather(p, c->st, c->splitk_ws, kSplitKWsFloats);
   }
   if (e != cudaSuccess) return LTB_FAIL(std::string("conv2d launch: ") + cudaGetErrorString(e));
   c->launches += 1;

@@ -18,6 +18,7 @@
 #include "../../include/ltb200.h"
 #include "conv_halo.h"
 #include "ltb_internal.h"
+#include "stem_umma.h"
 
 namespace ltb {
 
@@ -67,6 +68,7 @@ static const LDef kLayers[54] = {
     {'c', 80, 32, 3, 1, 1, 1, false},
 };
 constexpr int kNumLayers = 54;
+constexpr size_t kSplitKFloats = (size_t)8 << 20;  // 8M floats: ksplit * M * Cout of the small-spatial layers (<= 10 x 1024 x 512)
 constexpr int kStem = 13, kConvT4 = 34;
 
 // expected packed sizes (elements) of layer i's weight matrix [rows][K]
@@ -197,7 +199,7 @@ struct Tensor {
   int H = 0, W = 0, C = 0;  // C = pixel pitch (total channels)
 };
 struct Op {
-  int type;  // 0 = conv (gather kernel), 1 = prep, 2 = audio conv0, 3 = head, 4 = conv (halo kernel)
+  int type;  // 0 = conv (gather kernel), 1 = prep, 2 = audio conv0, 3 = head, 4 = conv (halo kernel), 5 = stem (tensor-core)
   ConvParams cp;
   int halo = -1;    // index into the session's halo plans (type 4)
   int branch = 0;   // 1 = audio-encoder branch: runs on the side stream, concurrently with the face encoder
@@ -227,8 +229,10 @@ struct ltb_w2l_session {
   float* pred_scratch = nullptr;  // one host-supplied prediction (ltb_w2l_paste_pred)
   uint8_t* frames_out = nullptr;
   int* d_index = nullptr;
+  float* splitk_ws[2] = {nullptr, nullptr};  // one fp32 split-K workspace per stream (main, audio branch)
   std::vector<Op> ops;
   std::vector<HaloPlan> halo_plans;
+  StemParams stem;
   LayerOut louts[kNumLayers];
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
@@ -488,7 +492,13 @@ static int build_plan(ltb_w2l_session* s) {
       p.ph[0].dy[t] = (signed char)t;
       p.ph[0].dx[t] = 0;
     }
-    push_conv(kStem, p);
+    Op so;
+    so.type = 0;
+    so.cp = p;
+    if (!(s->flags & LTB_SESSION_NO_HALO) && m->wt[kStem] &&
+        stem_make_plan(s->img_pad, B, m->wt[kStem], m->bias[kStem], out.p, out.Ctot, out.c_off, &s->stem) == 0)
+      so.type = 5;
+    s->ops.push_back(so);
     record(kStem, out);
   }
   {
@@ -570,6 +580,7 @@ static const char* op_name(const Op& o) {
     case 2: return "audio_conv0";
     case 3: return "head";
     case 4: return "conv_halo";
+    case 5: return "stem_umma";
   }
   return "?";
 }
@@ -598,11 +609,12 @@ static int run_ops(ltb_w2l_session* s, cudaEvent_t* events = nullptr) {
     }
     cudaError_t e = cudaSuccess;
     switch (o.type) {
-      case 0: e = launch_conv_gather(o.cp, st); break;
+      case 0: e = launch_conv_gather(o.cp, st, s->splitk_ws[st == s->st2 ? 1 : 0], kSplitKFloats); break;
       case 1: e = launch_w2l_prep_faces(s->a->faces, s->a->n, s->d_index, s->B, s->img_pad, st); break;
       case 2: e = launch_w2l_audio_conv0(s->mel, s->m->w0, s->m->bias[0], o.cp.out, s->B, st); break;
       case 3: e = launch_w2l_head(o.cp.in, s->m->head_w, s->m->head_b, s->pred, s->B * 65536, st); break;
       case 4: e = launch_conv_halo(s->halo_plans[o.halo], st); break;
+      case 5: e = launch_stem(s->stem, st); break;
     }
     if (e != cudaSuccess) return LTB_FAIL(std::string("kernel launch failed (") + op_name(o) + "): " + cudaGetErrorString(e));
     ++i;
@@ -665,6 +677,14 @@ static int model_from(ltb_w2l_model* m, const uint8_t* header_host, size_t nbyte
     if (e != cudaSuccess) {
       model_free(m);
       return LTB_FAIL(std::string("tap-major weight copy: ") + cudaGetErrorString(e));
+    }
+  }
+  {  // stem: [16][7][64] -> [7][16][64]
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->wt[kStem]), (size_t)16 * 7 * 64 * 2);
+    if (e == cudaSuccess) e = launch_w_tap_major(m->w[kStem], m->wt[kStem], 16, 64, nullptr, 7);
+    if (e != cudaSuccess) {
+      model_free(m);
+      return LTB_FAIL(std::string("stem weight copy: ") + cudaGetErrorString(e));
     }
   }
   if (cudaDeviceSynchronize() != cudaSuccess) {
@@ -801,6 +821,10 @@ int ltb_w2l_session_create(ltb_w2l_model* m, ltb_w2l_avatar* a, int batch, int s
   s->frames_out = static_cast<uint8_t*>(p);
   if (dev_alloc(s, 256, &p, true)) return bail(1);
   s->d_index = static_cast<int*>(p);
+  for (int i = 0; i < 2; ++i) {
+    if (dev_alloc(s, kSplitKFloats * sizeof(float), &p, true)) return bail(1);
+    s->splitk_ws[i] = static_cast<float*>(p);
+  }
   if (build_plan(s)) return bail(1);
   // warm-up (also the reference's warm_up, wav2lip_avatar.py:90-96): one eager pass
   if (launch_set_int(s->d_index, 0, s->st) != cudaSuccess) return bail(LTB_FAIL("set_int launch failed"));
@@ -940,7 +964,7 @@ int ltb_w2l_profile_ops(ltb_w2l_session* s, int index, int max_ops, int* n_ops, 
     if (kinds) kinds[i] = o.type;
     if (flops) {
       double f = 0;
-      if (o.type == 0 || o.type == 4) {
+      if (o.type == 0 || o.type == 4 || o.type == 5) {
         for (int p = 0; p < o.cp.nphases; ++p) f += 2.0 * o.cp.M * o.cp.Cout * (double)o.cp.ph[p].ntaps * o.cp.Cin;
       }
       flops[i] = f;
@@ -1013,6 +1037,7 @@ int ltb_conv2d_f16(const ltb_conv_desc* d, const void* in_f16, const float* w_f3
   const size_t in_b = (size_t)d->N * d->IH * d->IW * d->Cin * 2, out_b = (size_t)d->N * OH * OW * d->Cout * 2;
   __half *din = nullptr, *dout = nullptr, *dw = nullptr, *dres = nullptr, *dwt = nullptr;
   float* dbias = nullptr;
+  float* dws = nullptr;
   int rc = 0;
   auto cleanup = [&]() {
     cudaFree(din);
@@ -1020,6 +1045,7 @@ int ltb_conv2d_f16(const ltb_conv_desc* d, const void* in_f16, const float* w_f3
     cudaFree(dw);
     cudaFree(dres);
     cudaFree(dwt);
+    cudaFree(dws);
     cudaFree(dbias);
   };
 #define CK(x)                                                             \
@@ -1076,7 +1102,9 @@ int ltb_conv2d_f16(const ltb_conv_desc* d, const void* in_f16, const float* w_f3
     }
     CK(launch_conv_halo(pl, nullptr));
   } else {
-    CK(launch_conv_gather(p, nullptr));
+    CK(cudaMalloc(&dws, ((size_t)1 << 22) * sizeof(float)));
+    CK(cudaMemset(dws, 0, ((size_t)1 << 22) * sizeof(float)));
+    CK(launch_conv_gather(p, nullptr, dws, (size_t)1 << 22));
   }
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out_f16, dout, out_b, cudaMemcpyDeviceToHost));

@@ -273,7 +273,7 @@ class MuseTalkModel:
                 blk["up"] = ConvWeight(ctx, _np(sd[p + ".weight"]), _np(sd[p + ".bias"]))
             self.u_up.append(blk)
         self.u_norm_out = _Norm(ctx, sd, "conv_norm_out")
-        self.u_conv_out = ConvWeight(ctx, _np(sd["conv_out.weight"]), _np(sd["conv_out.bias"]), pad_cout=16)
+        self.u_conv_out = ConvWeight(ctx, _np(sd["conv_out.weight"]), _np(sd["conv_out.bias"]), pad_cout=32)   # 32: TMA halo kernel
 
         # ---- VAE decoder
         sd = vae_sd
@@ -291,7 +291,7 @@ class MuseTalkModel:
                 blk["up"] = ConvWeight(ctx, _np(sd[p + ".weight"]), _np(sd[p + ".bias"]))
             self.v_dec_up.append(blk)
         self.v_dec_norm_out = _Norm(ctx, sd, "decoder.conv_norm_out")
-        self.v_dec_out = ConvWeight(ctx, _np(sd["decoder.conv_out.weight"]), _np(sd["decoder.conv_out.bias"]), pad_cout=16)
+        self.v_dec_out = ConvWeight(ctx, _np(sd["decoder.conv_out.weight"]), _np(sd["decoder.conv_out.bias"]), pad_cout=32)
         # ---- VAE encoder (BASELINE config 3; offline in the reference: avatars/musetalk/genavatar.py:126-128)
         self.with_encoder = with_encoder
         if with_encoder:
@@ -306,7 +306,7 @@ class MuseTalkModel:
                 self.v_enc_down.append(blk)
             self.v_enc_mid = self._vae_mid(ctx, sd, "encoder.mid_block")
             self.v_enc_norm_out = _Norm(ctx, sd, "encoder.conv_norm_out")
-            self.v_enc_out = ConvWeight(ctx, _np(sd["encoder.conv_out.weight"]), _np(sd["encoder.conv_out.bias"]), pad_cout=16)
+            self.v_enc_out = ConvWeight(ctx, _np(sd["encoder.conv_out.weight"]), _np(sd["encoder.conv_out.bias"]), pad_cout=32)
             L = vcfg.latent_channels
             qw, qb = _np(sd["quant_conv.weight"])[:L, :, 0, 0] * sf, _np(sd["quant_conv.bias"])[:L] * sf   # mean rows, x scaling_factor
             w_lo = np.zeros((16, 16), np.float32)
@@ -382,7 +382,7 @@ class MuseTalkModel:
         """pred16 (B,h,w,16) latents [4 real channels] -> uint8 BGR image written to out_u8 (B,8h,8w,3)."""
         cfg = self.vcfg
         G, eps = cfg.norm_groups, cfg.norm_eps
-        h = b.conv3(b.linear(pred16, self.v_post_quant), self.v_dec_in)
+        h = b.conv3(b.linear(DevTensor(pred16.ptr, (*pred16.shape[:-1], 16), pitch=pred16.pitch), self.v_post_quant), self.v_dec_in)
         h = self._emit_vae_mid(b, h, self.v_dec_mid, G, eps)
         if taps is not None:
             taps["dec_mid"] = h
@@ -415,10 +415,10 @@ class MuseTalkModel:
                 h = b.conv3(h, blk["down"], stride=2, pad=(0, 0))     # F.pad(x,(0,1,0,1)) + conv s2 p0
         h = self._emit_vae_mid(b, h, self.v_enc_mid, G, eps)
         m = b.conv3(b.groupnorm(h, self.v_enc_norm_out, G, eps, True), self.v_enc_out)   # (2B,h,w,16): moments in 0..7
-        _, lh, lw, _ = m.shape
-        half = B * lh * lw * 16
-        tmp = b.linear(DevTensor(m.ptr, (B, lh, lw, 16)), self.v_quant_masked)
-        b.linear(DevTensor(m.offset(half), (B, lh, lw, 16)), self.v_quant_ref, res=tmp, out=out_latents16)
+        _, lh, lw, mc = m.shape
+        half = B * lh * lw * mc
+        tmp = b.linear(DevTensor(m.ptr, (B, lh, lw, 16), pitch=mc), self.v_quant_masked)
+        b.linear(DevTensor(m.offset(half), (B, lh, lw, 16), pitch=mc), self.v_quant_ref, res=tmp, out=out_latents16)
         return out_latents16
 
 

@@ -26,6 +26,9 @@ CASES = [
     (1, 24, 24, 80, 32, 3, (1, 1), 1, False, False),     # head conv: KB=16, 5 chunks per tap
     (1, 64, 64, 64, 64, 3, (1, 1), 1, False, True),      # many M tiles
     (1, 32, 32, 320, 128, 3, (2, 2), 1, True, False),    # ConvT 320 -> 128
+    (8, 8, 8, 512, 512, 3, (1, 1), 1, False, True),      # split-K: M = 512, 72 K blocks, residual through the finalize kernel
+    (8, 4, 4, 1280, 640, 3, (1, 1), 1, False, False),    # split-K: M = 128, 180 K blocks
+    (2, 8, 8, 256, 512, 3, (2, 2), 1, False, False),     # split-K with stride 2 (M = 32)
 ]
 
 
