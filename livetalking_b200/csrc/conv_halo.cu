@@ -24,12 +24,16 @@ namespace ltb {
 
 constexpr int kHaloP = 10;  // halo row pitch in pixels (8 + 2)
 
-template <int BN, int NSUB, int NACC>
+// TAPS = 9: 3x3 conv / sub-pixel ConvT over a (16*NSUB+2) x 10 pixel halo.
+// TAPS = 1: plain GEMM (1x1 conv / nn.Linear): the "halo" is the 128*NSUB-row tile itself (pitch 8 -> SBO 1024 B).
+template <int BN, int NSUB, int NACC, int TAPS>
 struct HaloCfg {
-  static constexpr int HR = 16 * NSUB + 2;                                  // halo rows
-  static constexpr int A_BYTES_RAW = HR * kHaloP * 128;                     // TMA transaction bytes per A stage
+  static constexpr int P = (TAPS == 9) ? kHaloP : 8;                        // halo row pitch (pixels)
+  static constexpr int HR = (TAPS == 9) ? 16 * NSUB + 2 : 16 * NSUB;        // halo rows
+  static constexpr int TG = (TAPS == 9) ? 3 : 1;                            // B stages per K chunk / taps per B stage
+  static constexpr int A_BYTES_RAW = HR * P * 128;                          // TMA transaction bytes per A stage
   static constexpr int A_BYTES = (A_BYTES_RAW + 1023) & ~1023;
-  static constexpr int B_BYTES = 3 * BN * 128;                              // 3 taps x BN rows x 64 k
+  static constexpr int B_BYTES = TG * BN * 128;                             // TG taps x BN rows x 64 k
   // stage counts: fill the 227 KB of shared memory
   static constexpr int BUDGET = 226 * 1024;
   static constexpr int A_STAGES = (BN <= 32) ? 4 : (BN <= 64 ? 3 : (NSUB == 1 ? 3 : 2));
@@ -43,9 +47,9 @@ struct HaloCfg {
   static_assert(B_STAGES >= 2, "not enough shared memory for the weight ring");
 };
 
-template <int BN, int NSUB, int NACC>
+template <int BN, int NSUB, int NACC, int TAPS>
 __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_constant__ HaloParams p) {
-  using C = HaloCfg<BN, NSUB, NACC>;
+  using C = HaloCfg<BN, NSUB, NACC, TAPS>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[C::A_STAGES], a_empty[C::A_STAGES];
   __shared__ __align__(8) uint64_t b_full[C::B_STAGES], b_empty[C::B_STAGES];
@@ -84,7 +88,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  const int tiles_m = p.tiles_x * p.tiles_y * p.N;
+  const int tiles_m = (TAPS == 9) ? p.tiles_x * p.tiles_y * p.N : p.tiles_x;
 
   if (warp == 0) {
     // =============================================================== TMA producer
@@ -93,21 +97,27 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const int nt = t / tiles_m;
         int mt = t - nt * tiles_m;
-        const int img = mt / (p.tiles_x * p.tiles_y);
-        mt -= img * (p.tiles_x * p.tiles_y);
-        const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
-        const int y0 = ty * (16 * NSUB) + p.halo_y0, x0 = tx * 8 + p.halo_x0;
+        int img = 0, y0 = 0, x0 = 0;
+        if (TAPS == 9) {
+          img = mt / (p.tiles_x * p.tiles_y);
+          mt -= img * (p.tiles_x * p.tiles_y);
+          const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+          y0 = ty * (16 * NSUB) + p.halo_y0;
+          x0 = tx * 8 + p.halo_x0;
+        }
         for (int c = 0; c < chunks; ++c) {
           const uint32_t as = ai % C::A_STAGES;
           mbar_wait(smem_u32(&a_empty[as]), ((ai / C::A_STAGES) & 1u) ^ 1u);
           mbar_arrive_expect_tx(smem_u32(&a_full[as]), C::A_BYTES_RAW);
-          tma_load_4d(a_smem + as * C::A_BYTES, &p.tm_in, smem_u32(&a_full[as]), c * 64, x0, y0, img);
+          if (TAPS == 9) tma_load_4d(a_smem + as * C::A_BYTES, &p.tm_in, smem_u32(&a_full[as]), c * 64, x0, y0, img);
+          else tma_load_2d(a_smem + as * C::A_BYTES, &p.tm_in, smem_u32(&a_full[as]), c * 64, mt * (128 * NSUB));
           ++ai;
-          for (int j = 0; j < 3; ++j) {
+          for (int j = 0; j < C::TG; ++j) {
             const uint32_t bs = bi % C::B_STAGES;
             mbar_wait(smem_u32(&b_empty[bs]), ((bi / C::B_STAGES) & 1u) ^ 1u);
             mbar_arrive_expect_tx(smem_u32(&b_full[bs]), C::B_BYTES);
-            tma_load_3d(b_smem + bs * C::B_BYTES, &p.tm_w, smem_u32(&b_full[bs]), c * 64, nt * BN, j * 3);
+            if (TAPS == 9) tma_load_3d(b_smem + bs * C::B_BYTES, &p.tm_w, smem_u32(&b_full[bs]), c * 64, nt * BN, j * 3);
+            else tma_load_2d(b_smem + bs * C::B_BYTES, &p.tm_w, smem_u32(&b_full[bs]), c * 64, nt * BN);
             ++bi;
           }
         }
@@ -117,7 +127,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
     // =============================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(128, BN);
-      constexpr uint32_t kADescHi = ((kHaloP * 128) >> 4) | (1u << 14) | (2u << 29);  // SBO = 1280 B (halo pitch)
+      constexpr uint32_t kADescHi = ((C::P * 128) >> 4) | (1u << 14) | (2u << 29);    // SBO = halo pitch (1280 B) / 1024 B in GEMM mode
       constexpr uint32_t kBDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);            // SBO = 1024 B
       uint32_t ai = 0, bi = 0, it = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
@@ -129,7 +139,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
           const uint32_t as = ai % C::A_STAGES;
           mbar_wait(smem_u32(&a_full[as]), (ai / C::A_STAGES) & 1u);
           const uint32_t a_base = a_smem + as * C::A_BYTES;
-          for (int j = 0; j < 3; ++j) {
+          for (int j = 0; j < C::TG; ++j) {
             const uint32_t bs = bi % C::B_STAGES;
             mbar_wait(smem_u32(&b_full[bs]), (bi / C::B_STAGES) & 1u);
             tc_fence_after();
@@ -138,8 +148,8 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
             const uint32_t b_lo0 = ((b_base & 0x3FFFFu) >> 4) | (1u << 16);
             const uint32_t a_lo0 = ((a_base & 0x3FFFFu) >> 4) | (1u << 16);
 #pragma unroll
-            for (int tt = 0; tt < 3; ++tt) {
-              const int tap = j * 3 + tt;
+            for (int tt = 0; tt < C::TG; ++tt) {
+              const int tap = j * C::TG + tt;
               const uint32_t a_lo_tap = a_lo0 + (uint32_t)p.tap_row[tap] * 8u;   // 128 B rows -> 8 x 16 B
               const uint32_t d_tap = dbase + (uint32_t)p.tap_acc[tap] * (NSUB * BN);
               const uint32_t fresh = (c == 0 && p.tap_first[tap]) ? 1u : 0u;
@@ -147,7 +157,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
               for (int sub = 0; sub < NSUB; ++sub) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  umma_f16_lohi(d_tap + sub * BN, a_lo_tap + sub * (16 * kHaloP * 8) + k * 2, kADescHi,
+                  umma_f16_lohi(d_tap + sub * BN, a_lo_tap + sub * (16 * C::P * 8) + k * 2, kADescHi,
                                 b_lo0 + tt * (BN * 8) + k * 2, kBDescHi, idesc, (fresh && k == 0) ? 0u : 1u);
                 }
               }
@@ -174,9 +184,13 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       const int nt = t / tiles_m;
       int mt = t - nt * tiles_m;
-      const int img = mt / (p.tiles_x * p.tiles_y);
-      mt -= img * (p.tiles_x * p.tiles_y);
-      const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
+      int img = 0, ty = 0, tx = 0;
+      if (TAPS == 9) {
+        img = mt / (p.tiles_x * p.tiles_y);
+        mt -= img * (p.tiles_x * p.tiles_y);
+        ty = mt / p.tiles_x;
+        tx = mt - ty * p.tiles_x;
+      }
       const uint32_t buf = it & 1u;
       mbar_wait(smem_u32(&acc_full[buf]), (it >> 1) & 1u);
       tc_fence_after();
@@ -186,10 +200,17 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
       for (int acc = 0; acc < NACC; ++acc) {
 #pragma unroll 1
         for (int sub = 0; sub < NSUB; ++sub) {
-          const int gy = ty * (16 * NSUB) + sub * 16 + ry, gx = tx * 8 + rx;
-          const size_t opix = ((size_t)img * p.OH + gy * p.osy + p.acc_oy[acc]) * p.OW + gx * p.osx + p.acc_ox[acc];
+          size_t opix;
+          bool row_ok = true;
+          if (TAPS == 9) {
+            const int gy = ty * (16 * NSUB) + sub * 16 + ry, gx = tx * 8 + rx;
+            opix = ((size_t)img * p.OH + gy * p.osy + p.acc_oy[acc]) * p.OW + gx * p.osx + p.acc_ox[acc];
+          } else {
+            opix = (size_t)mt * (128 * NSUB) + sub * 128 + row;      // GEMM mode: output row index
+            row_ok = opix < (size_t)p.M;
+          }
           __half* optr = p.out + opix * p.OCtot + p.oc_off + n0;
-          const __half* rptr = p.res ? (p.res + opix * p.RCtot + p.rc_off + n0) : nullptr;
+          const __half* rptr = (p.res && row_ok) ? (p.res + opix * p.RCtot + p.rc_off + n0) : nullptr;
 #pragma unroll 1
           for (int c0 = 0; c0 < BN; c0 += 32) {
             if (((((acc * NSUB + sub) * BN + c0) >> 5) & 1) != grp) continue;
@@ -218,7 +239,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
               const __half2 lo = p.relu ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(-65504.f, -65504.f);
 #pragma unroll
               for (int u = 0; u < 4; ++u) oh[u] = __hmin2(__hmax2(oh[u], lo), hmax);
-              *reinterpret_cast<uint4*>(optr + c0 + g) = ov;
+              if (row_ok) *reinterpret_cast<uint4*>(optr + c0 + g) = ov;
             }
           }
         }
@@ -280,7 +301,17 @@ static bool is_convT(const ConvParams& p) {
   return p.IH == p.GH && p.IW == p.GW && p.OH == 2 * p.GH && p.OW == 2 * p.GW;
 }
 
+static bool is_gemm(const ConvParams& p) {
+  return p.nphases == 1 && p.ph[0].ntaps == 1 && p.ph[0].dy[0] == 0 && p.ph[0].dx[0] == 0 && p.sy == 1 && p.sx == 1 && p.osy == 1 &&
+         p.osx == 1 && p.IH == p.GH && p.IW == p.GW && p.OH == p.GH && p.OW == p.GW && p.zbatch <= 1;
+}
+
 bool conv_halo_supported(const ConvParams& p) {
+  if (is_gemm(p)) {
+    // TMA GEMM: K-major rows with 16-byte aligned pitch; worth it from a few M tiles upwards
+    return p.Cout % 32 == 0 && p.Cin % 8 == 0 && p.Cin >= 32 && (p.ICtot % 8) == 0 && (p.ic_off % 8) == 0 && (p.Ktot % 8) == 0 &&
+           (p.ph[0].koff % 8) == 0 && p.M >= 512 && get_encode() != nullptr;
+  }
   if (!(is_conv3x3(p) || is_convT(p))) return false;
   if (p.GH % 16 != 0 || p.GW % 8 != 0) return false;
   if (p.Cout % 32 != 0 || p.Cin < 16) return false;
@@ -290,6 +321,14 @@ bool conv_halo_supported(const ConvParams& p) {
 
 // picks (BN, NSUB, NACC) ; returns false if unsupported
 static bool pick_cfg(const ConvParams& p, int* BN, int* NSUB, int* NACC) {
+  if (is_gemm(p)) {
+    *NACC = 1;
+    *BN = (p.Cout % 128 == 0) ? 128 : (p.Cout % 64 == 0) ? 64 : 32;
+    auto tiles = [&](int bn, int nsub) { return (long)((p.M + 128 * nsub - 1) / (128 * nsub)) * (p.Cout / bn); };
+    *NSUB = tiles(*BN, 2) >= 148 ? 2 : 1;
+    while (*BN > 32 && tiles(*BN, *NSUB) < 120) *BN >>= 1;
+    return true;
+  }
   const bool tr = is_convT(p);
   *NACC = tr ? 4 : 1;
   if (tr) {
@@ -316,6 +355,19 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
   out->NSUB = NSUB;
   out->NACC = NACC;
   const bool tr = NACC == 4;
+  const bool gemm = is_gemm(p);
+  out->TAPS = gemm ? 1 : 9;
+  if (gemm) {
+    // A: 2-D (K, rows) ; B: 2-D (K, Cout) over the layer's own K-major weight rows
+    cuuint64_t dims[2] = {(cuuint64_t)p.Cin, (cuuint64_t)p.M};
+    cuuint64_t strides[1] = {(cuuint64_t)p.ICtot * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)(128 * NSUB)};
+    if (!encode(&h.tm_in, 2, p.in + p.ic_off, dims, strides, box)) return 2;
+    cuuint64_t wdims[2] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout};
+    cuuint64_t wstrides[1] = {(cuuint64_t)p.Ktot * 2};
+    cuuint32_t wbox[2] = {64, (cuuint32_t)BN};
+    if (!encode(&h.tm_w, 2, p.w + p.ph[0].koff, wdims, wstrides, wbox)) return 2;
+  } else
   // input: 4-D (C, W, H, N) view of the NHWC channel slice
   {
     cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.IW, (cuuint64_t)p.IH, (cuuint64_t)p.N};
@@ -324,7 +376,7 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
     if (!encode(&h.tm_in, 4, p.in + p.ic_off, dims, strides, box)) return 2;
   }
   // weights: 3-D (k = Cin, n = Cout, tap = 9) view of the tap-major copy [9][Cout][Cin]
-  {
+  if (!gemm) {
     cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, 9};
     cuuint64_t strides[2] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Cout * p.Cin * 2};
     cuuint32_t box[3] = {64, (cuuint32_t)BN, 3};
@@ -334,6 +386,7 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
   h.res = p.res;
   h.bias = p.bias;
   h.N = p.N;
+  h.M = p.M;
   h.Cin = p.Cin;
   h.OCtot = p.OCtot;
   h.oc_off = p.oc_off;
@@ -357,25 +410,33 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
       h.tap_first[t] = (i == 0) ? 1 : 0;
     }
   }
+  h.tiles_n = p.Cout / BN;
+  if (gemm) {
+    h.halo_y0 = h.halo_x0 = 0;
+    h.tap_row[0] = 0;
+    h.tiles_x = (p.M + 128 * NSUB - 1) / (128 * NSUB);
+    h.tiles_y = 1;
+    h.total_tiles = h.tiles_x * h.tiles_n;
+    return 0;
+  }
   h.tiles_x = p.GW / 8;
   h.tiles_y = p.GH / (16 * NSUB);
-  h.tiles_n = p.Cout / BN;
   h.total_tiles = h.tiles_x * h.tiles_y * p.N * h.tiles_n;
   return 0;
 }
 
-template <int BN, int NSUB, int NACC>
+template <int BN, int NSUB, int NACC, int TAPS = 9>
 static cudaError_t launch_cfg(const HaloPlan& pl, int sms, cudaStream_t st) {
-  using C = HaloCfg<BN, NSUB, NACC>;
+  using C = HaloCfg<BN, NSUB, NACC, TAPS>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_umma_kernel<BN, NSUB, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_umma_kernel<BN, NSUB, NACC, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int grid = pl.hp.total_tiles < sms ? pl.hp.total_tiles : sms;
-  conv_halo_umma_kernel<BN, NSUB, NACC><<<grid, 320, C::SMEM_BYTES, st>>>(pl.hp);
+  conv_halo_umma_kernel<BN, NSUB, NACC, TAPS><<<grid, 320, C::SMEM_BYTES, st>>>(pl.hp);
   return cudaGetLastError();
 }
 
@@ -388,6 +449,17 @@ cudaError_t launch_conv_halo(const HaloPlan& pl, cudaStream_t st) {
     if (sms <= 0) sms = 148;
   }
   const int key = pl.BN * 100 + pl.NSUB * 10 + pl.NACC;
+  if (pl.TAPS == 1) {
+    switch (key) {
+      case 12821: return launch_cfg<128, 2, 1, 1>(pl, sms, st);
+      case 12811: return launch_cfg<128, 1, 1, 1>(pl, sms, st);
+      case 6421: return launch_cfg<64, 2, 1, 1>(pl, sms, st);
+      case 6411: return launch_cfg<64, 1, 1, 1>(pl, sms, st);
+      case 3221: return launch_cfg<32, 2, 1, 1>(pl, sms, st);
+      case 3211: return launch_cfg<32, 1, 1, 1>(pl, sms, st);
+    }
+    return cudaErrorInvalidValue;
+  }
   switch (key) {
     case 12821: return launch_cfg<128, 2, 1>(pl, sms, st);
     case 12811: return launch_cfg<128, 1, 1>(pl, sms, st);

@@ -15,7 +15,7 @@ struct alignas(64) HaloParams {
   __half* out;
   const __half* res;
   const float* bias;
-  int N, Cin;
+  int N, M, Cin;  // M: GEMM-mode row count
   int OCtot, oc_off, RCtot, rc_off;
   int OH, OW, osy, osx;
   int relu;
@@ -29,11 +29,11 @@ struct alignas(64) HaloParams {
 
 struct HaloPlan {
   HaloParams hp;
-  int BN, NSUB, NACC;
+  int BN, NSUB, NACC, TAPS;  // TAPS = 9 (3x3 conv / ConvT halo mode) or 1 (TMA GEMM mode: 1x1 conv / linear)
 };
 
 bool conv_halo_supported(const ConvParams& p);
-// w_tap_major: device pointer to the [9][Cout][Cin] copy of the layer's weights. returns 0 on success.
+// w_tap_major: device pointer to the [9][Cout][Cin] copy of the layer's weights (unused in GEMM mode). returns 0 on success.
 int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan* out);
 cudaError_t launch_conv_halo(const HaloPlan& pl, cudaStream_t st);
 cudaError_t launch_w_tap_major(const __half* w, __half* wt, int cout, int cin, cudaStream_t st, int ntaps = 9);

@@ -211,7 +211,8 @@ int ltb_op_conv2d(ltb_ctx* c, const ltb_conv_op* d) {
   p.out_zo = d->out_zo;
   p.out_zi = d->out_zi;
   cudaError_t e;
-  if (d->w_tap && d->zbatch <= 1 && d->w_koff == 0 && !d->no_halo && conv_halo_supported(p)) {
+  const bool one_by_one = (d->KH == 1 && d->KW == 1);
+  if ((d->w_tap || one_by_one) && d->zbatch <= 1 && !d->no_halo && conv_halo_supported(p)) {
     HaloPlan pl;
     if (conv_halo_make_plan(p, static_cast<const __half*>(d->w_tap), &pl) != 0) return LTB_FAIL("conv2d: tensor map creation failed");
     e = launch_conv_halo(pl, c->st);

@@ -400,7 +400,8 @@ static int build_plan(ltb_w2l_session* s) {
     Op o;
     o.type = 0;
     o.cp = p;
-    if (!(s->flags & LTB_SESSION_NO_HALO) && m->wt[li] && conv_halo_supported(p)) {
+    const bool gemm1x1 = (p.nphases == 1 && p.ph[0].ntaps == 1);
+    if (!(s->flags & LTB_SESSION_NO_HALO) && (m->wt[li] || gemm1x1) && conv_halo_supported(p)) {
       HaloPlan pl;
       if (conv_halo_make_plan(p, m->wt[li], &pl) == 0) {
         o.type = 4;
@@ -1094,7 +1095,7 @@ int ltb_conv2d_f16(const ltb_conv_desc* d, const void* in_f16, const float* w_f3
   }
   if (d->force_path != 1 && can_halo) {
     CK(cudaMalloc(&dwt, wp.size() * 2));
-    CK(launch_w_tap_major(dw, dwt, d->Cout, d->Cin, nullptr));
+    if (d->KH == 3) CK(launch_w_tap_major(dw, dwt, d->Cout, d->Cin, nullptr));
     HaloPlan pl;
     if (conv_halo_make_plan(p, dwt, &pl) != 0) {
       cleanup();

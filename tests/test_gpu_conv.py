@@ -133,3 +133,39 @@ def test_halo_kernel_matches_torch_fp32(case):
     out_g = engine.conv2d_f16(xn, w.numpy(), b.numpy(), stride=(1, 1), pad=1, transposed=transposed, relu=True, res=rn,
                               force_path=1).astype(np.float32)
     assert np.abs(out - out_g).max() <= 2e-2
+
+
+# ---- TMA GEMM mode of the halo kernel (1x1 convs / linears with M >= 512)
+GEMM_CASES = [
+    # N, H, W, Cin, Cout, res
+    (1, 32, 32, 320, 2560, False),      # FF1 of the 32x32 transformer block (5 K chunks, 20 N tiles)
+    (1, 64, 128, 64, 128, True),        # 8192 rows, residual
+    (1, 25, 40, 96, 64, False),         # ragged M = 1000, partial K chunk (96 = 64 + 32)
+    (2, 16, 16, 1280, 320, True),       # FF2-like: deep K
+    (1, 32, 32, 384, 96, False),        # Cout = 96 -> BN 32
+]
+
+
+@pytest.mark.parametrize("case", GEMM_CASES, ids=[f"g{i}" for i in range(len(GEMM_CASES))])
+def test_tma_gemm_mode_matches_torch_fp32(case):
+    from livetalking_b200 import engine
+    engine.set_device(0)
+    N, H, W, Cin, Cout, res = case
+    g = torch.Generator().manual_seed(77 + Cin + Cout)
+    x = (torch.randn(N, Cin, H, W, generator=g) * 0.7).half()
+    w = torch.randn(Cout, Cin, 1, 1, generator=g) * (1.0 / Cin) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.2
+    ref = F.conv2d(x.float(), w.half().float(), b)
+    r = None
+    if res:
+        r = (torch.randn(ref.shape, generator=g) * 0.5).half()
+        ref = ref + r.float()
+    ref = ref.permute(0, 2, 3, 1).contiguous().numpy()
+    xn = x.permute(0, 2, 3, 1).contiguous().numpy()
+    rn = None if r is None else r.permute(0, 2, 3, 1).contiguous().numpy()
+    out = engine.conv2d_f16(xn, w.numpy(), b.numpy(), relu=False, res=rn, force_path=2).astype(np.float32)
+    assert np.isfinite(out).all()
+    err = np.abs(out - ref)
+    assert (err <= 2e-2 + 1e-2 * np.abs(ref)).all(), f"max err {err.max():.4f} at {np.unravel_index(err.argmax(), err.shape)}"
+    out_g = engine.conv2d_f16(xn, w.numpy(), b.numpy(), relu=False, res=rn, force_path=1).astype(np.float32)
+    assert np.abs(out - out_g).max() <= 2e-2
