@@ -124,6 +124,19 @@ def cpu_path_fps(frames_per_rep: int, reps: int, threads: int):
             idx = paste_ref.mirror_index(len(faces), step * B + i)
             paste_ref.w2l_paste_back(pred[i], frames[idx], coords[idx])
 
+    # the reference's PyTorch CPU path does not scale to all cores of a 128-core host at this batch size: calibrate the
+    # thread count on one repetition each and keep the fastest (reported as `cores`)
+    best_t, best = threads, None
+    for cand in sorted({threads, min(threads, 64), min(threads, 32), min(threads, 16)}, reverse=True):
+        torch.set_num_threads(cand)
+        one(0)
+        t0 = time.perf_counter()
+        one(1)
+        d = time.perf_counter() - t0
+        if best is None or d < best:
+            best, best_t = d, cand
+    torch.set_num_threads(best_t)
+    cpu_path_fps.threads_used = best_t
     one(0)
     t0 = time.perf_counter()
     for r in range(reps):
@@ -145,7 +158,8 @@ def run_reference(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "wav2lip256 batch 16, 256x256, 60 s synthetic audio, U-Net fwd + paste-back (configs[1]); "
                                f"CPU arm: each step = a bounded sample of {fpr} frames of that workload"},
-        "cpu_baseline": {"value": round(fps, 4), "unit": "frames/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": round(fps, 4), "unit": "frames/s", "cores": getattr(cpu_path_fps, "threads_used", cores), "kind": "port",
+                         "host_cores": cores,
                          "sample": f"{args.steps} steps x {fpr} frames: numpy mel + CPU PyTorch fp32 wav2lip256 + paste-back"},
         "e2e": {"value": round(fps, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -223,31 +237,37 @@ def run_ours(args):
     ms_max = float(t.item())
     value = world * BATCH * args.steps / (ms_max / 1000.0)
 
-    # ---- e2e: public API, host buffers, copies inside the timed region
-    pin_pcm = engine.PinnedBuffer(((SL + SR + 2 * BATCH) * 320,), np.float32)
-    pin_out = engine.PinnedBuffer((BATCH, FRAME_H, FRAME_W, 3), np.uint8)
+    # ---- e2e: public C-ABI call with HOST buffers; H2D of the PCM window and D2H of the 16 composited frames inside the
+    # timed region, pipelined: the D2H of step i (copy stream) overlaps the kernels of step i+1 (two pinned buffer pairs)
+    pin_pcm = [engine.PinnedBuffer(((SL + SR + 2 * BATCH) * 320,), np.float32) for _ in range(2)]
+    pin_out = [engine.PinnedBuffer((BATCH, FRAME_H, FRAME_W, 3), np.uint8) for _ in range(2)]
 
     def e2e_step(k, index):
-        pin_pcm.array[:] = step_pcm(audio, k)                    # "TTS" hands over host PCM
-        sess.mel_step(pin_pcm.array, want_output=False)          # H2D + mel kernels
-        sess.infer(index, None, want_pred=False)                 # forward
-        sess.paste_batch(index, out=pin_out.array)               # composite + D2H of 16 frames
+        b = e2e_step.n & 1
+        e2e_step.n += 1
+        sess.e2e_acquire()                                        # buffer pair b was last used two steps ago: wait until it is drained
+        pin_pcm[b].array[:] = step_pcm(audio, k)                  # "TTS" hands over host PCM
+        sess.step_e2e_async(index, pin_pcm[b].array, pin_out[b].array)
 
-    for k in range(max(3, args.warmup)):
+    e2e_step.n = 0
+    for k in range(max(4, args.warmup)):
         e2e_step(k, k * BATCH)
+    sess.sync()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
     t0 = time.perf_counter()
     for k in range(args.steps):
         e2e_step(k, idx + k * BATCH)
-    e1.record(stream)
-    barrier()
+    sess.sync()                                                   # every frame of every step is in host memory here
     wall_ms = (time.perf_counter() - t0) * 1000.0
-    te = torch.tensor([max(e0.elapsed_time(e1), wall_ms)], dtype=torch.float64, device="cuda")
+    barrier()
+    te = torch.tensor([wall_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * BATCH * args.steps / (float(te.item()) / 1000.0)
+    # sanity: the synchronous plugin-level calls produce the same frames as the pipelined call
+    chk = sess.paste_batch(idx + (args.steps - 1) * BATCH)
+    if not np.array_equal(chk, pin_out[(e2e_step.n - 1) & 1].array):
+        raise RuntimeError("pipelined e2e frames differ from the synchronous path")
 
     # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv): per-op CUDA-event timing, median of 3 passes
     roof = None
@@ -284,7 +304,7 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             fps, dt = cpu_path_fps(2, 4, cores)
-            cpu = {"value": round(fps, 4), "unit": "frames/s", "cores": cores, "kind": "port",
+            cpu = {"value": round(fps, 4), "unit": "frames/s", "cores": getattr(cpu_path_fps, "threads_used", cores), "host_cores": cores, "kind": "port",
                    "sample": "4 reps x 2 frames (+1 warm-up): numpy mel + CPU PyTorch fp32 wav2lip256 + paste-back (oracle port)"}
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -294,8 +314,8 @@ def run_ours(args):
                                    "mel + U-Net fwd + paste-back into 720p frames (BASELINE.json configs[1])",
                        "global_batch": BATCH * world, "sessions_per_gpu": 1, "parallelism": f"session-sharded x{world}",
                        "l2": "working set per step (activations ~0.9 GB + 107 MB weights) exceeds the 126 MB L2; no explicit flush"},
-            "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": int(pin_pcm.nbytes),
-                    "d2h_bytes_per_step": int(pin_out.nbytes)},
+            "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": int(pin_pcm[0].nbytes),
+                    "d2h_bytes_per_step": int(pin_out[0].nbytes), "how": "ltb_w2l_step_e2e_async, pinned host buffers, wall clock incl. final sync"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,

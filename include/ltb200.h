@@ -90,6 +90,14 @@ int ltb_w2l_step_async(ltb_w2l_session* s, int index);
  * algorithmic FLOPs of each op (2*M*N*K of the conv it implements, 0 for non-conv ops) and op kinds
  * (0 conv, 1 prep_faces, 2 audio_conv0, 3 head).  Call with ms == NULL to query n_ops. */
 int ltb_w2l_profile_ops(ltb_w2l_session* s, int index, int max_ops, int* n_ops, float* ms, double* flops, int* kinds);
+/* pipelined end-to-end step with HOST buffers: H2D of the PCM window, mel, forward, batched paste-back, and the D2H of
+ * the `batch` composited frames on a copy stream (double-buffered on the device, so the copy of step i overlaps the
+ * kernels of step i+1).  pcm_host / frames_host must be page-locked (ltb_host_alloc) and stay untouched until
+ * ltb_w2l_sync (use two alternating buffers when steps are issued back to back). */
+int ltb_w2l_step_e2e_async(ltb_w2l_session* s, int index, const float* pcm_host, int nsamples, uint8_t* frames_host);
+/* blocks the host until the step issued two calls ago (which used the same alternating host buffers) has completely
+ * finished, i.e. its PCM has been consumed and its frames are in host memory — call before refilling the PCM buffer */
+int ltb_w2l_e2e_acquire(ltb_w2l_session* s);
 int ltb_w2l_sync(ltb_w2l_session* s);
 /* the session's cudaStream_t (so a caller can record CUDA events on it) */
 int ltb_w2l_stream(ltb_w2l_session* s, void** cuda_stream);

@@ -228,6 +228,11 @@ struct ltb_w2l_session {
   float* pred = nullptr;
   float* pred_scratch = nullptr;  // one host-supplied prediction (ltb_w2l_paste_pred)
   uint8_t* frames_out = nullptr;
+  uint8_t* frames_out2 = nullptr;        // second composite buffer: D2H of step i overlaps the kernels of step i+1
+  cudaStream_t st_copy = nullptr;
+  cudaEvent_t ev_paste[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  bool copied_valid[2] = {false, false};
+  unsigned e2e_seq = 0;
   int* d_index = nullptr;
   float* splitk_ws[2] = {nullptr, nullptr};  // one fp32 split-K workspace per stream (main, audio branch)
   std::vector<Op> ops;
@@ -772,6 +777,12 @@ int ltb_w2l_session_destroy(ltb_w2l_session* s) {
   if (s->gexec) cudaGraphExecDestroy(s->gexec);
   if (s->graph) cudaGraphDestroy(s->graph);
   for (void* p : s->allocs) cudaFree(p);
+  if (s->st_copy) cudaStreamSynchronize(s->st_copy);
+  for (int i = 0; i < 2; ++i) {
+    if (s->ev_paste[i]) cudaEventDestroy(s->ev_paste[i]);
+    if (s->ev_copied[i]) cudaEventDestroy(s->ev_copied[i]);
+  }
+  if (s->st_copy) cudaStreamDestroy(s->st_copy);
   if (s->ev_fork) cudaEventDestroy(s->ev_fork);
   if (s->ev_join) cudaEventDestroy(s->ev_join);
   if (s->st2) cudaStreamDestroy(s->st2);
@@ -914,9 +925,9 @@ int ltb_w2l_paste_pred(ltb_w2l_session* s, const float* pred, int idx, uint8_t* 
   return 0;
 }
 
-static int paste_batch_enqueue(ltb_w2l_session* s, int index) {
+static int paste_batch_enqueue(ltb_w2l_session* s, int index, uint8_t* dst = nullptr) {
   cudaError_t e = launch_w2l_paste(s->a->frames, s->a->coords, s->a->n, s->a->H, s->a->W, s->pred, 0, index, -1, s->B,
-                                   s->frames_out, s->st);
+                                   dst ? dst : s->frames_out, s->st);
   if (e != cudaSuccess) return LTB_FAIL(std::string("paste kernel: ") + cudaGetErrorString(e));
   s->launches += 1;
   return 0;
@@ -975,9 +986,48 @@ int ltb_w2l_profile_ops(ltb_w2l_session* s, int index, int max_ops, int* n_ops, 
   return rc;
 }
 
+int ltb_w2l_e2e_acquire(ltb_w2l_session* s) {
+  if (!s) return LTB_FAIL("null session");
+  const int slot = (int)(s->e2e_seq & 1u);
+  if (s->copied_valid[slot]) LTB_CUDA(cudaEventSynchronize(s->ev_copied[slot]));   // step seq-2 (same host buffers) fully drained
+  return 0;
+}
+
+int ltb_w2l_step_e2e_async(ltb_w2l_session* s, int index, const float* pcm_host, int nsamples, uint8_t* frames_host) {
+  if (!s || !pcm_host || !frames_host) return LTB_FAIL("null argument");
+  const int expect = (s->l + s->r + 2 * s->B) * 320;
+  if (nsamples != expect) return LTB_FAIL("step_e2e: expected " + std::to_string(expect) + " samples");
+  if (!s->st_copy) {
+    LTB_CUDA(cudaStreamCreateWithFlags(&s->st_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      LTB_CUDA(cudaEventCreateWithFlags(&s->ev_paste[i], cudaEventDisableTiming));
+      LTB_CUDA(cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming));
+    }
+    void* p = nullptr;
+    if (dev_alloc(s, (size_t)s->B * s->a->H * s->a->W * 3, &p, true)) return 1;
+    s->frames_out2 = static_cast<uint8_t*>(p);
+  }
+  const int slot = (int)(s->e2e_seq & 1u);
+  uint8_t* dev_frames = slot ? s->frames_out2 : s->frames_out;
+  // the paste kernel of this step must not overwrite the buffer while the copy of step-2 is still draining it
+  if (s->copied_valid[slot]) LTB_CUDA(cudaStreamWaitEvent(s->st, s->ev_copied[slot], 0));
+  LTB_CUDA(cudaMemcpyAsync(s->pcm, pcm_host, (size_t)nsamples * 4, cudaMemcpyHostToDevice, s->st));
+  if (ltb_w2l_mel_resident(s)) return 1;
+  if (forward_enqueue(s, index)) return 1;
+  if (paste_batch_enqueue(s, index, dev_frames)) return 1;
+  LTB_CUDA(cudaEventRecord(s->ev_paste[slot], s->st));
+  LTB_CUDA(cudaStreamWaitEvent(s->st_copy, s->ev_paste[slot], 0));
+  LTB_CUDA(cudaMemcpyAsync(frames_host, dev_frames, (size_t)s->B * s->a->H * s->a->W * 3, cudaMemcpyDeviceToHost, s->st_copy));
+  LTB_CUDA(cudaEventRecord(s->ev_copied[slot], s->st_copy));
+  s->copied_valid[slot] = true;
+  ++s->e2e_seq;
+  return 0;
+}
+
 int ltb_w2l_sync(ltb_w2l_session* s) {
   if (!s) return LTB_FAIL("null session");
   LTB_CUDA(cudaStreamSynchronize(s->st));
+  if (s->st_copy) LTB_CUDA(cudaStreamSynchronize(s->st_copy));
   return 0;
 }
 

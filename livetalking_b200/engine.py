@@ -183,6 +183,14 @@ class W2LSession:
     def step_async(self, index: int) -> None:
         check(lib().ltb_w2l_step_async(self._h, int(index)))
 
+    def step_e2e_async(self, index: int, pcm_pinned: np.ndarray, frames_pinned: np.ndarray) -> None:
+        """Pipelined host-to-host step (pinned buffers): H2D PCM -> mel -> forward -> paste -> D2H frames on a copy stream."""
+        check(lib().ltb_w2l_step_e2e_async(self._h, int(index), _ptr(pcm_pinned), int(pcm_pinned.size), _ptr(frames_pinned)))
+
+    def e2e_acquire(self) -> None:
+        """Wait until the host buffers of the step issued two calls ago are free again."""
+        check(lib().ltb_w2l_e2e_acquire(self._h))
+
     def sync(self) -> None:
         check(lib().ltb_w2l_sync(self._h))
 
