@@ -160,12 +160,19 @@ typedef struct ltb_conv_op {
   int Ktot, w_koff, relu, no_halo;
   int zbatch, zdiv;
   long long in_zo, in_zi, w_zo, w_zi, out_zo, out_zi;
+  /* optional: also produce the GroupNorm statistics (sum, sum of squares per (image, group); gn_hw pixels per image) of the
+   * output tensor into gn_stats[N][gn_groups][2] — fused into the conv epilogue when the kernel supports it */
+  void* gn_stats;
+  int gn_groups, gn_hw;
 } ltb_conv_op;
 int ltb_op_conv2d(ltb_ctx* c, const ltb_conv_op* d);
 int ltb_op_w_tap_major(ltb_ctx* c, const void* w, void* wt, int cout, int cin);
 /* torch.nn.GroupNorm (+ optional SiLU) on an NHWC channel slice; fp32 statistics */
 int ltb_op_groupnorm(ltb_ctx* c, const void* x, int N, int HW, int C, int Ctot, int c_off, int groups, float eps, const float* gamma,
                      const float* beta, int silu, void* out, int OCtot, int oc_off);
+/* normalisation pass only, with statistics produced by a previous ltb_op_conv2d (gn_stats) */
+int ltb_op_groupnorm_apply(ltb_ctx* c, const void* x, int N, int HW, int C, int Ctot, int c_off, int groups, float eps, const void* stats,
+                           const float* gamma, const float* beta, int silu, void* out, int OCtot, int oc_off);
 /* torch.nn.LayerNorm over the last dim of [rows, C] */
 int ltb_op_layernorm(ltb_ctx* c, const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out);
 /* softmax(scale * x[:, :valid]) per row of a [rows, ld] matrix; columns [valid, cols) are written as 0 */

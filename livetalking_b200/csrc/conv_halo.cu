@@ -217,6 +217,9 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
             uint32_t v[32];
             tmem_ld32(tbase + (acc * NSUB + sub) * BN + c0, v);
             tmem_ld_wait();
+            float gs[8], gq[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gs[i] = gq[i] = 0.f;
 #pragma unroll
             for (int g = 0; g < 32; g += 8) {
               // packed-half epilogue (the narrow layers are epilogue-issue bound): fp32 accumulator + fp32 bias -> half2,
@@ -240,6 +243,54 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
 #pragma unroll
               for (int u = 0; u < 4; ++u) oh[u] = __hmin2(__hmax2(oh[u], lo), hmax);
               if (row_ok) *reinterpret_cast<uint4*>(optr + c0 + g) = ov;
+              if (p.gn_stats && row_ok) {
+                float ps[4], pq[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float2 f2 = __half22float2(oh[u]);
+                  ps[u] = f2.x + f2.y;
+                  pq[u] = f2.x * f2.x + f2.y * f2.y;
+                }
+                if (p.gn_cpg == 4) {
+                  gs[g / 4] += ps[0] + ps[1];
+                  gq[g / 4] += pq[0] + pq[1];
+                  gs[g / 4 + 1] += ps[2] + ps[3];
+                  gq[g / 4 + 1] += pq[2] + pq[3];
+                } else {
+                  const float ts = (ps[0] + ps[1]) + (ps[2] + ps[3]), tq = (pq[0] + pq[1]) + (pq[2] + pq[3]);
+                  if (p.gn_cpg == 8) {
+                    gs[g / 8] += ts;
+                    gq[g / 8] += tq;
+                  } else if (p.gn_cpg == 16) {
+                    gs[g / 16] += ts;
+                    gq[g / 16] += tq;
+                  } else {
+                    gs[0] += ts;
+                    gq[0] += tq;
+                  }
+                }
+              }
+            }
+            if (p.gn_stats) {
+              const int ng = p.gn_cpg >= 32 ? 1 : 32 / p.gn_cpg;
+              int gimg = img;
+              if (TAPS != 9) gimg = (int)(((size_t)mt * (128 * NSUB) + sub * 128 + q * 32) / (size_t)p.gn_hw);
+              float* sbase = p.gn_stats + ((size_t)gimg * p.gn_groups + (n0 + c0) / p.gn_cpg) * 2;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (i < ng) {
+                  float a = gs[i], b = gq[i];
+#pragma unroll
+                  for (int o = 16; o > 0; o >>= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    b += __shfl_xor_sync(0xffffffffu, b, o);
+                  }
+                  if (lane == 0) {
+                    atomicAdd(sbase + 2 * i, a);
+                    atomicAdd(sbase + 2 * i + 1, b);
+                  }
+                }
+              }
             }
           }
         }
@@ -388,6 +439,7 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
   h.N = p.N;
   h.M = p.M;
   h.Cin = p.Cin;
+  h.gn_stats = nullptr;
   h.OCtot = p.OCtot;
   h.oc_off = p.oc_off;
   h.RCtot = p.RCtot;
@@ -471,6 +523,16 @@ cudaError_t launch_conv_halo(const HaloPlan& pl, cudaStream_t st) {
     case 3214: return launch_cfg<32, 1, 4>(pl, sms, st);
   }
   return cudaErrorInvalidValue;
+}
+
+// can the epilogue of this plan accumulate GroupNorm statistics of its output?  (power-of-two channels per group >= 4,
+// whole 32-row groups inside one image)
+bool conv_halo_gn_fusable(const HaloPlan& pl, int cout_total, int groups, int hw) {
+  if (pl.NACC != 1 || groups <= 0 || cout_total % groups) return false;
+  const int cpg = cout_total / groups;
+  if (cpg < 4 || (cpg & (cpg - 1))) return false;
+  if (pl.TAPS == 1 && (hw % 128) != 0) return false;
+  return true;
 }
 
 // [Cout][ntaps][Cin] -> [ntaps][Cout][Cin] (one-off, at model load)

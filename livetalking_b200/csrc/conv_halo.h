@@ -25,6 +25,10 @@ struct alignas(64) HaloParams {
   int tap_first[9];      // 1 = first slice of its accumulator (overwrite instead of accumulate on the first K chunk)
   int acc_oy[4], acc_ox[4];
   int tiles_x, tiles_y, tiles_n, total_tiles;
+  // optional fused GroupNorm statistics of the OUTPUT tensor (sum, sum of squares per (image, group)), accumulated by the
+  // epilogue from the fp16-rounded values: saves the separate statistics pass of the following GroupNorm
+  float* gn_stats;
+  int gn_groups, gn_cpg, gn_hw;
 };
 
 struct HaloPlan {
@@ -36,6 +40,7 @@ bool conv_halo_supported(const ConvParams& p);
 // w_tap_major: device pointer to the [9][Cout][Cin] copy of the layer's weights (unused in GEMM mode). returns 0 on success.
 int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan* out);
 cudaError_t launch_conv_halo(const HaloPlan& pl, cudaStream_t st);
+bool conv_halo_gn_fusable(const HaloPlan& pl, int cout_total, int groups, int hw);
 cudaError_t launch_w_tap_major(const __half* w, __half* wt, int cout, int cin, cudaStream_t st, int ntaps = 9);
 
 }  // namespace ltb

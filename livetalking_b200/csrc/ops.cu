@@ -142,10 +142,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
   }
 }
 
-cudaError_t launch_groupnorm(const __half* x, int N, int HW, int C, int Ctot, int c_off, int groups, float eps, const float* gamma,
-                             const float* beta, int silu, __half* out, int OCtot, int oc_off, float* stats_ws, cudaStream_t st) {
+cudaError_t launch_gn_stats(const __half* x, int N, int HW, int C, int Ctot, int c_off, int groups, float* stats, cudaStream_t st) {
   if (C % groups != 0 || C % 8 != 0 || groups > 64 || C / 8 > 512 || (Ctot % 8) || (c_off % 8)) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(stats_ws, 0, (size_t)N * groups * 2 * sizeof(float), st);
+  cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)N * groups * 2 * sizeof(float), st);
   if (e != cudaSuccess) return e;
   const int vpr = C / 8;
   int R = 512 / vpr;
@@ -156,14 +155,27 @@ cudaError_t launch_groupnorm(const __half* x, int N, int HW, int C, int Ctot, in
   const int max_splits = (HW + 4 * R - 1) / (4 * R);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
-  gn_stats_kernel<<<dim3(splits, N), threads, 0, st>>>(x, HW, C, Ctot, c_off, groups, R, stats_ws);
+  gn_stats_kernel<<<dim3(splits, N), threads, 0, st>>>(x, HW, C, Ctot, c_off, groups, R, stats);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gn_apply(const __half* x, int N, int HW, int C, int Ctot, int c_off, int groups, float eps, const float* stats,
+                            const float* gamma, const float* beta, int silu, __half* out, int OCtot, int oc_off, cudaStream_t st) {
+  if (C % groups != 0 || C % 8 != 0 || groups > 64 || (Ctot % 8) || (c_off % 8)) return cudaErrorInvalidValue;
   const size_t total_vec = (size_t)HW * (C / 8);
   int blocks = (int)((total_vec + 255) / 256);
   const int cap = (1184 + N - 1) / N;
   if (blocks > cap) blocks = cap;
-  gn_apply_kernel<<<dim3(blocks, N), 256, 2 * C * sizeof(float), st>>>(x, HW, C, Ctot, c_off, groups, eps, stats_ws, gamma, beta, silu, out,
+  gn_apply_kernel<<<dim3(blocks, N), 256, 2 * C * sizeof(float), st>>>(x, HW, C, Ctot, c_off, groups, eps, stats, gamma, beta, silu, out,
                                                                         OCtot, oc_off, total_vec);
   return cudaGetLastError();
+}
+
+cudaError_t launch_groupnorm(const __half* x, int N, int HW, int C, int Ctot, int c_off, int groups, float eps, const float* gamma,
+                             const float* beta, int silu, __half* out, int OCtot, int oc_off, float* stats_ws, cudaStream_t st) {
+  cudaError_t e = launch_gn_stats(x, N, HW, C, Ctot, c_off, groups, stats_ws, st);
+  if (e != cudaSuccess) return e;
+  return launch_gn_apply(x, N, HW, C, Ctot, c_off, groups, eps, stats_ws, gamma, beta, silu, out, OCtot, oc_off, st);
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm (warp per row)

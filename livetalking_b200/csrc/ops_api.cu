@@ -211,16 +211,34 @@ int ltb_op_conv2d(ltb_ctx* c, const ltb_conv_op* d) {
   p.out_zo = d->out_zo;
   p.out_zi = d->out_zi;
   cudaError_t e;
+  const bool want_stats = d->gn_stats != nullptr && d->gn_groups > 0 && d->gn_hw > 0 && (p.M % d->gn_hw) == 0 && d->zbatch <= 1;
+  bool stats_fused = false;
   const bool one_by_one = (d->KH == 1 && d->KW == 1);
   if ((d->w_tap || one_by_one) && d->zbatch <= 1 && !d->no_halo && conv_halo_supported(p)) {
     HaloPlan pl;
     if (conv_halo_make_plan(p, static_cast<const __half*>(d->w_tap), &pl) != 0) return LTB_FAIL("conv2d: tensor map creation failed");
+    if (want_stats && d->oc_off == 0 && d->OCtot == d->Cout && conv_halo_gn_fusable(pl, d->Cout, d->gn_groups, d->gn_hw)) {
+      // GroupNorm statistics of the output are accumulated by the conv epilogue
+      LTB_CUDA(cudaMemsetAsync(d->gn_stats, 0, (size_t)(p.M / d->gn_hw) * d->gn_groups * 2 * sizeof(float), c->st));
+      pl.hp.gn_stats = static_cast<float*>(d->gn_stats);
+      pl.hp.gn_groups = d->gn_groups;
+      pl.hp.gn_cpg = d->Cout / d->gn_groups;
+      pl.hp.gn_hw = d->gn_hw;
+      stats_fused = true;
+    }
     e = launch_conv_halo(pl, c->st);
   } else {
     e = launch_conv_gather(p, c->st, c->splitk_ws, kSplitKWsFloats);
   }
   if (e != cudaSuccess) return LTB_FAIL(std::string("conv2d launch: ") + cudaGetErrorString(e));
   c->launches += 1;
+  if (want_stats && !stats_fused) {
+    // fallback: separate statistics pass over the freshly written output
+    e = launch_gn_stats(static_cast<const __half*>(d->out), p.M / d->gn_hw, d->gn_hw, d->Cout, d->OCtot, d->oc_off, d->gn_groups,
+                        static_cast<float*>(d->gn_stats), c->st);
+    if (e != cudaSuccess) return LTB_FAIL(std::string("conv2d gn_stats: ") + cudaGetErrorString(e));
+    c->launches += 1;
+  }
   return 0;
 }
 
@@ -239,6 +257,15 @@ int ltb_op_groupnorm(ltb_ctx* c, const void* x, int N, int HW, int C, int Ctot, 
                                    static_cast<__half*>(out), OCtot, oc_off, c->gn_ws, c->st);
   if (e != cudaSuccess) return LTB_FAIL(std::string("groupnorm: ") + cudaGetErrorString(e));
   c->launches += 2;
+  return 0;
+}
+int ltb_op_groupnorm_apply(ltb_ctx* c, const void* x, int N, int HW, int C, int Ctot, int c_off, int groups, float eps, const void* stats,
+                           const float* gamma, const float* beta, int silu, void* out, int OCtot, int oc_off) {
+  if (!c || !x || !out || !gamma || !beta || !stats) return LTB_FAIL("groupnorm_apply: null argument");
+  cudaError_t e = launch_gn_apply(static_cast<const __half*>(x), N, HW, C, Ctot, c_off, groups, eps, static_cast<const float*>(stats), gamma,
+                                  beta, silu, static_cast<__half*>(out), OCtot, oc_off, c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("groupnorm_apply: ") + cudaGetErrorString(e));
+  c->launches += 1;
   return 0;
 }
 int ltb_op_layernorm(ltb_ctx* c, const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out) {

@@ -125,9 +125,23 @@ class _Transformer:
 class Builder:
     """Emits engine ops for the diffusers building blocks.  Tensors are NHWC fp16 ``DevTensor``s of shape (N,H,W,C)."""
 
+    GN_GROUPS = 32   # every GroupNorm of the diffusers UNet / VAE uses 32 groups
+    # Fusing the GroupNorm statistics into the producing conv's epilogue (ltb_conv_op.gn_stats) is implemented and parity-tested,
+    # but measured SLOWER on B200 (MuseTalk B=8: 15.6 -> 17.6 ms/step): the extra shuffles/atomics make the 0.9 PFLOP/s VAE convs
+    # epilogue-bound, which costs more than the separate statistics pass (1.0 ms) saves.  Off by default.
+    FUSE_GN_STATS = False
+
     def __init__(self, ctx: Ctx):
         self.ctx = ctx
         self.temps: List[DevTensor] = []
+
+    def _stats_for(self, out: DevTensor, n_img: int):
+        """Ask the producing conv to also emit the GroupNorm statistics of `out` (fused into its epilogue when possible)."""
+        if not self.FUSE_GN_STATS or out.C % self.GN_GROUPS or out.pitch != out.C or out.c_off:
+            return None
+        st = self.new(n_img * self.GN_GROUPS * 4)                  # n_img * groups * 2 floats
+        out.stats = (st, self.GN_GROUPS)
+        return st
 
     def new(self, *shape) -> DevTensor:
         t = self.ctx.alloc(shape, np.float16, zero=True)
@@ -135,27 +149,35 @@ class Builder:
         return t
 
     # -- primitives
-    def conv3(self, x: DevTensor, w: ConvWeight, res: Optional[DevTensor] = None, stride: int = 1, pad=(1, 1), out: Optional[DevTensor] = None):
+    def conv3(self, x: DevTensor, w: ConvWeight, res: Optional[DevTensor] = None, stride: int = 1, pad=(1, 1), out: Optional[DevTensor] = None,
+              stats: bool = False):
         N, H, W, _ = x.shape
         OH = (H + (2 if pad == (1, 1) else 1) - 3) // stride + 1
         OW = (W + (2 if pad == (1, 1) else 1) - 3) // stride + 1
         if out is None:
             out = self.new(N, OH, OW, w.cout)
-        self.ctx.conv(x, w, out, N=N, IH=H, IW=W, OH=OH, OW=OW, stride=(stride, stride), pad=pad, res=res)
+        st = self._stats_for(out, N) if stats else None
+        self.ctx.conv(x, w, out, N=N, IH=H, IW=W, OH=OH, OW=OW, stride=(stride, stride), pad=pad, res=res,
+                      gn_stats=st, gn_groups=self.GN_GROUPS if st is not None else 0, gn_hw=OH * OW)
         return out
 
-    def linear(self, x: DevTensor, w: ConvWeight, res: Optional[DevTensor] = None, out: Optional[DevTensor] = None):
-        """x (..., Cin) -> (..., Cout) ; also 1x1 convs."""
+    def linear(self, x: DevTensor, w: ConvWeight, res: Optional[DevTensor] = None, out: Optional[DevTensor] = None, stats_imgs: int = 0):
+        """x (..., Cin) -> (..., Cout) ; also 1x1 convs.  stats_imgs > 0: also produce GroupNorm statistics (rows/stats_imgs pixels per image)."""
         rows = x.rows
         if out is None:
             out = self.new(*x.shape[:-1], w.cout)
-        self.ctx.conv(x, w, out, N=1, IH=1, IW=rows, OH=1, OW=rows, res=res)
+        st = self._stats_for(out, stats_imgs) if stats_imgs else None
+        self.ctx.conv(x, w, out, N=1, IH=1, IW=rows, OH=1, OW=rows, res=res,
+                      gn_stats=st, gn_groups=self.GN_GROUPS if st is not None else 0, gn_hw=(rows // stats_imgs) if stats_imgs else 0)
         return out
 
     def groupnorm(self, x: DevTensor, n: _Norm, groups: int, eps: float, silu: bool):
         N, H, W, C = x.shape
         out = self.new(N, H, W, C)
-        self.ctx.groupnorm(x, N, H * W, groups, eps, n.gamma, n.beta, silu, out)
+        if x.stats is not None and x.stats[1] == groups:
+            self.ctx.groupnorm_apply(x, N, H * W, groups, eps, x.stats[0], n.gamma, n.beta, silu, out)
+        else:
+            self.ctx.groupnorm(x, N, H * W, groups, eps, n.gamma, n.beta, silu, out)
         return out
 
     def layernorm(self, x: DevTensor, n: _Norm, eps: float = 1e-5):
@@ -165,13 +187,13 @@ class Builder:
 
     # -- blocks
     def resnet(self, x: DevTensor, r: _Resnet, groups: int, eps: float):
-        h = self.conv3(self.groupnorm(x, r.norm1, groups, eps, True), r.conv1)
+        h = self.conv3(self.groupnorm(x, r.norm1, groups, eps, True), r.conv1, stats=True)
         h = self.groupnorm(h, r.norm2, groups, eps, True)
         skip = self.linear(x, r.shortcut) if r.shortcut is not None else x
-        return self.conv3(h, r.conv2, res=skip)
+        return self.conv3(h, r.conv2, res=skip, stats=True)
 
     def attention(self, a, xq: DevTensor, B: int, nq: int, res: DevTensor, kv_src: Optional[DevTensor] = None, n_keys: Optional[int] = None,
-                  n_valid: Optional[int] = None):
+                  n_valid: Optional[int] = None, stats_imgs: int = 0):
         """xq: (B*nq, C) normalised tokens.  Self-attention when kv_src is None, else keys/values from kv_src (B*n_keys, kv_dim).
         Key counts are padded to a multiple of 16 (tensor-core N / K granularity); padded keys get probability 0."""
         ctx, H, dp, d = self.ctx, a.heads, a.dp, a.d
@@ -204,7 +226,7 @@ class Builder:
         ov = DevTensor(O.ptr, (nq, dp), pitch=Hdp)
         ctx.conv(sv, None, ov, N=1, IH=1, IW=nq, OH=1, OW=nq, cin=nk, cout=dp, w_ptr=VT.ptr, ktot=nk,
                  zbatch=B * H, zdiv=H, in_z=(H * nq * nk, nq * nk), w_z=(H * dp * nk, dp * nk), out_z=(nq * Hdp, dp))
-        return self.linear(O, a.out, res=res)
+        return self.linear(O, a.out, res=res, stats_imgs=stats_imgs)
 
     def transformer(self, x: DevTensor, t: _Transformer, audio: DevTensor, groups: int):
         N, H, W, C = x.shape
@@ -221,7 +243,7 @@ class Builder:
         N, H, W, C = x.shape
         up = self.new(N, 2 * H, 2 * W, C)
         self.ctx.upsample2x(x, N, H, W, up)
-        return self.conv3(up, w)
+        return self.conv3(up, w, stats=True)
 
     def concat(self, a: DevTensor, b: DevTensor):
         N, H, W, _ = a.shape
@@ -341,7 +363,7 @@ class MuseTalkModel:
         """latents16 (B,h,w,16) [8 real channels], audio_pe (B*64, 384) -> predicted latents (B,h,w,16) [4 real channels]."""
         cfg = self.ucfg
         G, eps = cfg.norm_groups, cfg.norm_eps
-        h = b.conv3(latents16, self.u_conv_in)
+        h = b.conv3(latents16, self.u_conv_in, stats=True)
         skips = [h]
         for i, blk in enumerate(self.u_down):
             for j, r in enumerate(blk["res"]):
@@ -374,15 +396,17 @@ class MuseTalkModel:
         r0, gn, attn, r1 = mid
         h = b.resnet(h, r0, G, eps)
         N, H, W, C = h.shape
-        h = b.attention(attn, b.groupnorm(h, gn, G, eps, False), N, H * W, res=h)
+        h = b.attention(attn, b.groupnorm(h, gn, G, eps, False), N, H * W, res=h, stats_imgs=N)
+        st = h.stats
         h = DevTensor(h.ptr, (N, H, W, C))
+        h.stats = st
         return b.resnet(h, r1, G, eps)
 
     def emit_vae_decode(self, b: Builder, pred16: DevTensor, out_u8: DevTensor, taps: Optional[dict] = None) -> DevTensor:
         """pred16 (B,h,w,16) latents [4 real channels] -> uint8 BGR image written to out_u8 (B,8h,8w,3)."""
         cfg = self.vcfg
         G, eps = cfg.norm_groups, cfg.norm_eps
-        h = b.conv3(b.linear(DevTensor(pred16.ptr, (*pred16.shape[:-1], 16), pitch=pred16.pitch), self.v_post_quant), self.v_dec_in)
+        h = b.conv3(b.linear(DevTensor(pred16.ptr, (*pred16.shape[:-1], 16), pitch=pred16.pitch), self.v_post_quant), self.v_dec_in, stats=True)
         h = self._emit_vae_mid(b, h, self.v_dec_mid, G, eps)
         if taps is not None:
             taps["dec_mid"] = h
@@ -407,12 +431,12 @@ class MuseTalkModel:
         x = b.new(2 * B, H, W, 16)
         self.ctx.vae_pre(img_u8, B, H, W, True, DevTensor(x.ptr, (B, H, W, 16)))                                  # masked copies
         self.ctx.vae_pre(img_u8, B, H, W, False, DevTensor(x.offset(B * H * W * 16), (B, H, W, 16)))              # reference copies
-        h = b.conv3(x, self.v_enc_in)
+        h = b.conv3(x, self.v_enc_in, stats=True)
         for blk in self.v_enc_down:
             for r in blk["res"]:
                 h = b.resnet(h, r, G, eps)
             if blk["down"] is not None:
-                h = b.conv3(h, blk["down"], stride=2, pad=(0, 0))     # F.pad(x,(0,1,0,1)) + conv s2 p0
+                h = b.conv3(h, blk["down"], stride=2, pad=(0, 0), stats=True)     # F.pad(x,(0,1,0,1)) + conv s2 p0
         h = self._emit_vae_mid(b, h, self.v_enc_mid, G, eps)
         m = b.conv3(b.groupnorm(h, self.v_enc_norm_out, G, eps, True), self.v_enc_out)   # (2B,h,w,16): moments in 0..7
         _, lh, lw, mc = m.shape

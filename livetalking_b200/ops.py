@@ -16,7 +16,7 @@ from ._capi import ConvOp, MtPasteOp, check, lib
 
 
 class DevTensor:
-    __slots__ = ("ptr", "shape", "dtype", "nbytes", "pitch", "c_off")
+    __slots__ = ("ptr", "shape", "dtype", "nbytes", "pitch", "c_off", "stats")
 
     def __init__(self, ptr: int, shape: Sequence[int], dtype=np.float16, pitch: Optional[int] = None, c_off: int = 0):
         self.ptr = int(ptr)
@@ -25,6 +25,7 @@ class DevTensor:
         self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
         self.pitch = int(pitch) if pitch is not None else self.shape[-1]   # elements between consecutive pixels / rows
         self.c_off = int(c_off)                                            # first channel inside the pitch
+        self.stats = None                                                  # (DevTensor, groups): GroupNorm statistics produced with the tensor
 
     @property
     def C(self) -> int:
@@ -139,7 +140,8 @@ class Ctx:
     def conv(self, x: DevTensor, w: "ConvWeight", out: DevTensor, *, N: int, IH: int, IW: int, OH: int, OW: int, stride=(1, 1),
              pad=(0, 0), res: Optional[DevTensor] = None, relu: bool = False, cin: Optional[int] = None, no_halo: bool = False,
              zbatch: int = 0, zdiv: int = 1, in_z=(0, 0), w_z=(0, 0), out_z=(0, 0), w_ptr: Optional[int] = None,
-             ktot: Optional[int] = None, cout: Optional[int] = None, in_ptr: Optional[int] = None, out_ptr: Optional[int] = None):
+             ktot: Optional[int] = None, cout: Optional[int] = None, in_ptr: Optional[int] = None, out_ptr: Optional[int] = None,
+             gn_stats: Optional[DevTensor] = None, gn_groups: int = 0, gn_hw: int = 0):
         d = ConvOp()
         d.in_ = in_ptr if in_ptr is not None else x.ptr
         d.w = w_ptr if w_ptr is not None else w.w.ptr
@@ -165,12 +167,19 @@ class Ctx:
         d.in_zo, d.in_zi = in_z
         d.w_zo, d.w_zi = w_z
         d.out_zo, d.out_zi = out_z
+        d.gn_stats = gn_stats.ptr if gn_stats is not None else None
+        d.gn_groups, d.gn_hw = gn_groups, gn_hw
         check(lib().ltb_op_conv2d(self._h, C.byref(d)))
 
     def groupnorm(self, x: DevTensor, N: int, HW: int, groups: int, eps: float, gamma: DevTensor, beta: DevTensor, silu: bool,
                   out: DevTensor):
         check(lib().ltb_op_groupnorm(self._h, C.c_void_p(x.ptr), N, HW, x.C, x.pitch, x.c_off, groups, eps, C.c_void_p(gamma.ptr),
                                      C.c_void_p(beta.ptr), int(silu), C.c_void_p(out.ptr), out.pitch, out.c_off))
+
+    def groupnorm_apply(self, x: DevTensor, N: int, HW: int, groups: int, eps: float, stats: DevTensor, gamma: DevTensor, beta: DevTensor,
+                        silu: bool, out: DevTensor):
+        check(lib().ltb_op_groupnorm_apply(self._h, C.c_void_p(x.ptr), N, HW, x.C, x.pitch, x.c_off, groups, eps, C.c_void_p(stats.ptr),
+                                           C.c_void_p(gamma.ptr), C.c_void_p(beta.ptr), int(silu), C.c_void_p(out.ptr), out.pitch, out.c_off))
 
     def layernorm(self, x: DevTensor, rows: int, Cc: int, eps: float, gamma: DevTensor, beta: DevTensor, out: DevTensor):
         check(lib().ltb_op_layernorm(self._h, C.c_void_p(x.ptr), rows, Cc, eps, C.c_void_p(gamma.ptr), C.c_void_p(beta.ptr),

@@ -135,3 +135,31 @@ def test_full_width_networks_once():
     assert np.abs(got_lat - want_lat).max() <= 0.08 * max(1.0, np.abs(want_lat).max())
     assert psnr_u8(got_u8, want_u8) >= 40.0, psnr_u8(got_u8, want_u8)
     ctx.close()
+
+
+def test_fused_groupnorm_statistics_path(small_nets):
+    """ltb_conv_op.gn_stats: statistics accumulated by the conv epilogue (or its fallback pass) must give the same network
+    output as the separate statistics kernel."""
+    from livetalking_b200 import engine
+    from livetalking_b200 import musetalk as MT
+    from livetalking_b200.ops import Ctx
+    from oracle import musetalk_ref as M
+    from oracle.wav2lip_ref import psnr_u8
+    ucfg, vcfg, us, vs = small_nets
+    engine.set_device(0)
+    lat, aud = M.synth_latents_and_audio(1, seed=6)
+    outs = []
+    for fuse in (False, True):
+        MT.Builder.FUSE_GN_STATS = fuse
+        try:
+            ctx = Ctx()
+            model = MT.MuseTalkModel(ctx, us, vs, ucfg, vcfg, with_encoder=False)
+            av, *_ = _avatar(ctx, lat.numpy(), 1)
+            s = MT.MuseTalkSession(model, av, 1)
+            outs.append(s.infer(0, aud.numpy()))
+            ctx.close()
+        finally:
+            MT.Builder.FUSE_GN_STATS = False
+    assert psnr_u8(outs[0], outs[1]) >= 48.0
+    want = M.decode_latents_u8(vs, vcfg, M.unet_forward(us, ucfg, lat, M.positional_encoding(aud)))
+    assert psnr_u8(outs[1], want) >= 40.0
