@@ -305,10 +305,10 @@ int conv_gather_pick_bn(const ConvParams& p) {
 __global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __restrict__ ws, int ksplit, int M, int Cout,
                                                               const float* __restrict__ bias, const __half* __restrict__ res, int RCtot,
                                                               int rc_off, int relu, __half* __restrict__ out, int OCtot, int oc_off) {
-  const int vpr = Cout / 8;
-  const size_t total = (size_t)M * vpr;
+  const unsigned vpr = Cout / 8;
+  const unsigned total = (unsigned)M * vpr;
   const size_t slice = (size_t)M * Cout;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+  for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
     const size_t m = i / vpr;
     const int c = (int)(i % vpr) * 8;
     float f[8];

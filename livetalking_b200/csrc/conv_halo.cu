@@ -221,53 +221,71 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
 #pragma unroll
             for (int i = 0; i < 8; ++i) gs[i] = gq[i] = 0.f;
 #pragma unroll
-            for (int g = 0; g < 32; g += 8) {
-              // packed-half epilogue (the narrow layers are epilogue-issue bound): fp32 accumulator + fp32 bias -> half2,
-              // then residual add / ReLU / saturation as half2 ops (3 instructions per element instead of 8)
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + g));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + g + 4));
-              uint4 ov;
-              __half2* oh = reinterpret_cast<__half2*>(&ov);
-              oh[0] = __floats2half2_rn(__uint_as_float(v[g + 0]) + b0.x, __uint_as_float(v[g + 1]) + b0.y);
-              oh[1] = __floats2half2_rn(__uint_as_float(v[g + 2]) + b0.z, __uint_as_float(v[g + 3]) + b0.w);
-              oh[2] = __floats2half2_rn(__uint_as_float(v[g + 4]) + b1.x, __uint_as_float(v[g + 5]) + b1.y);
-              oh[3] = __floats2half2_rn(__uint_as_float(v[g + 6]) + b1.z, __uint_as_float(v[g + 7]) + b1.w);
+            for (int g16 = 0; g16 < 32; g16 += 16) {
+              // packed-half epilogue: fp32 accumulator + fp32 bias -> half2, then residual add / ReLU / saturation as half2 ops.
+              // 16 channels (32 bytes = one full sector) per thread and instruction: 256-bit residual loads and output stores.
+              uint4 ovv[2], rvv[2];
               if (rptr) {
-                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rptr + c0 + g));
-                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) oh[u] = __hadd2(oh[u], rh[u]);
-              }
-              const __half2 hmax = __floats2half2_rn(65504.f, 65504.f);
-              const __half2 lo = p.relu ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(-65504.f, -65504.f);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) oh[u] = __hmin2(__hmax2(oh[u], lo), hmax);
-              if (row_ok) *reinterpret_cast<uint4*>(optr + c0 + g) = ov;
-              if (p.gn_stats && row_ok) {
-                float ps[4], pq[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float2 f2 = __half22float2(oh[u]);
-                  ps[u] = f2.x + f2.y;
-                  pq[u] = f2.x * f2.x + f2.y * f2.y;
-                }
-                if (p.gn_cpg == 4) {
-                  gs[g / 4] += ps[0] + ps[1];
-                  gq[g / 4] += pq[0] + pq[1];
-                  gs[g / 4 + 1] += ps[2] + ps[3];
-                  gq[g / 4 + 1] += pq[2] + pq[3];
+                if (p.wide_io) {
+                  ldg256(rptr + c0 + g16, rvv[0], rvv[1]);
                 } else {
-                  const float ts = (ps[0] + ps[1]) + (ps[2] + ps[3]), tq = (pq[0] + pq[1]) + (pq[2] + pq[3]);
-                  if (p.gn_cpg == 8) {
-                    gs[g / 8] += ts;
-                    gq[g / 8] += tq;
-                  } else if (p.gn_cpg == 16) {
-                    gs[g / 16] += ts;
-                    gq[g / 16] += tq;
-                  } else {
-                    gs[0] += ts;
-                    gq[0] += tq;
+                  rvv[0] = __ldg(reinterpret_cast<const uint4*>(rptr + c0 + g16));
+                  rvv[1] = __ldg(reinterpret_cast<const uint4*>(rptr + c0 + g16 + 8));
+                }
+              }
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const int g = g16 + hh * 8;
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + g));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + g + 4));
+                __half2* oh = reinterpret_cast<__half2*>(&ovv[hh]);
+                oh[0] = __floats2half2_rn(__uint_as_float(v[g + 0]) + b0.x, __uint_as_float(v[g + 1]) + b0.y);
+                oh[1] = __floats2half2_rn(__uint_as_float(v[g + 2]) + b0.z, __uint_as_float(v[g + 3]) + b0.w);
+                oh[2] = __floats2half2_rn(__uint_as_float(v[g + 4]) + b1.x, __uint_as_float(v[g + 5]) + b1.y);
+                oh[3] = __floats2half2_rn(__uint_as_float(v[g + 6]) + b1.z, __uint_as_float(v[g + 7]) + b1.w);
+                if (rptr) {
+                  const __half2* rh = reinterpret_cast<const __half2*>(&rvv[hh]);
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) oh[u] = __hadd2(oh[u], rh[u]);
+                }
+                const __half2 hmax = __floats2half2_rn(65504.f, 65504.f);
+                const __half2 lo = p.relu ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(-65504.f, -65504.f);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) oh[u] = __hmin2(__hmax2(oh[u], lo), hmax);
+                if (p.gn_stats && row_ok) {
+                  float ps[4], pq[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const float2 f2 = __half22float2(oh[u]);
+                    ps[u] = f2.x + f2.y;
+                    pq[u] = f2.x * f2.x + f2.y * f2.y;
                   }
+                  if (p.gn_cpg == 4) {
+                    gs[g / 4] += ps[0] + ps[1];
+                    gq[g / 4] += pq[0] + pq[1];
+                    gs[g / 4 + 1] += ps[2] + ps[3];
+                    gq[g / 4 + 1] += pq[2] + pq[3];
+                  } else {
+                    const float ts = (ps[0] + ps[1]) + (ps[2] + ps[3]), tq = (pq[0] + pq[1]) + (pq[2] + pq[3]);
+                    if (p.gn_cpg == 8) {
+                      gs[g / 8] += ts;
+                      gq[g / 8] += tq;
+                    } else if (p.gn_cpg == 16) {
+                      gs[g / 16] += ts;
+                      gq[g / 16] += tq;
+                    } else {
+                      gs[0] += ts;
+                      gq[0] += tq;
+                    }
+                  }
+                }
+              }
+              if (row_ok) {
+                if (p.wide_io) {
+                  stg256(optr + c0 + g16, ovv[0], ovv[1]);
+                } else {
+                  *reinterpret_cast<uint4*>(optr + c0 + g16) = ovv[0];
+                  *reinterpret_cast<uint4*>(optr + c0 + g16 + 8) = ovv[1];
                 }
               }
             }
@@ -440,6 +458,11 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
   h.M = p.M;
   h.Cin = p.Cin;
   h.gn_stats = nullptr;
+  // 256-bit epilogue accesses need 32-byte aligned rows
+  h.wide_io = ((p.OCtot % 16) == 0 && (p.oc_off % 16) == 0 && (reinterpret_cast<uintptr_t>(p.out) % 32) == 0 &&
+               (!p.res || ((p.RCtot % 16) == 0 && (p.rc_off % 16) == 0 && (reinterpret_cast<uintptr_t>(p.res) % 32) == 0)))
+                  ? 1
+                  : 0;
   h.OCtot = p.OCtot;
   h.oc_off = p.oc_off;
   h.RCtot = p.RCtot;

@@ -29,6 +29,7 @@ struct alignas(64) HaloParams {
   // epilogue from the fp16-rounded values: saves the separate statistics pass of the following GroupNorm
   float* gn_stats;
   int gn_groups, gn_cpg, gn_hw;
+  int wide_io;  // 1: 32-byte aligned rows -> 256-bit residual loads / output stores
 };
 
 struct HaloPlan {

@@ -117,28 +117,47 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
     s_ab[C + c] = beta[c] - s_mean[g] * a;
   }
   __syncthreads();
-  const int vpr = C / 8;  // vectors per pixel
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * 256) {
-    const int p = (int)(i / vpr), cv = (int)(i - (size_t)p * vpr) * 8;
-    const uint4 v = *reinterpret_cast<const uint4*>(x + ((size_t)n * HW + p) * Ctot + c_off + cv);
-    const __half2* h = reinterpret_cast<const __half2*>(&v);
-    const float4 a0 = *reinterpret_cast<const float4*>(s_ab + cv), a1 = *reinterpret_cast<const float4*>(s_ab + cv + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(s_ab + C + cv), b1 = *reinterpret_cast<const float4*>(s_ab + C + cv + 4);
-    float y[8];
-    float2 t;
-    t = __half22float2(h[0]); y[0] = fmaf(t.x, a0.x, b0.x); y[1] = fmaf(t.y, a0.y, b0.y);
-    t = __half22float2(h[1]); y[2] = fmaf(t.x, a0.z, b0.z); y[3] = fmaf(t.y, a0.w, b0.w);
-    t = __half22float2(h[2]); y[4] = fmaf(t.x, a1.x, b1.x); y[5] = fmaf(t.y, a1.y, b1.y);
-    t = __half22float2(h[3]); y[6] = fmaf(t.x, a1.z, b1.z); y[7] = fmaf(t.y, a1.w, b1.w);
-    if (silu) {
+  const unsigned vpr = C / 8;  // vectors per pixel
+  const unsigned tv = (unsigned)total_vec;   // per image: HW * C/8 < 2^31
+  const unsigned stride = gridDim.x * 256u;
+  const __half* xin = x + (size_t)n * HW * Ctot + c_off;
+  __half* yout = out + (size_t)n * HW * OCtot + oc_off;
+  // 4 independent 16-byte loads in flight per thread (a single dependent load per iteration left the kernel latency-bound
+  // at ~1.6 TB/s)
+  for (unsigned i0 = blockIdx.x * 256u + threadIdx.x; i0 < tv; i0 += 4 * stride) {
+    uint4 v[4];
+    unsigned pp[4];
+    int cvv[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = silu_f(y[j]);
+    for (int u = 0; u < 4; ++u) {
+      const unsigned i = i0 + u * stride;
+      pp[u] = i / vpr;
+      cvv[u] = (int)(i - pp[u] * vpr) * 8;
+      if (i < tv) v[u] = *reinterpret_cast<const uint4*>(xin + (size_t)pp[u] * Ctot + cvv[u]);
     }
-    uint4 o;
-    __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
-    *reinterpret_cast<uint4*>(out + ((size_t)n * HW + p) * OCtot + oc_off + cv) = o;
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u * stride >= tv) break;
+      const int cv = cvv[u];
+      const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+      const float4 a0 = *reinterpret_cast<const float4*>(s_ab + cv), a1 = *reinterpret_cast<const float4*>(s_ab + cv + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(s_ab + C + cv), b1 = *reinterpret_cast<const float4*>(s_ab + C + cv + 4);
+      float y[8];
+      float2 t;
+      t = __half22float2(h[0]); y[0] = fmaf(t.x, a0.x, b0.x); y[1] = fmaf(t.y, a0.y, b0.y);
+      t = __half22float2(h[1]); y[2] = fmaf(t.x, a0.z, b0.z); y[3] = fmaf(t.y, a0.w, b0.w);
+      t = __half22float2(h[2]); y[4] = fmaf(t.x, a1.x, b1.x); y[5] = fmaf(t.y, a1.y, b1.y);
+      t = __half22float2(h[3]); y[6] = fmaf(t.x, a1.z, b1.z); y[7] = fmaf(t.y, a1.w, b1.w);
+      if (silu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = silu_f(y[j]);
+      }
+      uint4 o;
+      __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+      *reinterpret_cast<uint4*>(yout + (size_t)pp[u] * OCtot + cv) = o;
+    }
   }
 }
 
@@ -302,8 +321,8 @@ cudaError_t launch_softmax(const __half* x, int rows, int cols, int ld, int vali
 // ------------------------------------------------------------------------------------------------ GEGLU / GELU / add
 // h: rows x 2H  ->  out rows x H = h[:, :H] * gelu(h[:, H:])   (diffusers GEGLU: hidden, gate = proj(x).chunk(2))
 __global__ void __launch_bounds__(256) geglu_kernel(const __half* __restrict__ h, size_t total_vec, int H, __half* __restrict__ out) {
-  const int vpr = H / 8;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * 256) {
+  const unsigned vpr = H / 8;
+  for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < (unsigned)total_vec; i += gridDim.x * 256u) {
     const size_t r = i / vpr;
     const int cv = (int)(i % vpr) * 8;
     const uint4 a = *reinterpret_cast<const uint4*>(h + r * 2 * H + cv);
@@ -329,11 +348,12 @@ cudaError_t launch_geglu(const __half* h, size_t rows, int H, __half* out, cudaS
 // elementwise: out = act(x (+ y broadcast over rows with period `period` vectors)) ; act 0 none, 1 gelu(erf), 2 silu
 __global__ void __launch_bounds__(256) eltwise_kernel(const __half* __restrict__ x, const __half* __restrict__ y, size_t total_vec,
                                                       size_t period_vec, int act, __half* __restrict__ out) {
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * 256) {
+  const unsigned tv = (unsigned)total_vec, pv = (unsigned)period_vec;
+  for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < tv; i += gridDim.x * 256u) {
     const uint4 a = reinterpret_cast<const uint4*>(x)[i];
     const __half* ah = reinterpret_cast<const __half*>(&a);
     uint4 b = make_uint4(0, 0, 0, 0);
-    if (y) b = reinterpret_cast<const uint4*>(y)[i % period_vec];
+    if (y) b = reinterpret_cast<const uint4*>(y)[i % pv];
     const __half* bh = reinterpret_cast<const __half*>(&b);
     uint4 o;
     __half* oh = reinterpret_cast<__half*>(&o);
@@ -358,15 +378,15 @@ cudaError_t launch_eltwise(const __half* x, const __half* y, size_t n, size_t pe
 
 // ------------------------------------------------------------------------------------------------ layout helpers
 __global__ void __launch_bounds__(256) upsample2x_kernel(const __half* __restrict__ x, int N, int H, int W, int C, __half* __restrict__ out) {
-  const int vpp = C / 8;
-  const size_t total = (size_t)N * (2 * H) * (2 * W) * vpp;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-    const int cv = (int)(i % vpp);
-    size_t p = i / vpp;
-    const int ox = (int)(p % (2 * W));
-    p /= (2 * W);
-    const int oy = (int)(p % (2 * H));
-    const int n = (int)(p / (2 * H));
+  const unsigned vpp = C / 8;
+  const unsigned total = (unsigned)N * (2 * H) * (2 * W) * vpp;   // < 2^32 for every tensor of the path
+  for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
+    const unsigned cv = i % vpp;
+    unsigned p = i / vpp;
+    const unsigned ox = p % (2u * W);
+    p /= (2u * W);
+    const unsigned oy = p % (2u * H);
+    const unsigned n = p / (2u * H);
     reinterpret_cast<uint4*>(out)[i] =
         reinterpret_cast<const uint4*>(x)[(((size_t)n * H + (oy >> 1)) * W + (ox >> 1)) * vpp + cv];
   }
@@ -382,9 +402,9 @@ cudaError_t launch_upsample2x(const __half* x, int N, int H, int W, int C, __hal
 
 __global__ void __launch_bounds__(256) copy_channels_kernel(const __half* __restrict__ src, size_t rows, int C, int SCtot, int sc_off,
                                                             __half* __restrict__ dst, int DCtot, int dc_off) {
-  const int vpr = C / 8;
-  const size_t total = rows * vpr;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+  const unsigned vpr = C / 8;
+  const unsigned total = (unsigned)(rows * vpr);
+  for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
     const size_t r = i / vpr;
     const int cv = (int)(i % vpr) * 8;
     *reinterpret_cast<uint4*>(dst + r * DCtot + dc_off + cv) = *reinterpret_cast<const uint4*>(src + r * SCtot + sc_off + cv);
