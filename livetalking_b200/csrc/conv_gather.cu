@@ -263,13 +263,8 @@ __global__ void __launch_bounds__(160) conv_gather_umma_kernel(const __grid_cons
 template <int BN, int KB>
 static cudaError_t launch_one(const ConvParams& p, cudaStream_t st) {
   using C = GatherCfg<BN, KB>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gather_umma_kernel<BN, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static SmemConfigOnce once;
+  if (cudaError_t e = once.ensure(conv_gather_umma_kernel<BN, KB>, C::SMEM_BYTES); e != cudaSuccess) return e;
   dim3 grid((p.M + 127) / 128, p.Cout / BN, p.ksplit > 1 ? p.ksplit : p.nphases * (p.zbatch > 1 ? p.zbatch : 1));
   conv_gather_umma_kernel<BN, KB><<<grid, 160, C::SMEM_BYTES, st>>>(p);
   return cudaGetLastError();

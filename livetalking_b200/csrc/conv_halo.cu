@@ -18,6 +18,7 @@
 #include <mutex>
 
 #include "conv_halo.h"
+#include "ltb_internal.h"
 #include "ptx_sm100.cuh"
 
 namespace ltb {
@@ -503,13 +504,8 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
 template <int BN, int NSUB, int NACC, int TAPS = 9>
 static cudaError_t launch_cfg(const HaloPlan& pl, int sms, cudaStream_t st) {
   using C = HaloCfg<BN, NSUB, NACC, TAPS>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_umma_kernel<BN, NSUB, NACC, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static SmemConfigOnce once;
+  if (cudaError_t e = once.ensure(conv_halo_umma_kernel<BN, NSUB, NACC, TAPS>, C::SMEM_BYTES); e != cudaSuccess) return e;
   const int grid = pl.hp.total_tiles < sms ? pl.hp.total_tiles : sms;
   conv_halo_umma_kernel<BN, NSUB, NACC, TAPS><<<grid, 320, C::SMEM_BYTES, st>>>(pl.hp);
   return cudaGetLastError();

@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
+#include <atomic>
 #include <string>
 
 #include "conv_params.h"
@@ -19,6 +20,22 @@ int fail(const char* file, int line, const std::string& msg);
     cudaError_t _e = (expr);                                                                   \
     if (_e != cudaSuccess) return LTB_FAIL(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
   } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: configure each kernel once per device, thread-safely
+struct SmemConfigOnce {
+  std::atomic<unsigned long long> done{0};  // bit d = configured on device d
+  template <typename K>
+  cudaError_t ensure(K kernel, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+  }
+};
 
 // ---- kernel launchers ----
 // splitk_ws: optional zero-initialised fp32 workspace (one per stream) enabling split-K for small-M deep-K layers

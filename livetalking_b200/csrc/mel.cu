@@ -9,6 +9,7 @@
 // latency-bound, and float64 keeps the windows within 1e-9 of the CPU path.  The 800-point DFT is evaluated
 // directly against a shared-memory twiddle table (800 = 2^5 * 5^2; a radix FFT would save FLOPs nobody is short of).
 #include <cmath>
+#include <mutex>
 #include <vector>
 
 #include "ltb_internal.h"
@@ -94,8 +95,10 @@ static double mel_to_hz(double m) {
 }
 
 static double* g_fb_dev[64] = {nullptr};
+static std::mutex g_fb_mutex;
 
 static cudaError_t ensure_filterbank(double** out) {
+  std::lock_guard<std::mutex> lock(g_fb_mutex);
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;

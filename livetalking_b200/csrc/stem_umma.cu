@@ -181,17 +181,17 @@ int stem_make_plan(const __half* img_pad, int B, const __half* w_tap_major, cons
 }
 
 cudaError_t launch_stem(const StemParams& sp, cudaStream_t st) {
-  static bool configured = false;
-  static int sms = 0;
+  static SmemConfigOnce once;
+  static std::atomic<int> sms_cached{0};
   constexpr int smem = kStemWBytes + kStemStages * kStemAStride + 1024;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(stem_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
+  if (cudaError_t e = once.ensure(stem_umma_kernel, smem); e != cudaSuccess) return e;
+  int sms = sms_cached.load();
+  if (!sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
-    configured = true;
+    sms_cached.store(sms);
   }
   const int grid = sp.total_tiles < sms ? sp.total_tiles : sms;
   stem_umma_kernel<<<grid, 192, smem, st>>>(sp);

@@ -738,6 +738,8 @@ int ltb_w2l_model_destroy(ltb_w2l_model* m) {
   return 0;
 }
 
+int ltb_w2l_avatar_destroy(ltb_w2l_avatar* a);
+
 int ltb_w2l_avatar_create(const uint8_t* faces, const uint8_t* frames, const int32_t* coords, int n, int H, int W,
                           ltb_w2l_avatar** out) {
   if (!faces || !frames || !coords || !out || n <= 0 || H <= 0 || W <= 0) return LTB_FAIL("bad avatar arguments");
@@ -746,19 +748,23 @@ int ltb_w2l_avatar_create(const uint8_t* faces, const uint8_t* frames, const int
     if (y1 < 0 || x1 < 0 || y2 > H || x2 > W || y2 <= y1 || x2 <= x1)
       return LTB_FAIL("avatar coords[" + std::to_string(i) + "] outside the frame");
   }
-  auto a = std::make_unique<ltb_w2l_avatar>();
-  LTB_CUDA(cudaGetDevice(&a->device));
+  auto* a = new ltb_w2l_avatar();
   a->n = n;
   a->H = H;
   a->W = W;
   a->coords_host.assign(coords, coords + (size_t)n * 4);
-  LTB_CUDA(cudaMalloc(reinterpret_cast<void**>(&a->faces), (size_t)n * 65536 * 3));
-  LTB_CUDA(cudaMalloc(reinterpret_cast<void**>(&a->frames), (size_t)n * H * W * 3));
-  LTB_CUDA(cudaMalloc(reinterpret_cast<void**>(&a->coords), (size_t)n * 4 * sizeof(int)));
-  LTB_CUDA(cudaMemcpy(a->faces, faces, (size_t)n * 65536 * 3, cudaMemcpyHostToDevice));
-  LTB_CUDA(cudaMemcpy(a->frames, frames, (size_t)n * H * W * 3, cudaMemcpyHostToDevice));
-  LTB_CUDA(cudaMemcpy(a->coords, coords, (size_t)n * 4 * sizeof(int), cudaMemcpyHostToDevice));
-  *out = a.release();
+  cudaError_t e = cudaGetDevice(&a->device);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&a->faces), (size_t)n * 65536 * 3);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&a->frames), (size_t)n * H * W * 3);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&a->coords), (size_t)n * 4 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(a->faces, faces, (size_t)n * 65536 * 3, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(a->frames, frames, (size_t)n * H * W * 3, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(a->coords, coords, (size_t)n * 4 * sizeof(int), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    ltb_w2l_avatar_destroy(a);
+    return LTB_FAIL(std::string("avatar upload: ") + cudaGetErrorString(e));
+  }
+  *out = a;
   return 0;
 }
 
