@@ -332,7 +332,7 @@ def run_ours(args):
         per_op = [(int(k), round(float(m), 4), float(f)) for k, m, f in zip(kinds, med, flops)]
         if args.dump_ops:
             os.makedirs(os.path.dirname(os.path.abspath(args.dump_ops)), exist_ok=True)
-            json.dump({"ops": per_op, "note": "kind(0 conv gather,1 prep,2 audio_conv0,3 head,4 conv halo), median ms, algorithmic flops"},
+            json.dump({"ops": per_op, "note": "kind(0 conv gather,1 prep,2 audio_conv0,3 head,4 conv halo,5 stem,6 mel), median ms, algorithmic flops"},
                       open(args.dump_ops, "w"))
 
     if rank == 0:

@@ -49,7 +49,11 @@ def _deps_mtime() -> float:
     return mt
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), tag: str = "") -> str:
+    """defines/tag: diagnostic variants only (e.g. tools/diag_halo.py builds lib/libltb200_diag.so with -DLTB_HALO_DIAG)."""
+    LIB = os.path.join(LIBDIR, f"libltb200{tag}.so")
+    OBJDIR = os.path.join(HERE, "build" + tag)
+    NVCC_FLAGS = [*globals()["NVCC_FLAGS"], *[f"-D{d}" for d in defines]]
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     nvcc = _nvcc()

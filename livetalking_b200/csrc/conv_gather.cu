@@ -230,8 +230,10 @@ __global__ void __launch_bounds__(160) conv_gather_umma_kernel(const __grid_cons
       }
     }
   } else {
-    // ------------------------------------------------------------------ MMA issuer (warp 4, one lane)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp 4; warp-uniform control flow,
+    // tcgen05 instructions predicated on the elected lane — see umma_f16_lohi_if)
+    {
+      const uint32_t leader = elect_one() ? 1u : 0u;
       constexpr uint32_t idesc = umma_idesc_f16(128, BN);
       for (int it = 0; it < kiters; ++it) {
         const int stage = it % C::STAGES;
@@ -243,11 +245,11 @@ __global__ void __launch_bounds__(160) conv_gather_umma_kernel(const __grid_cons
         for (int k = 0; k < KB / 16; ++k) {
           const uint64_t ad = umma_smem_desc(a_base + k * 32, C::SBO, C::LAYOUT);
           const uint64_t bd = umma_smem_desc(b_base + k * 32, C::SBO, C::LAYOUT);
-          umma_f16(tmem, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+          umma_f16_if(leader, tmem, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
         }
-        umma_commit(smem_u32(&bar_empty[stage]));
+        umma_commit_if(leader, smem_u32(&bar_empty[stage]));
       }
-      umma_commit(smem_u32(&bar_accum));
+      umma_commit_if(leader, smem_u32(&bar_accum));
     }
     __syncwarp();
   }

@@ -21,6 +21,13 @@
 #include "ltb_internal.h"
 #include "ptx_sm100.cuh"
 
+#ifdef LTB_HALO_DIAG
+#include <cstdlib>
+#define LTB_DIAG(bit) (p.dbg & (bit))
+#else
+#define LTB_DIAG(bit) 0
+#endif
+
 namespace ltb {
 
 constexpr int kHaloP = 10;  // halo row pitch in pixels (8 + 2)
@@ -109,13 +116,22 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
         for (int c = 0; c < chunks; ++c) {
           const uint32_t as = ai % C::A_STAGES;
           mbar_wait(smem_u32(&a_empty[as]), ((ai / C::A_STAGES) & 1u) ^ 1u);
+          if (LTB_DIAG(8)) {
+            mbar_arrive(smem_u32(&a_full[as]));
+          } else {
           mbar_arrive_expect_tx(smem_u32(&a_full[as]), C::A_BYTES_RAW);
           if (TAPS == 9) tma_load_4d(a_smem + as * C::A_BYTES, &p.tm_in, smem_u32(&a_full[as]), c * 64, x0, y0, img);
           else tma_load_2d(a_smem + as * C::A_BYTES, &p.tm_in, smem_u32(&a_full[as]), c * 64, mt * (128 * NSUB));
+          }
           ++ai;
           for (int j = 0; j < C::TG; ++j) {
             const uint32_t bs = bi % C::B_STAGES;
             mbar_wait(smem_u32(&b_empty[bs]), ((bi / C::B_STAGES) & 1u) ^ 1u);
+            if (LTB_DIAG(16)) {
+              mbar_arrive(smem_u32(&b_full[bs]));
+              ++bi;
+              continue;
+            }
             mbar_arrive_expect_tx(smem_u32(&b_full[bs]), C::B_BYTES);
             if (TAPS == 9) tma_load_3d(b_smem + bs * C::B_BYTES, &p.tm_w, smem_u32(&b_full[bs]), c * 64, nt * BN, j * 3);
             else tma_load_2d(b_smem + bs * C::B_BYTES, &p.tm_w, smem_u32(&b_full[bs]), c * 64, nt * BN);
@@ -126,7 +142,9 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // =============================================================== MMA issuer
-    if (lane == 0) {
+    // warp-uniform: all 32 lanes walk the pipeline, the tcgen05 instructions are predicated on the elected lane
+    {
+      const uint32_t leader = elect_one() ? 1u : 0u;
       constexpr uint32_t idesc = umma_idesc_f16(128, BN);
       constexpr uint32_t kADescHi = ((C::P * 128) >> 4) | (1u << 14) | (2u << 29);    // SBO = halo pitch (1280 B) / 1024 B in GEMM mode
       constexpr uint32_t kBDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);            // SBO = 1024 B
@@ -158,18 +176,19 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
               for (int sub = 0; sub < NSUB; ++sub) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  umma_f16_lohi(d_tap + sub * BN, a_lo_tap + sub * (16 * C::P * 8) + k * 2, kADescHi,
+                  if (LTB_DIAG(4)) continue;
+                  umma_f16_lohi_if(leader, d_tap + sub * BN, a_lo_tap + sub * (16 * C::P * 8) + k * 2, kADescHi,
                                 b_lo0 + tt * (BN * 8) + k * 2, kBDescHi, idesc, (fresh && k == 0) ? 0u : 1u);
                 }
               }
             }
-            umma_commit(smem_u32(&b_empty[bs]));
+            umma_commit_if(leader, smem_u32(&b_empty[bs]));
             ++bi;
           }
-          umma_commit(smem_u32(&a_empty[as]));
+          umma_commit_if(leader, smem_u32(&a_empty[as]));
           ++ai;
         }
-        umma_commit(smem_u32(&acc_full[buf]));
+        umma_commit_if(leader, smem_u32(&acc_full[buf]));
       }
     }
     __syncwarp();
@@ -215,6 +234,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
 #pragma unroll 1
           for (int c0 = 0; c0 < BN; c0 += 32) {
             if (((((acc * NSUB + sub) * BN + c0) >> 5) & 1) != grp) continue;
+            if (LTB_DIAG(2)) continue;
             uint32_t v[32];
             tmem_ld32(tbase + (acc * NSUB + sub) * BN + c0, v);
             tmem_ld_wait();
@@ -226,7 +246,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
               // packed-half epilogue: fp32 accumulator + fp32 bias -> half2, then residual add / ReLU / saturation as half2 ops.
               // 16 channels (32 bytes = one full sector) per thread and instruction: 256-bit residual loads and output stores.
               uint4 ovv[2], rvv[2];
-              if (rptr) {
+              if (rptr && !LTB_DIAG(1)) {
                 if (p.wide_io) {
                   ldg256(rptr + c0 + g16, rvv[0], rvv[1]);
                 } else {
@@ -281,7 +301,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
                   }
                 }
               }
-              if (row_ok) {
+              if (row_ok && !LTB_DIAG(1)) {
                 if (p.wide_io) {
                   stg256(optr + c0 + g16, ovv[0], ovv[1]);
                 } else {
@@ -460,6 +480,9 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
   h.Cin = p.Cin;
   h.gn_stats = nullptr;
   // 256-bit epilogue accesses need 32-byte aligned rows
+#ifdef LTB_HALO_DIAG
+  if (const char* e = std::getenv("LTB_HALO_DIAG")) h.dbg = std::atoi(e);
+#endif
   h.wide_io = ((p.OCtot % 16) == 0 && (p.oc_off % 16) == 0 && (reinterpret_cast<uintptr_t>(p.out) % 32) == 0 &&
                (!p.res || ((p.RCtot % 16) == 0 && (p.rc_off % 16) == 0 && (reinterpret_cast<uintptr_t>(p.res) % 32) == 0)))
                   ? 1

@@ -30,6 +30,10 @@ struct alignas(64) HaloParams {
   float* gn_stats;
   int gn_groups, gn_cpg, gn_hw;
   int wide_io;  // 1: 32-byte aligned rows -> 256-bit residual loads / output stores
+#ifdef LTB_HALO_DIAG
+  int dbg;      // diagnostic build only (tools/diag_halo.py): bit0 no epilogue global I/O, bit1 no epilogue at all,
+                // bit2 no MMAs, bit3 no A loads, bit4 no B loads.  Never compiled into libltb200.so.
+#endif
 };
 
 struct HaloPlan {

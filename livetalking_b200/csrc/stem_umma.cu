@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(192, 1) stem_umma_kernel(const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // warp-uniform MMA issue (see umma_f16_lohi_if)
+      const uint32_t leader = elect_one() ? 1u : 0u;
       constexpr uint32_t idesc = umma_idesc_f16(128, 16);
       // A: SWIZZLE_NONE, LBO = 16 B (next K chunk = next pixel), SBO = 256 B (next image row of the halo)
       constexpr uint32_t a_hi = (256u >> 4) | (1u << 14);
@@ -93,11 +94,11 @@ __global__ void __launch_bounds__(192, 1) stem_umma_kernel(const __grid_constant
           for (int k = 0; k < 4; ++k) {
             const uint32_t a_lo = (((a_base + kh * 256 + k * 32) & 0x3FFFFu) >> 4) | (1u << 16);   // LBO = 16 B
             const uint32_t b_lo = (((w_smem + kh * 2048 + k * 32) & 0x3FFFFu) >> 4) | (1u << 16);
-            umma_f16_lohi(tmem + buf * 16, a_lo, a_hi, b_lo, b_hi, idesc, (kh | k) ? 1u : 0u);
+            umma_f16_lohi_if(leader, tmem + buf * 16, a_lo, a_hi, b_lo, b_hi, idesc, (kh | k) ? 1u : 0u);
           }
         }
-        umma_commit(smem_u32(&a_empty[as]));
-        umma_commit(smem_u32(&acc_full[buf]));
+        umma_commit_if(leader, smem_u32(&a_empty[as]));
+        umma_commit_if(leader, smem_u32(&acc_full[buf]));
       }
     }
     __syncwarp();

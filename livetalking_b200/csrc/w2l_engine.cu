@@ -199,7 +199,8 @@ struct Tensor {
   int H = 0, W = 0, C = 0;  // C = pixel pitch (total channels)
 };
 struct Op {
-  int type;  // 0 = conv (gather kernel), 1 = prep, 2 = audio conv0, 3 = head, 4 = conv (halo kernel), 5 = stem (tensor-core)
+  int type;  // 0 = conv (gather kernel), 1 = prep, 2 = audio conv0, 3 = head, 4 = conv (halo kernel), 5 = stem (tensor-core),
+             // 6 = mel of the resident PCM chunk (skipped when the host supplies mel windows)
   ConvParams cp;
   int halo = -1;    // index into the session's halo plans (type 4)
   int branch = 0;   // 1 = audio-encoder branch: runs on the side stream, concurrently with the face encoder
@@ -241,6 +242,8 @@ struct ltb_w2l_session {
   LayerOut louts[kNumLayers];
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
+  cudaGraph_t graph_mel = nullptr;       // same forward with the mel kernels heading the audio branch
+  cudaGraphExec_t gexec_mel = nullptr;
   long long launches = 0;
   int graph_nodes = 0;
 };
@@ -451,11 +454,12 @@ static int build_plan(ltb_w2l_session* s) {
     return 0;
   };
 
-  // ---- prep (faces -> padded 8-channel fp16 image) and audio conv0
+  // ---- audio branch first (so the fork precedes the face path): mel of the resident PCM chunk, then audio conv0
   {
     Op o;
     std::memset(&o.cp, 0, sizeof(o.cp));
-    o.type = 1;
+    o.type = 6;
+    o.branch = 1;
     s->ops.push_back(o);
   }
   View a_prev;
@@ -485,6 +489,13 @@ static int build_plan(ltb_w2l_session* s) {
     }
   }
   const View audio_emb = a_prev;  // [B,1,1,512]
+  // ---- prep (faces -> padded 8-channel fp16 image)
+  {
+    Op o;
+    std::memset(&o.cp, 0, sizeof(o.cp));
+    o.type = 1;
+    s->ops.push_back(o);
+  }
 
   // ---- face encoder
   // stem (layer 13): 7 row-taps, each K block = 8 consecutive pixels x 8 channels of the padded image
@@ -587,13 +598,14 @@ static const char* op_name(const Op& o) {
     case 3: return "head";
     case 4: return "conv_halo";
     case 5: return "stem_umma";
+    case 6: return "mel";
   }
   return "?";
 }
 
 // enqueue the forward plan on the session stream (reads the step's first avatar index from *d_index).
 // events (optional): ops.size()+1 events recorded around every op (profiling pass only).
-static int run_ops(ltb_w2l_session* s, cudaEvent_t* events = nullptr) {
+static int run_ops(ltb_w2l_session* s, bool with_mel, cudaEvent_t* events = nullptr) {
   size_t i = 0;
   const bool branches = (events == nullptr);  // the profiling pass serialises everything on the main stream
   bool forked = false;
@@ -621,6 +633,9 @@ static int run_ops(ltb_w2l_session* s, cudaEvent_t* events = nullptr) {
       case 3: e = launch_w2l_head(o.cp.in, s->m->head_w, s->m->head_b, s->pred, s->B * 65536, st); break;
       case 4: e = launch_conv_halo(s->halo_plans[o.halo], st); break;
       case 5: e = launch_stem(s->stem, st); break;
+      case 6:
+        if (with_mel) e = launch_mel_step(s->pcm, s->pcm_cap, s->B, s->l, s->fps, s->mel_spec, s->mel_mel, s->mel, st);
+        break;
     }
     if (e != cudaSuccess) return LTB_FAIL(std::string("kernel launch failed (") + op_name(o) + "): " + cudaGetErrorString(e));
     ++i;
@@ -782,6 +797,8 @@ int ltb_w2l_session_destroy(ltb_w2l_session* s) {
   if (s->st) cudaStreamSynchronize(s->st);
   if (s->gexec) cudaGraphExecDestroy(s->gexec);
   if (s->graph) cudaGraphDestroy(s->graph);
+  if (s->gexec_mel) cudaGraphExecDestroy(s->gexec_mel);
+  if (s->graph_mel) cudaGraphDestroy(s->graph_mel);
   for (void* p : s->allocs) cudaFree(p);
   if (s->st_copy) cudaStreamSynchronize(s->st_copy);
   for (int i = 0; i < 2; ++i) {
@@ -846,22 +863,26 @@ int ltb_w2l_session_create(ltb_w2l_model* m, ltb_w2l_avatar* a, int batch, int s
   if (build_plan(s)) return bail(1);
   // warm-up (also the reference's warm_up, wav2lip_avatar.py:90-96): one eager pass
   if (launch_set_int(s->d_index, 0, s->st) != cudaSuccess) return bail(LTB_FAIL("set_int launch failed"));
-  if (run_ops(s)) return bail(1);
+  if (run_ops(s, true)) return bail(1);
   cudaError_t e = cudaStreamSynchronize(s->st);
   if (e != cudaSuccess) return bail(LTB_FAIL(std::string("warm-up forward failed: ") + cudaGetErrorString(e)));
   if (!(flags & (LTB_SESSION_NO_GRAPH | LTB_SESSION_KEEP_LAYERS))) {
-    // capture the whole forward (57 launches) into one CUDA graph; the per-step index lives in device memory
-    e = cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal);
-    if (e != cudaSuccess) return bail(LTB_FAIL(std::string("graph capture begin: ") + cudaGetErrorString(e)));
-    const int rc = run_ops(s);
-    e = cudaStreamEndCapture(s->st, &s->graph);
-    if (rc) return bail(1);
-    if (e != cudaSuccess) return bail(LTB_FAIL(std::string("graph capture end: ") + cudaGetErrorString(e)));
-    e = cudaGraphInstantiate(&s->gexec, s->graph, 0);
-    if (e != cudaSuccess) return bail(LTB_FAIL(std::string("graph instantiate: ") + cudaGetErrorString(e)));
-    e = cudaGraphLaunch(s->gexec, s->st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
-    if (e != cudaSuccess) return bail(LTB_FAIL(std::string("graph warm-up: ") + cudaGetErrorString(e)));
+    // capture the whole forward into CUDA graphs (with and without the mel kernels); the per-step index lives in device memory
+    for (int with_mel = 0; with_mel < 2; ++with_mel) {
+      cudaGraph_t* g = with_mel ? &s->graph_mel : &s->graph;
+      cudaGraphExec_t* ge = with_mel ? &s->gexec_mel : &s->gexec;
+      e = cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal);
+      if (e != cudaSuccess) return bail(LTB_FAIL(std::string("graph capture begin: ") + cudaGetErrorString(e)));
+      const int rc = run_ops(s, with_mel != 0);
+      e = cudaStreamEndCapture(s->st, g);
+      if (rc) return bail(1);
+      if (e != cudaSuccess) return bail(LTB_FAIL(std::string("graph capture end: ") + cudaGetErrorString(e)));
+      e = cudaGraphInstantiate(ge, *g, 0);
+      if (e != cudaSuccess) return bail(LTB_FAIL(std::string("graph instantiate: ") + cudaGetErrorString(e)));
+      e = cudaGraphLaunch(*ge, s->st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+      if (e != cudaSuccess) return bail(LTB_FAIL(std::string("graph warm-up: ") + cudaGetErrorString(e)));
+    }
   }
   *out = s;
   return 0;
@@ -882,22 +903,22 @@ int ltb_w2l_mel_step(ltb_w2l_session* s, const float* pcm, int nsamples, float* 
   return 0;
 }
 
-static int forward_enqueue(ltb_w2l_session* s, int index) {
+static int forward_enqueue(ltb_w2l_session* s, int index, bool with_mel) {
   if (index < 0) return LTB_FAIL("negative index");
   if (launch_set_int(s->d_index, index, s->st) != cudaSuccess) return LTB_FAIL("set_int launch failed");
   if (s->gexec) {
-    LTB_CUDA(cudaGraphLaunch(s->gexec, s->st));
+    LTB_CUDA(cudaGraphLaunch(with_mel ? s->gexec_mel : s->gexec, s->st));
   } else {
-    if (run_ops(s)) return 1;
+    if (run_ops(s, with_mel)) return 1;
   }
-  s->launches += 1 + (long long)s->ops.size();
+  s->launches += (long long)s->ops.size() + (with_mel ? 3 : 0);   // set_int + every op but the mel slot (+ 3 mel kernels)
   return 0;
 }
 
 int ltb_w2l_infer(ltb_w2l_session* s, int index, const float* mel, float* pred_out) {
   if (!s) return LTB_FAIL("null session");
   if (mel) LTB_CUDA(cudaMemcpyAsync(s->mel, mel, (size_t)s->B * 1280 * 4, cudaMemcpyHostToDevice, s->st));
-  if (forward_enqueue(s, index)) return 1;
+  if (forward_enqueue(s, index, false)) return 1;
   if (pred_out) LTB_CUDA(cudaMemcpyAsync(pred_out, s->pred, (size_t)s->B * 65536 * 3 * 4, cudaMemcpyDeviceToHost, s->st));
   LTB_CUDA(cudaStreamSynchronize(s->st));
   return 0;
@@ -960,8 +981,7 @@ int ltb_w2l_mel_resident(ltb_w2l_session* s) {
 
 int ltb_w2l_step_async(ltb_w2l_session* s, int index) {
   if (!s) return LTB_FAIL("null session");
-  if (ltb_w2l_mel_resident(s)) return 1;
-  if (forward_enqueue(s, index)) return 1;
+  if (forward_enqueue(s, index, true)) return 1;
   return paste_batch_enqueue(s, index);
 }
 
@@ -974,7 +994,7 @@ int ltb_w2l_profile_ops(ltb_w2l_session* s, int index, int max_ops, int* n_ops, 
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) LTB_CUDA(cudaEventCreate(&e));
   if (launch_set_int(s->d_index, index, s->st) != cudaSuccess) return LTB_FAIL("set_int launch failed");
-  int rc = run_ops(s, ev.data());
+  int rc = run_ops(s, true, ev.data());
   if (!rc && cudaStreamSynchronize(s->st) != cudaSuccess) rc = LTB_FAIL("profile pass failed");
   for (int i = 0; i < n && !rc; ++i) {
     cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
@@ -1018,8 +1038,7 @@ int ltb_w2l_step_e2e_async(ltb_w2l_session* s, int index, const float* pcm_host,
   // the paste kernel of this step must not overwrite the buffer while the copy of step-2 is still draining it
   if (s->copied_valid[slot]) LTB_CUDA(cudaStreamWaitEvent(s->st, s->ev_copied[slot], 0));
   LTB_CUDA(cudaMemcpyAsync(s->pcm, pcm_host, (size_t)nsamples * 4, cudaMemcpyHostToDevice, s->st));
-  if (ltb_w2l_mel_resident(s)) return 1;
-  if (forward_enqueue(s, index)) return 1;
+  if (forward_enqueue(s, index, true)) return 1;
   if (paste_batch_enqueue(s, index, dev_frames)) return 1;
   LTB_CUDA(cudaEventRecord(s->ev_paste[slot], s->st));
   LTB_CUDA(cudaStreamWaitEvent(s->st_copy, s->ev_paste[slot], 0));
