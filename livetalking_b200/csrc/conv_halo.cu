@@ -15,6 +15,7 @@
 // accumulators: the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "conv_halo.h"
@@ -34,7 +35,10 @@ constexpr int kHaloP = 10;  // halo row pitch in pixels (8 + 2)
 
 // TAPS = 9: 3x3 conv / sub-pixel ConvT over a (16*NSUB+2) x 10 pixel halo.
 // TAPS = 1: plain GEMM (1x1 conv / nn.Linear): the "halo" is the 128*NSUB-row tile itself (pitch 8 -> SBO 1024 B).
-template <int BN, int NSUB, int NACC, int TAPS>
+// RC > 0: "weights resident" variant for layers whose whole tap-major weight set (RC K-chunks x 9 taps x BN rows) fits
+// next to the halo ring — the CTA loads it once instead of once per tile (for the 64-channel 256x256 layers the
+// re-streamed weights were 60 % of all L2->SM traffic).  Requires Cout == BN (every tile uses the same weights).
+template <int BN, int NSUB, int NACC, int TAPS, int RC = 0>
 struct HaloCfg {
   static constexpr int P = (TAPS == 9) ? kHaloP : 8;                        // halo row pitch (pixels)
   static constexpr int HR = (TAPS == 9) ? 16 * NSUB + 2 : 16 * NSUB;        // halo rows
@@ -44,27 +48,34 @@ struct HaloCfg {
   static constexpr int B_BYTES = TG * BN * 128;                             // TG taps x BN rows x 64 k
   // stage counts: fill the 227 KB of shared memory
   static constexpr int BUDGET = 226 * 1024;
-  static constexpr int A_STAGES = (BN <= 32) ? 4 : (BN <= 64 ? 3 : (NSUB == 1 ? 3 : 2));
+  static constexpr int A_STAGES_STREAM = (BN <= 32) ? 4 : (BN <= 64 ? 3 : (NSUB == 1 ? 3 : 2));
+  static constexpr int A_STAGES_RES = ((BUDGET - RC * TG * B_BYTES) / A_BYTES) > 4 ? 4 : ((BUDGET - RC * TG * B_BYTES) / A_BYTES);
+  static constexpr int A_STAGES = RC ? A_STAGES_RES : A_STAGES_STREAM;
   static constexpr int B_STAGES_MAX = (BUDGET - A_STAGES * A_BYTES) / B_BYTES;
-  static constexpr int B_STAGES = B_STAGES_MAX > 6 ? 6 : B_STAGES_MAX;
+  static constexpr int B_STAGES = RC ? RC * TG : (B_STAGES_MAX > 6 ? 6 : B_STAGES_MAX);
   static constexpr int ACC_COLS = NACC * NSUB * BN;                         // fp32 columns per accumulator buffer
   static constexpr int TCOLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
                                : (2 * ACC_COLS <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_STAGES * B_BYTES + 1024;
   static_assert(2 * ACC_COLS <= 512, "TMEM overflow");
   static_assert(B_STAGES >= 2, "not enough shared memory for the weight ring");
+  static_assert(A_STAGES >= 2, "not enough shared memory for the halo ring");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory overflow");
 };
 
-template <int BN, int NSUB, int NACC, int TAPS>
+template <int BN, int NSUB, int NACC, int TAPS, int RC>
 __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_constant__ HaloParams p) {
-  using C = HaloCfg<BN, NSUB, NACC, TAPS>;
+  using C = HaloCfg<BN, NSUB, NACC, TAPS, RC>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[C::A_STAGES], a_empty[C::A_STAGES];
   __shared__ __align__(8) uint64_t b_full[C::B_STAGES], b_empty[C::B_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ float head_sw[100];   // fused head: 3 x 32 weights + 3 biases
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr bool kHeadOk = (BN == 32 && NACC == 1 && TAPS == 9);
+  if (kHeadOk && p.head_out && tid >= 64 && tid < 64 + 99) head_sw[tid - 64] = (tid - 64 < 96) ? p.head_w[tid - 64] : p.head_b[tid - 64 - 96];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = smem0;
   const uint32_t b_smem = smem0 + C::A_STAGES * C::A_BYTES;
@@ -102,6 +113,13 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
     // =============================================================== TMA producer
     if (lane == 0) {
       uint32_t ai = 0, bi = 0;  // running stage counters
+      if (RC) {
+        // resident weights: every (chunk, tap-group) box once, all on b_full[0]
+        mbar_arrive_expect_tx(smem_u32(&b_full[0]), RC * C::TG * C::B_BYTES);
+        for (int c = 0; c < RC; ++c)
+          for (int j = 0; j < C::TG; ++j)
+            tma_load_3d(b_smem + (c * C::TG + j) * C::B_BYTES, &p.tm_w, smem_u32(&b_full[0]), c * 64, 0, j * 3);
+      }
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const int nt = t / tiles_m;
         int mt = t - nt * tiles_m;
@@ -119,11 +137,12 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
           if (LTB_DIAG(8)) {
             mbar_arrive(smem_u32(&a_full[as]));
           } else {
-          mbar_arrive_expect_tx(smem_u32(&a_full[as]), C::A_BYTES_RAW);
-          if (TAPS == 9) tma_load_4d(a_smem + as * C::A_BYTES, &p.tm_in, smem_u32(&a_full[as]), c * 64, x0, y0, img);
-          else tma_load_2d(a_smem + as * C::A_BYTES, &p.tm_in, smem_u32(&a_full[as]), c * 64, mt * (128 * NSUB));
+            mbar_arrive_expect_tx(smem_u32(&a_full[as]), C::A_BYTES_RAW);
+            if (TAPS == 9) tma_load_4d(a_smem + as * C::A_BYTES, &p.tm_in, smem_u32(&a_full[as]), c * 64, x0, y0, img);
+            else tma_load_2d(a_smem + as * C::A_BYTES, &p.tm_in, smem_u32(&a_full[as]), c * 64, mt * (128 * NSUB));
           }
           ++ai;
+          if (RC) continue;
           for (int j = 0; j < C::TG; ++j) {
             const uint32_t bs = bi % C::B_STAGES;
             mbar_wait(smem_u32(&b_empty[bs]), ((bi / C::B_STAGES) & 1u) ^ 1u);
@@ -149,40 +168,56 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
       constexpr uint32_t kADescHi = ((C::P * 128) >> 4) | (1u << 14) | (2u << 29);    // SBO = halo pitch (1280 B) / 1024 B in GEMM mode
       constexpr uint32_t kBDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);            // SBO = 1024 B
       uint32_t ai = 0, bi = 0, it = 0;
+      // per-tap constants in registers (all loops over taps below are fully unrolled): halo row offset in 16-byte units,
+      // accumulator column offset, and "accumulate" flag of the tap's first K step in the first chunk
+      constexpr int NT = C::TG * C::TG;
+      uint32_t tap_aoff[NT], tap_doff[NT], tap_acc0[NT];
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        tap_aoff[i] = (uint32_t)p.tap_row[i] * 8u;
+        tap_doff[i] = (uint32_t)p.tap_acc[i] * (NSUB * BN);
+        tap_acc0[i] = p.tap_first[i] ? 0u : 1u;
+      }
+      if (RC) mbar_wait(smem_u32(&b_full[0]), 0);
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
         const uint32_t buf = it & 1u;
         mbar_wait(smem_u32(&acc_empty[buf]), ((it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t dbase = tmem + buf * C::ACC_COLS;
+#pragma unroll 1
         for (int c = 0; c < chunks; ++c) {
           const uint32_t as = ai % C::A_STAGES;
           mbar_wait(smem_u32(&a_full[as]), (ai / C::A_STAGES) & 1u);
-          const uint32_t a_base = a_smem + as * C::A_BYTES;
+          const uint32_t a_lo0 = (((a_smem + as * C::A_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+          const int ksteps = (c == chunks - 1) ? p.last_ksteps : 4;   // skip the all-zero K steps of a ragged last chunk
+          const uint32_t later = (c != 0) ? 1u : 0u;
+#pragma unroll
           for (int j = 0; j < C::TG; ++j) {
-            const uint32_t bs = bi % C::B_STAGES;
-            mbar_wait(smem_u32(&b_full[bs]), (bi / C::B_STAGES) & 1u);
+            const uint32_t bs = RC ? (uint32_t)(c * C::TG + j) : bi % C::B_STAGES;
+            if (!RC) mbar_wait(smem_u32(&b_full[bs]), (bi / C::B_STAGES) & 1u);
             tc_fence_after();
-            const uint32_t b_base = b_smem + bs * C::B_BYTES;
             // descriptor words: hi = {SBO, version 1, SWIZZLE_128B} is loop invariant; lo = (addr >> 4) | LBO(1) << 16
-            const uint32_t b_lo0 = ((b_base & 0x3FFFFu) >> 4) | (1u << 16);
-            const uint32_t a_lo0 = ((a_base & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t b_lo0 = (((b_smem + bs * C::B_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
 #pragma unroll
             for (int tt = 0; tt < C::TG; ++tt) {
               const int tap = j * C::TG + tt;
-              const uint32_t a_lo_tap = a_lo0 + (uint32_t)p.tap_row[tap] * 8u;   // 128 B rows -> 8 x 16 B
-              const uint32_t d_tap = dbase + (uint32_t)p.tap_acc[tap] * (NSUB * BN);
-              const uint32_t fresh = (c == 0 && p.tap_first[tap]) ? 1u : 0u;
+              const uint32_t acc0 = later | tap_acc0[tap];
 #pragma unroll
               for (int sub = 0; sub < NSUB; ++sub) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  if (LTB_DIAG(4)) continue;
-                  umma_f16_lohi_if(leader, d_tap + sub * BN, a_lo_tap + sub * (16 * C::P * 8) + k * 2, kADescHi,
-                                b_lo0 + tt * (BN * 8) + k * 2, kBDescHi, idesc, (fresh && k == 0) ? 0u : 1u);
+                const uint32_t d = dbase + tap_doff[tap] + sub * BN;
+                const uint32_t a_lo = a_lo0 + tap_aoff[tap] + sub * (16 * C::P * 8);
+                const uint32_t b_lo = b_lo0 + tt * (BN * 8);
+                if (LTB_DIAG(4)) continue;
+                if (ksteps == 4) {   // warp-uniform; straight-line issue of the four K steps
+                  umma_f16_lohi_x4_if(leader, d, a_lo, kADescHi, b_lo, kBDescHi, idesc, acc0);
+                } else {             // ragged last chunk: only the K steps that carry channels
+#pragma unroll 1
+                  for (int k = 0; k < ksteps; ++k)
+                    umma_f16_lohi_if(leader, d, a_lo + k * 2, kADescHi, b_lo + k * 2, kBDescHi, idesc, k ? 1u : acc0);
                 }
               }
             }
-            umma_commit_if(leader, smem_u32(&b_empty[bs]));
+            if (!RC) umma_commit_if(leader, smem_u32(&b_empty[bs]));
             ++bi;
           }
           umma_commit_if(leader, smem_u32(&a_empty[as]));
@@ -241,6 +276,13 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
             float gs[8], gq[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) gs[i] = gq[i] = 0.f;
+            const bool head = kHeadOk && p.head_out != nullptr;
+            float ha0 = 0.f, ha1 = 0.f, ha2 = 0.f;
+            if (head) {
+              ha0 = head_sw[96];
+              ha1 = head_sw[97];
+              ha2 = head_sw[98];
+            }
 #pragma unroll
             for (int g16 = 0; g16 < 32; g16 += 16) {
               // packed-half epilogue: fp32 accumulator + fp32 bias -> half2, then residual add / ReLU / saturation as half2 ops.
@@ -273,6 +315,19 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
                 const __half2 lo = p.relu ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(-65504.f, -65504.f);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) oh[u] = __hmin2(__hmax2(oh[u], lo), hmax);
+                if (kHeadOk && head) {
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const float2 f = __half22float2(oh[u]);
+                    const int c = g + 2 * u;
+                    ha0 = fmaf(f.x, head_sw[c], ha0);
+                    ha0 = fmaf(f.y, head_sw[c + 1], ha0);
+                    ha1 = fmaf(f.x, head_sw[32 + c], ha1);
+                    ha1 = fmaf(f.y, head_sw[32 + c + 1], ha1);
+                    ha2 = fmaf(f.x, head_sw[64 + c], ha2);
+                    ha2 = fmaf(f.y, head_sw[64 + c + 1], ha2);
+                  }
+                }
                 if (p.gn_stats && row_ok) {
                   float ps[4], pq[4];
 #pragma unroll
@@ -301,7 +356,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
                   }
                 }
               }
-              if (row_ok && !LTB_DIAG(1)) {
+              if (row_ok && !head && !LTB_DIAG(1)) {
                 if (p.wide_io) {
                   stg256(optr + c0 + g16, ovv[0], ovv[1]);
                 } else {
@@ -309,6 +364,12 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
                   *reinterpret_cast<uint4*>(optr + c0 + g16 + 8) = ovv[1];
                 }
               }
+            }
+            if (kHeadOk && head) {
+              float* o = p.head_out + opix * 3;
+              o[0] = (1.f / (1.f + expf(-ha0))) * 255.f;
+              o[1] = (1.f / (1.f + expf(-ha1))) * 255.f;
+              o[2] = (1.f / (1.f + expf(-ha2))) * 255.f;
             }
             if (p.gn_stats) {
               const int ng = p.gn_cpg >= 32 ? 1 : 32 / p.gn_cpg;
@@ -478,6 +539,7 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
   h.N = p.N;
   h.M = p.M;
   h.Cin = p.Cin;
+  h.last_ksteps = ((p.Cin - 1) % 64) / 16 + 1;
   h.gn_stats = nullptr;
   // 256-bit epilogue accesses need 32-byte aligned rows
 #ifdef LTB_HALO_DIAG
@@ -524,23 +586,25 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
   return 0;
 }
 
-template <int BN, int NSUB, int NACC, int TAPS = 9>
+template <int BN, int NSUB, int NACC, int TAPS = 9, int RC = 0>
 static cudaError_t launch_cfg(const HaloPlan& pl, int sms, cudaStream_t st) {
-  using C = HaloCfg<BN, NSUB, NACC, TAPS>;
+  using C = HaloCfg<BN, NSUB, NACC, TAPS, RC>;
   static SmemConfigOnce once;
-  if (cudaError_t e = once.ensure(conv_halo_umma_kernel<BN, NSUB, NACC, TAPS>, C::SMEM_BYTES); e != cudaSuccess) return e;
+  if (cudaError_t e = once.ensure(conv_halo_umma_kernel<BN, NSUB, NACC, TAPS, RC>, C::SMEM_BYTES); e != cudaSuccess) return e;
   const int grid = pl.hp.total_tiles < sms ? pl.hp.total_tiles : sms;
-  conv_halo_umma_kernel<BN, NSUB, NACC, TAPS><<<grid, 320, C::SMEM_BYTES, st>>>(pl.hp);
+  conv_halo_umma_kernel<BN, NSUB, NACC, TAPS, RC><<<grid, 320, C::SMEM_BYTES, st>>>(pl.hp);
   return cudaGetLastError();
 }
 
 cudaError_t launch_conv_halo(const HaloPlan& pl, cudaStream_t st) {
-  static int sms = 0;
+  static std::atomic<int> sms_cached{0};
+  int sms = sms_cached.load();
   if (!sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
+    sms_cached.store(sms);
   }
   const int key = pl.BN * 100 + pl.NSUB * 10 + pl.NACC;
   if (pl.TAPS == 1) {
@@ -553,6 +617,16 @@ cudaError_t launch_conv_halo(const HaloPlan& pl, cudaStream_t st) {
       case 3211: return launch_cfg<32, 1, 1, 1>(pl, sms, st);
     }
     return cudaErrorInvalidValue;
+  }
+  // weights-resident variants (single N tile, whole weight set in shared memory)
+  if (pl.hp.tiles_n == 1 && pl.hp.total_tiles >= 2 * sms) {
+    const int chunks = (pl.hp.Cin + 63) / 64;
+    if (key == 6421 && chunks == 1) return launch_cfg<64, 2, 1, 9, 1>(pl, sms, st);
+    if (key == 3221 && chunks == 1) return launch_cfg<32, 2, 1, 9, 1>(pl, sms, st);
+    if (key == 3221 && chunks == 2) return launch_cfg<32, 2, 1, 9, 2>(pl, sms, st);
+    if (key == 6414 && chunks == 2) return launch_cfg<64, 1, 4, 9, 2>(pl, sms, st);
+    if (key == 6414 && chunks == 1) return launch_cfg<64, 1, 4, 9, 1>(pl, sms, st);
+    if (key == 3214 && chunks <= 2) return chunks == 1 ? launch_cfg<32, 1, 4, 9, 1>(pl, sms, st) : launch_cfg<32, 1, 4, 9, 2>(pl, sms, st);
   }
   switch (key) {
     case 12821: return launch_cfg<128, 2, 1>(pl, sms, st);

@@ -16,6 +16,7 @@ struct alignas(64) HaloParams {
   const __half* res;
   const float* bias;
   int N, M, Cin;  // M: GEMM-mode row count
+  int last_ksteps;  // 16-wide K steps that carry data in the last 64-channel chunk (1..4)
   int OCtot, oc_off, RCtot, rc_off;
   int OH, OW, osy, osx;
   int relu;
@@ -30,6 +31,12 @@ struct alignas(64) HaloParams {
   float* gn_stats;
   int gn_groups, gn_cpg, gn_hw;
   int wide_io;  // 1: 32-byte aligned rows -> 256-bit residual loads / output stores
+  // optional fused output head (BN == Cout == 32 only): pred[pix][j] = sigmoid(sum_c head_w[j][c] * y[pix][c] + head_b[j]) * 255
+  // computed from the fp16-rounded activations in the order of w2l_head_kernel (bit-identical); the activations
+  // themselves are then not stored.  wav2lip256 output_block: avatars/wav2lip/models/wav2lip_v2.py:95-97.
+  const float* head_w;
+  const float* head_b;
+  float* head_out;
 #ifdef LTB_HALO_DIAG
   int dbg;      // diagnostic build only (tools/diag_halo.py): bit0 no epilogue global I/O, bit1 no epilogue at all,
                 // bit2 no MMAs, bit3 no A loads, bit4 no B loads.  Never compiled into libltb200.so.

@@ -149,6 +149,36 @@ __device__ __forceinline__ void umma_f16_lohi_if(uint32_t leader, uint32_t tmem_
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
+// Four consecutive K steps (16 elements = 32 bytes each: +2 in the descriptors' 16-byte address field) in one statement:
+// one predicate/idesc set-up for the four MMAs of a 64-channel K chunk.
+__device__ __forceinline__ void umma_f16_lohi_x4_if(uint32_t leader, uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                    uint32_t b_hi, uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, q, t;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "add.u32 al, %1, 2;\n\t"
+      "add.u32 bl, %3, 2;\n\t"
+      "mov.b64 da, {al, %2};\n\t"
+      "mov.b64 db, {bl, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
+      "add.u32 al, %1, 4;\n\t"
+      "add.u32 bl, %3, 4;\n\t"
+      "mov.b64 da, {al, %2};\n\t"
+      "mov.b64 db, {bl, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
+      "add.u32 al, %1, 6;\n\t"
+      "add.u32 bl, %3, 6;\n\t"
+      "mov.b64 da, {al, %2};\n\t"
+      "mov.b64 db, {bl, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate_first), "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ void umma_f16_if(uint32_t leader, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(

@@ -580,7 +580,13 @@ static int build_plan(ltb_w2l_session* s) {
   View h;
   if (new_tmp(256, 256, 32, &h)) return 1;
   if (add_conv(53, cat_all(7), h, nullptr)) return 1;
-  {
+  if (!keep && s->ops.back().type == 4 && s->halo_plans[s->ops.back().halo].BN == 32) {
+    // fuse the 1x1 head + sigmoid into the epilogue of layer 53 (its 32-channel activations are never stored)
+    HaloParams& hp = s->halo_plans[s->ops.back().halo].hp;
+    hp.head_w = m->head_w;
+    hp.head_b = m->head_b;
+    hp.head_out = s->pred;
+  } else {
     Op o;
     std::memset(&o.cp, 0, sizeof(o.cp));
     o.type = 3;
