@@ -33,6 +33,9 @@ def main():
         ("L46 256->256 res @64", 16, 64, 256, 256, True),
     ]
     variants = [0, 1, 2, 4, 8, 16, 24, 4 | 2, 8 | 16 | 2, 4 | 8 | 16, 4 | 8 | 16 | 2]
+    if os.environ.get("LTB_DIAG_ONLY"):          # e.g. "0:0" = first case, variant 0 (for an ncu capture)
+        ci, v = os.environ["LTB_DIAG_ONLY"].split(":")
+        cases, variants = [cases[int(ci)]], [int(v)]
     for name, N, H, cin, cout, res in cases:
         x = ctx.upload((rng.standard_normal((N * H * H, cin)) * 0.5).astype(np.float16))
         w = ops.ConvWeight(ctx, (rng.standard_normal((cout, cin, 3, 3)) * 0.05).astype(np.float32), np.zeros(cout, np.float32))
