@@ -51,6 +51,7 @@ int ltb_w2l_avatar_destroy(ltb_w2l_avatar* a);
 #define LTB_SESSION_KEEP_LAYERS 1 /* keep every layer's activations (debug / per-layer parity tests) */
 #define LTB_SESSION_NO_GRAPH 2    /* launch kernels eagerly instead of replaying a CUDA graph */
 #define LTB_SESSION_NO_HALO 4     /* route every conv to the generic gather kernel (A/B testing of the TMA halo kernel) */
+#define LTB_SESSION_NO_PDL 8      /* launch the conv kernels without programmatic dependent launch (A/B testing) */
 /* replaces LipReal.__init__ (avatars/wav2lip_avatar.py:101-114) + warm_up (:90-96): allocates the activation
  * arena for `batch` frames, builds the layer plan and (unless NO_GRAPH) captures it into a CUDA graph.
  * stride_left/right = opt.l / opt.r (20 ms chunks), fps = opt.fps. */

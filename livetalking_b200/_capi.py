@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libltb200.so")
 LTB_SESSION_KEEP_LAYERS = 1
 LTB_SESSION_NO_GRAPH = 2
 LTB_SESSION_NO_HALO = 4
+LTB_SESSION_NO_PDL = 8
 
 
 class LtbError(RuntimeError):

@@ -92,6 +92,9 @@ __global__ void __launch_bounds__(160) conv_gather_umma_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
+  // PDL: the prologue above overlaps the predecessor's tail; everything below touches activations
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp < 4) {
     // ------------------------------------------------------------------ producers
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(160) conv_gather_umma_kernel(const __grid_cons
           f[6] = __uint_as_float(v[g + 6]) + b1.z;
           f[7] = __uint_as_float(v[g + 7]) + b1.w;
           if (rptr) {
-            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rptr + c0 + g));
+            const uint4 rv = __ldcg(reinterpret_cast<const uint4*>(rptr + c0 + g));
             const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -268,8 +271,7 @@ static cudaError_t launch_one(const ConvParams& p, cudaStream_t st) {
   static SmemConfigOnce once;
   if (cudaError_t e = once.ensure(conv_gather_umma_kernel<BN, KB>, C::SMEM_BYTES); e != cudaSuccess) return e;
   dim3 grid((p.M + 127) / 128, p.Cout / BN, p.ksplit > 1 ? p.ksplit : p.nphases * (p.zbatch > 1 ? p.zbatch : 1));
-  conv_gather_umma_kernel<BN, KB><<<grid, 160, C::SMEM_BYTES, st>>>(p);
-  return cudaGetLastError();
+  return launch_kernel_pdl(conv_gather_umma_kernel<BN, KB>, grid, dim3(160), C::SMEM_BYTES, st, p);
 }
 
 template <int KB>
@@ -305,6 +307,8 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __res
   const unsigned vpr = Cout / 8;
   const unsigned total = (unsigned)M * vpr;
   const size_t slice = (size_t)M * Cout;
+  pdl_launch_dependents();
+  pdl_wait();   // the partial sums (and the residual) come from the predecessor kernels: coherent loads below, never .nc
   for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
     const size_t m = i / vpr;
     const int c = (int)(i % vpr) * 8;
@@ -313,12 +317,12 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __res
     for (int j = 0; j < 8; ++j) f[j] = __ldg(bias + c + j);
     for (int s = 0; s < ksplit; ++s) {
       const float4* w4 = reinterpret_cast<const float4*>(ws + s * slice + m * Cout + c);
-      const float4 a = w4[0], b = w4[1];
+      const float4 a = __ldcg(w4), b = __ldcg(w4 + 1);
       f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w;
       f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
     }
     if (res) {
-      const uint4 rv = *reinterpret_cast<const uint4*>(res + m * RCtot + rc_off + c);
+      const uint4 rv = __ldcg(reinterpret_cast<const uint4*>(res + m * RCtot + rc_off + c));
       const __half* rh = reinterpret_cast<const __half*>(&rv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] += __half2float(rh[j]);
@@ -379,9 +383,8 @@ cudaError_t launch_conv_gather(const ConvParams& p_in, cudaStream_t st, float* s
   const size_t total = (size_t)p.M * (p.Cout / 8);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 592) blocks = 592;
-  splitk_finalize_kernel<<<blocks, 256, 0, st>>>(p.ws, p.ksplit, p.M, p.Cout, p.bias, p.res, p.RCtot, p.rc_off, p.relu, p.out, p.OCtot,
-                                                 p.oc_off);
-  return cudaGetLastError();
+  return launch_kernel_pdl(splitk_finalize_kernel, dim3(blocks), dim3(256), 0, st, (const float*)p.ws, p.ksplit, p.M, p.Cout, p.bias, p.res,
+                           p.RCtot, p.rc_off, p.relu, p.out, p.OCtot, p.oc_off);
 }
 
 }  // namespace ltb

@@ -109,17 +109,22 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
 
   const int tiles_m = (TAPS == 9) ? p.tiles_x * p.tiles_y * p.N : p.tiles_x;
 
+  // PDL: the next kernel of the stream may start its own prologue now; resident weights (constants) are fetched before
+  // this kernel waits for its predecessor, everything that touches activations comes after pdl_wait()
+  pdl_launch_dependents();
+  if (RC && warp == 0 && lane == 0) {
+    // resident weights: every (chunk, tap-group) box once, all on b_full[0]
+    mbar_arrive_expect_tx(smem_u32(&b_full[0]), RC * C::TG * C::B_BYTES);
+    for (int c = 0; c < RC; ++c)
+      for (int j = 0; j < C::TG; ++j)
+        tma_load_3d(b_smem + (c * C::TG + j) * C::B_BYTES, &p.tm_w, smem_u32(&b_full[0]), c * 64, 0, j * 3);
+  }
+  pdl_wait();
+
   if (warp == 0) {
     // =============================================================== TMA producer
     if (lane == 0) {
       uint32_t ai = 0, bi = 0;  // running stage counters
-      if (RC) {
-        // resident weights: every (chunk, tap-group) box once, all on b_full[0]
-        mbar_arrive_expect_tx(smem_u32(&b_full[0]), RC * C::TG * C::B_BYTES);
-        for (int c = 0; c < RC; ++c)
-          for (int j = 0; j < C::TG; ++j)
-            tma_load_3d(b_smem + (c * C::TG + j) * C::B_BYTES, &p.tm_w, smem_u32(&b_full[0]), c * 64, 0, j * 3);
-      }
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const int nt = t / tiles_m;
         int mt = t - nt * tiles_m;
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
             ldg256(rptr + 16, rnext[2], rnext[3]);
           } else {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) rnext[u] = __ldg(reinterpret_cast<const uint4*>(rptr + 8 * u));
+            for (int u = 0; u < 4; ++u) rnext[u] = __ldcg(reinterpret_cast<const uint4*>(rptr + 8 * u));
           }
         } else {
 #pragma unroll
@@ -634,8 +639,7 @@ static cudaError_t launch_cfg(const HaloPlan& pl, int sms, cudaStream_t st) {
   static SmemConfigOnce once;
   if (cudaError_t e = once.ensure(conv_halo_umma_kernel<BN, NSUB, NACC, TAPS, RC>, C::SMEM_BYTES); e != cudaSuccess) return e;
   const int grid = pl.hp.total_tiles < sms ? pl.hp.total_tiles : sms;
-  conv_halo_umma_kernel<BN, NSUB, NACC, TAPS, RC><<<grid, 320, C::SMEM_BYTES, st>>>(pl.hp);
-  return cudaGetLastError();
+  return launch_kernel_pdl(conv_halo_umma_kernel<BN, NSUB, NACC, TAPS, RC>, dim3(grid), dim3(320), C::SMEM_BYTES, st, pl.hp);
 }
 
 cudaError_t launch_conv_halo(const HaloPlan& pl, cudaStream_t st) {

@@ -5,6 +5,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <atomic>
+#include <cstdlib>
+#include <utility>
 #include <string>
 
 #include "conv_params.h"
@@ -36,6 +38,28 @@ struct SmemConfigOnce {
     return e;
   }
 };
+
+// Programmatic dependent launch of the conv kernels (they all call pdl_wait() before touching activations): overlaps a
+// kernel's prologue (barrier init, TMEM allocation, descriptor prefetch, resident-weight loads) with its predecessor's tail.
+// Thread-local switch so that a session can capture its graph with or without it (LTB_NO_PDL=1 disables it globally).
+bool pdl_default();
+bool pdl_enabled();
+void pdl_set_enabled(bool on);
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- kernel launchers ----
 // splitk_ws: optional zero-initialised fp32 workspace (one per stream) enabling split-K for small-M deep-K layers

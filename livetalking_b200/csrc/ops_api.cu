@@ -165,6 +165,7 @@ int ltb_graph_destroy(ltb_graph* g) {
 int ltb_op_conv2d(ltb_ctx* c, const ltb_conv_op* d) {
   if (!c || !d || !d->in || !d->w || !d->out) return LTB_FAIL("conv2d: null argument");
   if (d->KH * d->KW > kMaxTaps) return LTB_FAIL("conv2d: kernel too large");
+  pdl_set_enabled(pdl_default());   // the calling thread may have run a w2l profiling pass with PDL off
   if (d->Cout > kZeroBias && !d->bias) return LTB_FAIL("conv2d: Cout too large for the implicit zero bias");
   ConvParams p;
   std::memset(&p, 0, sizeof(p));

@@ -249,7 +249,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // 256-bit global accesses (sm_100+): one full 32-byte sector per thread
 __device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
-  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  // plain (coherent) load, not .nc: with programmatic dependent launch the predecessor may still be writing this tensor
+  // while the kernel is resident, so it is not "read-only for the lifetime of the kernel"
+  asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
                : "l"(p));
 }
@@ -258,6 +260,13 @@ __device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) 
                "r"(b.y), "r"(b.z), "r"(b.w)
                : "memory");
 }
+
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still running; everything that touches the predecessor's output (or overwrites
+// its input) must come after pdl_wait(), which returns once the predecessor grid has completed and flushed.  Both are
+// no-ops for a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

@@ -57,10 +57,15 @@ __global__ void __launch_bounds__(192, 1) stem_umma_kernel(const __grid_constant
   const uint32_t tmem = tmem_slot;
   const int tiles_per_img = 16 * 32;  // 256/16 x 256/8
 
+  pdl_launch_dependents();   // PDL: weights (constants) before the wait, the padded image after it
+  if (warp == 0 && lane == 0) {
+    mbar_arrive_expect_tx(smem_u32(&w_full), kStemWBytes);
+    tma_load_3d(w_smem, &p.tm_w, smem_u32(&w_full), 0, 0, 0);
+  }
+  pdl_wait();
+
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(smem_u32(&w_full), kStemWBytes);
-      tma_load_3d(w_smem, &p.tm_w, smem_u32(&w_full), 0, 0, 0);
       uint32_t ai = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ai) {
         const int img = t / tiles_per_img, r = t - img * tiles_per_img;
@@ -195,8 +200,7 @@ cudaError_t launch_stem(const StemParams& sp, cudaStream_t st) {
     sms_cached.store(sms);
   }
   const int grid = sp.total_tiles < sms ? sp.total_tiles : sms;
-  stem_umma_kernel<<<grid, 192, smem, st>>>(sp);
-  return cudaGetLastError();
+  return launch_kernel_pdl(stem_umma_kernel, dim3(grid), dim3(192), smem, st, sp);
 }
 
 }  // namespace ltb

@@ -25,6 +25,17 @@ namespace ltb {
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+
+bool pdl_default() {   // process-wide default: on unless LTB_NO_PDL is set
+  static const bool on = [] {
+    const char* e = std::getenv("LTB_NO_PDL");
+    return !(e && e[0] && e[0] != '0');
+  }();
+  return on;
+}
+static thread_local int g_pdl = -1;   // current setting of the launching thread (-1: default)
+bool pdl_enabled() { return g_pdl < 0 ? pdl_default() : g_pdl == 1; }
+void pdl_set_enabled(bool on) { g_pdl = on ? 1 : 0; }
 int fail(const char* file, int line, const std::string& msg) {
   const char* base = std::strrchr(file, '/');
   g_last_error = std::string(base ? base + 1 : file) + ":" + std::to_string(line) + ": " + msg;
@@ -246,6 +257,7 @@ struct ltb_w2l_session {
   cudaGraphExec_t gexec_mel = nullptr;
   long long launches = 0;
   int graph_nodes = 0;
+  bool pdl = true;   // conv kernels use programmatic dependent launch
 };
 
 namespace ltb {
@@ -612,6 +624,7 @@ static const char* op_name(const Op& o) {
 // enqueue the forward plan on the session stream (reads the step's first avatar index from *d_index).
 // events (optional): ops.size()+1 events recorded around every op (profiling pass only).
 static int run_ops(ltb_w2l_session* s, bool with_mel, cudaEvent_t* events = nullptr) {
+  pdl_set_enabled(s->pdl && events == nullptr);   // the per-op profiling pass times kernels in isolation
   size_t i = 0;
   const bool branches = (events == nullptr);  // the profiling pass serialises everything on the main stream
   bool forked = false;
@@ -833,6 +846,7 @@ int ltb_w2l_session_create(ltb_w2l_model* m, ltb_w2l_avatar* a, int batch, int s
   s->r = stride_right;
   s->fps = fps;
   s->flags = flags;
+  s->pdl = !(flags & LTB_SESSION_NO_PDL) && pdl_default();
   auto bail = [&](int) {
     ltb_w2l_session_destroy(s);
     return 1;
@@ -873,21 +887,41 @@ int ltb_w2l_session_create(ltb_w2l_model* m, ltb_w2l_avatar* a, int batch, int s
   cudaError_t e = cudaStreamSynchronize(s->st);
   if (e != cudaSuccess) return bail(LTB_FAIL(std::string("warm-up forward failed: ") + cudaGetErrorString(e)));
   if (!(flags & (LTB_SESSION_NO_GRAPH | LTB_SESSION_KEEP_LAYERS))) {
-    // capture the whole forward into CUDA graphs (with and without the mel kernels); the per-step index lives in device memory
-    for (int with_mel = 0; with_mel < 2; ++with_mel) {
-      cudaGraph_t* g = with_mel ? &s->graph_mel : &s->graph;
-      cudaGraphExec_t* ge = with_mel ? &s->gexec_mel : &s->gexec;
-      e = cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal);
-      if (e != cudaSuccess) return bail(LTB_FAIL(std::string("graph capture begin: ") + cudaGetErrorString(e)));
-      const int rc = run_ops(s, with_mel != 0);
-      e = cudaStreamEndCapture(s->st, g);
-      if (rc) return bail(1);
-      if (e != cudaSuccess) return bail(LTB_FAIL(std::string("graph capture end: ") + cudaGetErrorString(e)));
-      e = cudaGraphInstantiate(ge, *g, 0);
-      if (e != cudaSuccess) return bail(LTB_FAIL(std::string("graph instantiate: ") + cudaGetErrorString(e)));
-      e = cudaGraphLaunch(*ge, s->st);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
-      if (e != cudaSuccess) return bail(LTB_FAIL(std::string("graph warm-up: ") + cudaGetErrorString(e)));
+    // capture the whole forward into CUDA graphs (with and without the mel kernels); the per-step index lives in device
+    // memory.  If the driver refuses programmatic edges in a captured graph, capture again without PDL.
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      bool ok = true;
+      std::string why;
+      for (int with_mel = 0; with_mel < 2 && ok; ++with_mel) {
+        cudaGraph_t* g = with_mel ? &s->graph_mel : &s->graph;
+        cudaGraphExec_t* ge = with_mel ? &s->gexec_mel : &s->gexec;
+        e = cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) return bail(LTB_FAIL(std::string("graph capture begin: ") + cudaGetErrorString(e)));
+        const int rc = run_ops(s, with_mel != 0);
+        e = cudaStreamEndCapture(s->st, g);
+        if (rc || e != cudaSuccess) {
+          ok = false;
+          why = std::string("graph capture: ") + (rc ? ltb_last_error() : cudaGetErrorString(e));
+          break;
+        }
+        e = cudaGraphInstantiate(ge, *g, 0);
+        if (e == cudaSuccess) e = cudaGraphLaunch(*ge, s->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+        if (e != cudaSuccess) {
+          ok = false;
+          why = std::string("graph instantiate/warm-up: ") + cudaGetErrorString(e);
+        }
+      }
+      if (ok) break;
+      cudaGetLastError();
+      if (s->gexec) cudaGraphExecDestroy(s->gexec);
+      if (s->graph) cudaGraphDestroy(s->graph);
+      if (s->gexec_mel) cudaGraphExecDestroy(s->gexec_mel);
+      if (s->graph_mel) cudaGraphDestroy(s->graph_mel);
+      s->gexec = s->gexec_mel = nullptr;
+      s->graph = s->graph_mel = nullptr;
+      if (attempt == 1 || !s->pdl) return bail(LTB_FAIL(why));
+      s->pdl = false;
     }
   }
   *out = s;

@@ -118,11 +118,11 @@ class W2LSession:
     """One avatar stream: activation arena + stream + layer plan for a fixed batch size."""
 
     def __init__(self, model: W2LModel, avatar: W2LAvatar, batch: int, stride_left: int = 10, stride_right: int = 10,
-                 fps: int = 25, keep_layers: bool = False, no_graph: bool = False, no_halo: bool = False):
+                 fps: int = 25, keep_layers: bool = False, no_graph: bool = False, no_halo: bool = False, no_pdl: bool = False):
         self.model, self.avatar = model, avatar
         self.batch, self.l, self.r, self.fps = int(batch), int(stride_left), int(stride_right), int(fps)
         flags = ((_capi.LTB_SESSION_KEEP_LAYERS if keep_layers else 0) | (_capi.LTB_SESSION_NO_GRAPH if no_graph else 0) |
-                 (_capi.LTB_SESSION_NO_HALO if no_halo else 0))
+                 (_capi.LTB_SESSION_NO_HALO if no_halo else 0) | (_capi.LTB_SESSION_NO_PDL if no_pdl else 0))
         self._h = C.c_void_p()
         check(lib().ltb_w2l_session_create(model._h, avatar._h, self.batch, self.l, self.r, self.fps, flags,
                                            C.byref(self._h)))

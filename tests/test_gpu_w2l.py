@@ -89,6 +89,28 @@ def test_forward_matches_reference_golden(model, golden_dir):
     av.close()
 
 
+def test_pdl_graph_equals_plain_launches(model):
+    """Programmatic dependent launch (conv kernels start before their predecessor ends, gated by griddepcontrol.wait) must
+    not change a single value: PDL graph vs plain graph vs eager launches, replayed several times at B=16."""
+    from livetalking_b200 import engine
+    from oracle import wav2lip_ref as R
+    mel, img = R.synth_inputs(2, seed=21)
+    av, _, _ = _avatar(_faces_from_inputs(img))
+    melB = np.tile(mel.numpy().reshape(2, 80, 16), (8, 1, 1))
+    plain = engine.W2LSession(model, av, 16, no_pdl=True)
+    want = plain.infer(3, melB)
+    plain.close()
+    pdl = engine.W2LSession(model, av, 16)
+    for _ in range(4):
+        got = pdl.infer(3, melB)
+        assert np.array_equal(got, want)
+    pdl.close()
+    eager = engine.W2LSession(model, av, 16, no_graph=True)
+    assert np.array_equal(eager.infer(3, melB), want)
+    eager.close()
+    av.close()
+
+
 def test_full_batch16_properties(model, w2l_state_dict):
     """BASELINE config 2 size (B=16): determinism, batch-size independence, mirror_index face gather."""
     from livetalking_b200 import engine
