@@ -17,6 +17,8 @@ Load-time rewrites (exact up to fp16 rounding):
 """
 from __future__ import annotations
 
+import os
+
 import math
 from typing import Dict, List, Optional
 
@@ -129,7 +131,7 @@ class Builder:
     # Fusing the GroupNorm statistics into the producing conv's epilogue (ltb_conv_op.gn_stats) is implemented and parity-tested,
     # but measured SLOWER on B200 (MuseTalk B=8: 15.6 -> 17.6 ms/step): the extra shuffles/atomics make the 0.9 PFLOP/s VAE convs
     # epilogue-bound, which costs more than the separate statistics pass (1.0 ms) saves.  Off by default.
-    FUSE_GN_STATS = False
+    FUSE_GN_STATS = os.environ.get("LTB_FUSE_GN", "0") == "1"
 
     def __init__(self, ctx: Ctx):
         self.ctx = ctx

@@ -186,6 +186,28 @@ def test_paste_back_bit_exact(model, golden_dir):
     av.close()
 
 
+def test_paste_vectorised_rows(model):
+    """W % 16 == 0 takes the 128-bit row path (w2l_paste_vec_kernel): generic, 2x-decimation (INTER_AREA) and 1:1 boxes with
+    unaligned edges, batch with mirror_index, bit-exact against the OpenCV restatement."""
+    from livetalking_b200 import engine
+    from oracle import paste_ref as P
+    rng = np.random.default_rng(11)
+    n, H, W = 4, 288, 320
+    faces = [rng.integers(0, 256, (256, 256, 3), dtype=np.uint8) for _ in range(n)]
+    frames = rng.integers(0, 256, (n, H, W, 3), dtype=np.uint8)
+    boxes = [(3, 283, 5, 317), (7, 135, 33, 161), (16, 272, 37, 293), (100, 131, 15, 18)]   # generic, 128x128, 256x256, sliver
+    av = engine.W2LAvatar(faces, frames, boxes)
+    s = engine.W2LSession(model, av, 6)
+    pred = s.infer(1, rng.standard_normal((6, 80, 16)).astype(np.float32))
+    got = s.paste_batch(1)
+    for i in range(6):
+        idx = P.mirror_index(n, 1 + i)
+        want = P.w2l_paste_back(pred[i], frames[idx], boxes[idx])
+        assert np.array_equal(got[i], want), (i, idx, int(np.abs(got[i].astype(int) - want).max()))
+    s.close()
+    av.close()
+
+
 def test_paste_batch_and_odd_width(model):
     from livetalking_b200 import engine
     from oracle import paste_ref as P
