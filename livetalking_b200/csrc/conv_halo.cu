@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
         if (TAPS == 9) {
           const int gy = ty * (16 * NSUB) + sub * 16 + ry, gx = tx * 8 + rx;
           opix = ((size_t)img * p.OH + gy * p.osy + p.acc_oy[acc]) * p.OW + gx * p.osx + p.acc_ox[acc];
+          row_ok = gy < p.GH && gx < p.GW;   // tiles may overhang small / odd-sized maps
         } else {
           opix = (size_t)mt * (128 * NSUB) + sub * 128 + row;      // GEMM mode: output row index
           row_ok = opix < (size_t)p.M;
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
                 }
               }
             }
-            if (kHeadOk && head) {
+            if (kHeadOk && head && row_ok) {
               float* o = p.head_out + opix * 3;
               o[0] = (1.f / (1.f + expf(-ha0))) * 255.f;
               o[1] = (1.f / (1.f + expf(-ha1))) * 255.f;
@@ -504,6 +505,8 @@ static bool is_gemm(const ConvParams& p) {
          p.osx == 1 && p.IH == p.GH && p.IW == p.GW && p.OH == p.GH && p.OW == p.GW && p.zbatch <= 1;
 }
 
+static bool pick_cfg(const ConvParams& p, int* BN, int* NSUB, int* NACC);
+
 bool conv_halo_supported(const ConvParams& p) {
   if (is_gemm(p)) {
     // TMA GEMM: K-major rows with 16-byte aligned pitch; worth it from a few M tiles upwards
@@ -511,9 +514,20 @@ bool conv_halo_supported(const ConvParams& p) {
            (p.ph[0].koff % 8) == 0 && p.M >= 512 && get_encode() != nullptr;
   }
   if (!(is_conv3x3(p) || is_convT(p))) return false;
-  if (p.GH % 16 != 0 || p.GW % 8 != 0) return false;
+  // tiles of 16*NSUB x 8 pixels may overhang the map (TMA zero-fills the halo, the epilogue masks the stores): small maps
+  // (8x8, 4x4 ...) waste MMA rows but still beat the latency-bound gather kernel
   if (p.Cout % 32 != 0 || p.Cin < 16) return false;
   if ((p.ICtot % 8) || (p.ic_off % 8) || (p.Ktot != 9 * p.Cin)) return false;
+  if (p.GH % 16 != 0 || p.GW % 8 != 0) {
+    // overhanging tiles burn MMA rows on pixels that do not exist: worth it only while the whole layer is a short chain
+    // (w2l 512-channel 4x4 / 8x8 maps at batch 16: 1 wave x 8..16 K chunks); the 1280-channel 4x4 / 8x8 maps of the MuseTalk
+    // UNet at batch 8 (2 waves x 20 chunks) stay on the split-K gather kernel, which measured faster there
+    int BN, NSUB, NACC;
+    if (!pick_cfg(p, &BN, &NSUB, &NACC)) return false;
+    const long tiles = (long)p.N * ((p.GH + 16 * NSUB - 1) / (16 * NSUB)) * ((p.GW + 7) / 8) * (p.Cout / BN);
+    const long waves = (tiles + 147) / 148, chunks = (p.Cin + 63) / 64;
+    if (waves * chunks > 16) return false;
+  }
   return get_encode() != nullptr;
 }
 
@@ -537,7 +551,7 @@ static bool pick_cfg(const ConvParams& p, int* BN, int* NSUB, int* NACC) {
   *NSUB = (p.GH % 32 == 0) ? 2 : 1;
   *BN = (p.Cout % 128 == 0) ? 128 : (p.Cout % 64 == 0) ? 64 : 32;
   // small problems: prefer more tiles over wider tiles so the persistent grid fills the 148 SMs
-  auto tiles = [&](int bn, int nsub) { return (long)p.N * (p.GH / (16 * nsub)) * (p.GW / 8) * (p.Cout / bn); };
+  auto tiles = [&](int bn, int nsub) { return (long)p.N * ((p.GH + 16 * nsub - 1) / (16 * nsub)) * ((p.GW + 7) / 8) * (p.Cout / bn); };
   if (*NSUB == 2 && tiles(*BN, 2) < 148) *NSUB = 1;
   while (*BN > 32 && tiles(*BN, *NSUB) < 120) *BN >>= 1;
   return true;
@@ -602,6 +616,8 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
   h.rc_off = p.rc_off;
   h.OH = p.OH;
   h.OW = p.OW;
+  h.GH = p.GH;
+  h.GW = p.GW;
   h.osy = p.osy;
   h.osx = p.osx;
   h.relu = p.relu;
@@ -627,8 +643,8 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
     h.total_tiles = h.tiles_x * h.tiles_n;
     return 0;
   }
-  h.tiles_x = p.GW / 8;
-  h.tiles_y = p.GH / (16 * NSUB);
+  h.tiles_x = (p.GW + 7) / 8;
+  h.tiles_y = (p.GH + 16 * NSUB - 1) / (16 * NSUB);
   h.total_tiles = h.tiles_x * h.tiles_y * p.N * h.tiles_n;
   return 0;
 }

@@ -19,6 +19,7 @@ struct alignas(64) HaloParams {
   int last_ksteps;  // 16-wide K steps that carry data in the last 64-channel chunk (1..4)
   int OCtot, oc_off, RCtot, rc_off;
   int OH, OW, osy, osx;
+  int GH, GW;            // tile-grid extent (= input H, W): tiles may overhang it, rows/columns beyond are masked
   int relu;
   int halo_y0, halo_x0;  // halo origin relative to the tile origin (-1 for pad-1 conv, 0 for ConvT phases)
   int tap_row[9];        // halo row offset (dy*10 + dx) of each of the 9 K-slices

@@ -96,6 +96,13 @@ HALO_CASES = [
     (1, 16, 8, 128, 32, True, False),       # ConvT BN=32
     (1, 32, 32, 320, 128, True, False),     # ConvT 320->128
     (1, 128, 128, 64, 64, False, True),     # many tiles per CTA
+    (16, 8, 8, 512, 512, False, True),      # map smaller than a tile: overhanging rows masked (w2l L28/L37)
+    (16, 4, 4, 512, 512, False, True),      # 4x4 map: rows and columns masked (w2l L30/L35)
+    (4, 4, 4, 1024, 512, True, False),      # ConvT 4x4 -> 8x8 (w2l L36)
+    (2, 8, 8, 1024, 512, True, False),      # ConvT 8x8 -> 16x16 (w2l L38)
+    (2, 27, 16, 64, 64, False, True),       # odd height (audio encoder 27x16)
+    (3, 9, 6, 128, 128, False, True),       # odd height and width
+    (2, 20, 12, 64, 32, True, False),       # ConvT over an odd-sized map
 ]
 
 
