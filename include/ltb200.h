@@ -87,9 +87,12 @@ int ltb_w2l_mel_resident(ltb_w2l_session* s);
 /* whole step with everything resident in HBM: mel (resident PCM) + forward + batched paste-back, enqueued on the
  * session stream WITHOUT synchronising — used for device-timed throughput. */
 int ltb_w2l_step_async(ltb_w2l_session* s, int index);
+/* the U-Net forward only (face gather + every conv + head; mel windows as left by the last mel call), enqueued without
+ * synchronising: the timed region of bench.py's roofline figure (all conv launches of one step, back to back). */
+int ltb_w2l_forward_async(ltb_w2l_session* s, int index);
 /* profiling pass: runs the forward eagerly with a CUDA event between every op; returns per-op milliseconds, the
  * algorithmic FLOPs of each op (2*M*N*K of the conv it implements, 0 for non-conv ops) and op kinds
- * (0 conv, 1 prep_faces, 2 audio_conv0, 3 head).  Call with ms == NULL to query n_ops. */
+ * (0 conv gather, 1 prep_faces, 2 audio_conv0, 3 head, 4 conv halo, 5 stem, 6 mel).  Call with ms == NULL to query n_ops. */
 int ltb_w2l_profile_ops(ltb_w2l_session* s, int index, int max_ops, int* n_ops, float* ms, double* flops, int* kinds);
 /* pipelined end-to-end step with HOST buffers: H2D of the PCM window, mel, forward, batched paste-back, and the D2H of
  * the `batch` composited frames on a copy stream (double-buffered on the device, so the copy of step i overlaps the

@@ -59,6 +59,7 @@ _SIGS = {
     "ltb_w2l_paste_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ltb_w2l_mel_resident": (C.c_int, [C.c_void_p]),
     "ltb_w2l_step_async": (C.c_int, [C.c_void_p, C.c_int]),
+    "ltb_w2l_forward_async": (C.c_int, [C.c_void_p, C.c_int]),
     "ltb_w2l_profile_ops": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p]),
     "ltb_w2l_step_e2e_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "ltb_w2l_e2e_acquire": (C.c_int, [C.c_void_p]),

@@ -1025,6 +1025,11 @@ int ltb_w2l_step_async(ltb_w2l_session* s, int index) {
   return paste_batch_enqueue(s, index);
 }
 
+int ltb_w2l_forward_async(ltb_w2l_session* s, int index) {
+  if (!s) return LTB_FAIL("null session");
+  return forward_enqueue(s, index, false);
+}
+
 int ltb_w2l_profile_ops(ltb_w2l_session* s, int index, int max_ops, int* n_ops, float* ms, double* flops, int* kinds) {
   if (!s || !n_ops) return LTB_FAIL("null argument");
   const int n = (int)s->ops.size();

@@ -183,6 +183,10 @@ class W2LSession:
     def step_async(self, index: int) -> None:
         check(lib().ltb_w2l_step_async(self._h, int(index)))
 
+    def forward_async(self, index: int) -> None:
+        """U-Net forward only (no mel, no paste-back), enqueued without synchronising."""
+        check(lib().ltb_w2l_forward_async(self._h, int(index)))
+
     def step_e2e_async(self, index: int, pcm_pinned: np.ndarray, frames_pinned: np.ndarray) -> None:
         """Pipelined host-to-host step (pinned buffers): H2D PCM -> mel -> forward -> paste -> D2H frames on a copy stream."""
         check(lib().ltb_w2l_step_e2e_async(self._h, int(index), _ptr(pcm_pinned), int(pcm_pinned.size), _ptr(frames_pinned)))
