@@ -54,10 +54,13 @@ struct HaloCfg {
   static constexpr int B_STAGES_MAX = (BUDGET - A_STAGES * A_BYTES) / B_BYTES;
   static constexpr int B_STAGES = RC ? RC * TG : (B_STAGES_MAX > 6 ? 6 : B_STAGES_MAX);
   static constexpr int ACC_COLS = NACC * NSUB * BN;                         // fp32 columns per accumulator buffer
-  static constexpr int TCOLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
-                               : (2 * ACC_COLS <= 256) ? 256 : 512;
+  // accumulator buffers: two (the epilogue of tile i overlaps the MMAs of tile i+1) unless one set already fills the 512
+  // TMEM columns (ConvT with BN = 128: four 128-column phase accumulators)
+  static constexpr int NBUF = (2 * ACC_COLS <= 512) ? 2 : 1;
+  static constexpr int TCOLS = (NBUF * ACC_COLS <= 32) ? 32 : (NBUF * ACC_COLS <= 64) ? 64 : (NBUF * ACC_COLS <= 128) ? 128
+                               : (NBUF * ACC_COLS <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_STAGES * B_BYTES + 1024;
-  static_assert(2 * ACC_COLS <= 512, "TMEM overflow");
+  static_assert(NBUF * ACC_COLS <= 512, "TMEM overflow");
   static_assert(B_STAGES >= 2, "not enough shared memory for the weight ring");
   static_assert(A_STAGES >= 2, "not enough shared memory for the halo ring");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory overflow");
@@ -185,8 +188,8 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
       }
       if (RC) mbar_wait(smem_u32(&b_full[0]), 0);
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-        const uint32_t buf = it & 1u;
-        mbar_wait(smem_u32(&acc_empty[buf]), ((it >> 1) & 1u) ^ 1u);
+        const uint32_t buf = it % C::NBUF;
+        mbar_wait(smem_u32(&acc_empty[buf]), ((it / C::NBUF) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t dbase = tmem + buf * C::ACC_COLS;
 #pragma unroll 1
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
         ty = mt / p.tiles_x;
         tx = mt - ty * p.tiles_x;
       }
-      const uint32_t buf = it & 1u;
+      const uint32_t buf = it % C::NBUF;
       const int n0 = nt * BN;
       // Work items of this warp: the 32-column accumulator chunks ci = grp, grp+2, ...  (ci -> phase acc, sub-tile sub, column c0)
       constexpr int NCH = NACC * NSUB * BN / 32;
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
         }
       };
       if (has_res && grp < NCH) load_res(grp);
-      mbar_wait(smem_u32(&acc_full[buf]), (it >> 1) & 1u);
+      mbar_wait(smem_u32(&acc_full[buf]), (it / C::NBUF) & 1u);
       tc_fence_after();
       const uint32_t tbase = tmem + buf * C::ACC_COLS + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
@@ -546,6 +549,10 @@ static bool pick_cfg(const ConvParams& p, int* BN, int* NSUB, int* NACC) {
   if (tr) {
     *NSUB = 1;
     *BN = (p.Cout % 64 == 0) ? 64 : 32;
+    // BN = 128 (single accumulator set, no epilogue overlap) halves the halo re-reads and the MMA count per FLOP: pays off
+    // once BN = 64 would need more than one wave of tiles
+    const long t64 = (long)p.N * ((p.GH + 15) / 16) * ((p.GW + 7) / 8) * (p.Cout / 64);
+    if (p.Cout % 128 == 0 && t64 > 148) *BN = 128;
     return true;
   }
   *NSUB = (p.GH % 32 == 0) ? 2 : 1;
@@ -697,6 +704,7 @@ cudaError_t launch_conv_halo(const HaloPlan& pl, cudaStream_t st) {
     case 6411: return launch_cfg<64, 1, 1>(pl, sms, st);
     case 3221: return launch_cfg<32, 2, 1>(pl, sms, st);
     case 3211: return launch_cfg<32, 1, 1>(pl, sms, st);
+    case 12814: return launch_cfg<128, 1, 4>(pl, sms, st);
     case 6414: return launch_cfg<64, 1, 4>(pl, sms, st);
     case 3214: return launch_cfg<32, 1, 4>(pl, sms, st);
   }
