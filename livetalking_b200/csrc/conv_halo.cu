@@ -552,7 +552,8 @@ static bool pick_cfg(const ConvParams& p, int* BN, int* NSUB, int* NACC) {
     // BN = 128 (single accumulator set, no epilogue overlap) halves the halo re-reads and the MMA count per FLOP: pays off
     // once BN = 64 would need more than one wave of tiles
     const long t64 = (long)p.N * ((p.GH + 15) / 16) * ((p.GW + 7) / 8) * (p.Cout / 64);
-    if (p.Cout % 128 == 0 && t64 > 148) *BN = 128;
+    // ... and the K loop is long enough (>= 8 chunks) to amortise the now serialised epilogue (320->128 @64x64 measured slower)
+    if (p.Cout % 128 == 0 && t64 > 148 && p.Cin >= 512) *BN = 128;
     return true;
   }
   *NSUB = (p.GH % 32 == 0) ? 2 : 1;

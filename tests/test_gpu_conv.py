@@ -103,8 +103,8 @@ HALO_CASES = [
     (2, 27, 16, 64, 64, False, True),       # odd height (audio encoder 27x16)
     (3, 9, 6, 128, 128, False, True),       # odd height and width
     (2, 20, 12, 64, 32, True, False),       # ConvT over an odd-sized map
-    (3, 64, 64, 96, 128, True, False),      # ConvT BN=128: one 512-column accumulator set (single-buffered TMEM), ragged chunk
-    (2, 64, 64, 64, 256, True, False),      # ConvT BN=128, two N tiles
+    (3, 64, 64, 544, 128, True, False),     # ConvT BN=128: one 512-column accumulator set (single-buffered TMEM), ragged chunk
+    (3, 64, 32, 512, 256, True, False),     # ConvT BN=128, two N tiles
 ]
 
 
