@@ -22,7 +22,8 @@ def main():
         print(build.build(defines=("LTB_HALO_DIAG",), tag="_diag"))
         return
     from livetalking_b200 import _capi
-    _capi.LIB_PATH = os.path.join(os.path.dirname(_capi.LIB_PATH), "libltb200_diag.so")
+    if not os.environ.get("LTB_DIAG_NORMAL_LIB"):     # LTB_DIAG_NORMAL_LIB=1: time / profile the product library (variant 0 only)
+        _capi.LIB_PATH = os.path.join(os.path.dirname(_capi.LIB_PATH), "libltb200_diag.so")
     from livetalking_b200 import ops
     ctx = ops.Ctx()
     rng = np.random.default_rng(0)
