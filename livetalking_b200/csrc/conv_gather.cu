@@ -51,7 +51,6 @@ __global__ void __launch_bounds__(160) conv_gather_umma_kernel(const __grid_cons
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int lane = tid & 31;
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
   const int zphase = (p.ksplit > 1) ? 0 : ((p.zbatch > 1) ? (int)(blockIdx.z % p.nphases) : (int)blockIdx.z);
