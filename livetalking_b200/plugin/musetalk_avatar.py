@@ -78,6 +78,9 @@ def load_avatar(avatar_id, model: EngineModel = None):
     """musetalk_avatar.py:69-91 — same on-disk format (full_imgs/, mask/, coords.pkl, mask_coords.pkl, latents.pt)."""
     import torch
     p = f"./data/avatars/{avatar_id}"
+    if os.path.exists(f"{p}/avatar.ltbav"):            # packed form (livetalking_b200.avatar_pack): one read, no PNG decodes
+        from .. import avatar_pack
+        return make_avatar(*avatar_pack.load_packed(f"{p}/avatar.ltbav").musetalk_lists(), model)
     key = lambda x: int(os.path.splitext(os.path.basename(x))[0])  # noqa: E731
     latents = torch.load(f"{p}/latents.pt", map_location="cpu")
     with open(f"{p}/coords.pkl", "rb") as f:

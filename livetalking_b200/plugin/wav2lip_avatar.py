@@ -20,7 +20,7 @@ import pickle
 
 import numpy as np
 
-from .. import engine
+from .. import avatar_pack, engine
 from .mel_asr import MelASR
 
 try:
@@ -57,8 +57,12 @@ def load_model(path):
 
 
 def load_avatar(avatar_id):
-    """wav2lip_avatar.py:72-88 — same on-disk format; additionally uploads the assets once."""
+    """wav2lip_avatar.py:72-88 — same on-disk format; additionally uploads the assets once.  A packed ``avatar.ltbav``
+    (``python -m livetalking_b200.avatar_pack``) next to the image folders is preferred: one sequential read, no PNG decodes."""
     avatar_path = f"./data/avatars/{avatar_id}"
+    packed = os.path.join(avatar_path, "avatar.ltbav")
+    if os.path.exists(packed):
+        return make_avatar(*avatar_pack.load_packed(packed).wav2lip_lists())
     with open(f"{avatar_path}/coords.pkl", "rb") as f:
         coord_list_cycle = pickle.load(f)
     key = lambda x: int(os.path.splitext(os.path.basename(x))[0])  # noqa: E731

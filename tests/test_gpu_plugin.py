@@ -122,3 +122,36 @@ def test_musereal_session_loop():
         out = av.paste_back_frame(pred[i], idxs[i])
         assert np.array_equal(out, P.mt_paste_back(pred[i], frames[idxs[i]], coords[idxs[i]], masks[idxs[i]], crops[idxs[i]]))
         assert out.flags.writeable and out.flags.c_contiguous
+
+
+def test_load_avatar_prefers_packed_assets(tmp_path, monkeypatch):
+    """plugin.load_avatar: the packed avatar.ltbav yields the same payload and the same resident
+    assets as the reference's directory of PNGs + coords.pkl (wav2lip_avatar.py:72-88)."""
+    import pickle
+    import cv2
+    stubs.install()
+    from livetalking_b200 import avatar_pack, engine
+    from livetalking_b200.plugin import wav2lip_avatar as W
+    engine.set_device(0)
+    rng = np.random.default_rng(8)
+    root = tmp_path / "data" / "avatars" / "demo"
+    (root / "full_imgs").mkdir(parents=True)
+    (root / "face_imgs").mkdir()
+    coords = []
+    for i in range(3):
+        cv2.imwrite(str(root / "full_imgs" / f"{i:08d}.png"), rng.integers(0, 256, (96, 128, 3), dtype=np.uint8))
+        cv2.imwrite(str(root / "face_imgs" / f"{i:08d}.png"), rng.integers(0, 256, (256, 256, 3), dtype=np.uint8))
+        coords.append((4 + i, 84 + i, 10, 100))
+    pickle.dump(coords, open(root / "coords.pkl", "wb"))
+    monkeypatch.chdir(tmp_path)
+    plain = W.load_avatar("demo")                                   # directory form
+    avatar_pack.pack_wav2lip(str(root))
+    packed = W.load_avatar("demo")                                  # packed form is picked up
+    for a, b in zip(plain[0] + plain[1], packed[0] + packed[1]):
+        assert np.array_equal(a, b)
+    assert [tuple(c) for c in plain[2]] == [tuple(c) for c in packed[2]]
+    ea, eb = plain.engine_avatar, packed.engine_avatar
+    assert (ea.n, ea.H, ea.W) == (eb.n, eb.H, eb.W) == (3, 96, 128)
+    assert np.array_equal(ea.faces, eb.faces) and np.array_equal(ea.frames, eb.frames) and np.array_equal(ea.coords, eb.coords)
+    ea.close()
+    eb.close()
