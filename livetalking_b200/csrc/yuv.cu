@@ -1,0 +1,75 @@
+// BGR (uint8 NHWC) -> planar YUV 4:2:0 (I420) on the GPU: the colour conversion that precedes the H.264 encoder.
+// SURVEY.md §8(f) rank 3 — the reference hands BGR frames to PyAV (avatars/base_avatar.py:449-453) and libswscale converts
+// them on the CPU inside the encoder (server/webrtc.py); with the composite already resident in HBM the conversion belongs
+// here (NVENC takes I420/NV12 device surfaces).  Arithmetic: OpenCV's COLOR_BGR2YUV_I420 (BT.601 limited range, 20-bit
+// fixed point, chroma from the top-left pixel of each 2x2 block) — bit-exact with oracle/yuv_ref.py, which is pinned
+// against the installed cv2.  Byte work, HBM-bound: 3 B read + 1.5 B written per pixel.
+// One thread = 4 x 2 pixels: two rows of three 32-bit loads, two 32-bit Y stores, one 16-bit U and one 16-bit V store.
+#include "ltb_internal.h"
+#include "ops.h"
+
+namespace ltb {
+
+namespace {
+constexpr int kShift = 20;
+constexpr int kCRY = 269484, kCGY = 528482, kCBY = 102760;
+constexpr int kCRU = -155188, kCGU = -305135, kCBU = 460324;
+constexpr int kCGV = -385875, kCBV = -74448;
+constexpr int kHalf = 1 << (kShift - 1);
+
+__device__ __forceinline__ uint32_t sat_u8(int v) { return (uint32_t)min(max(v, 0), 255); }
+__device__ __forceinline__ uint32_t luma(int b, int g, int r) {
+  return sat_u8((kCRY * r + kCGY * g + kCBY * b + kHalf + (16 << kShift)) >> kShift);
+}
+}  // namespace
+
+__global__ void __launch_bounds__(256) bgr_to_i420_kernel(const uint8_t* __restrict__ bgr, int N, int H, int W, uint8_t* __restrict__ out) {
+  const int gw = W >> 2, gh = H >> 1;                  // 4-pixel groups per row, row pairs
+  const long long total = (long long)N * gh * gw;
+  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
+    const int gx = (int)(t % gw);
+    const int gy = (int)((t / gw) % gh);
+    const int n = (int)(t / ((long long)gw * gh));
+    const uint8_t* src = bgr + ((size_t)n * H + 2 * gy) * W * 3 + (size_t)gx * 12;
+    uint8_t* dst = out + (size_t)n * (H * 3 / 2) * W;
+    uint32_t y4[2];
+    int b00 = 0, g00 = 0, r00 = 0, b02 = 0, g02 = 0, r02 = 0;
+#pragma unroll
+    for (int row = 0; row < 2; ++row) {
+      const uint32_t* p = reinterpret_cast<const uint32_t*>(src + (size_t)row * W * 3);
+      const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);   // B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+      const int b0 = w0 & 255, g0 = (w0 >> 8) & 255, r0 = (w0 >> 16) & 255;
+      const int b1 = w0 >> 24, g1 = w1 & 255, r1 = (w1 >> 8) & 255;
+      const int b2 = (w1 >> 16) & 255, g2 = w1 >> 24, r2 = w2 & 255;
+      const int b3 = (w2 >> 8) & 255, g3 = (w2 >> 16) & 255, r3 = w2 >> 24;
+      y4[row] = luma(b0, g0, r0) | (luma(b1, g1, r1) << 8) | (luma(b2, g2, r2) << 16) | (luma(b3, g3, r3) << 24);
+      if (row == 0) {
+        b00 = b0; g00 = g0; r00 = r0;
+        b02 = b2; g02 = g2; r02 = r2;
+      }
+    }
+    *reinterpret_cast<uint32_t*>(dst + (size_t)(2 * gy) * W + gx * 4) = y4[0];
+    *reinterpret_cast<uint32_t*>(dst + (size_t)(2 * gy + 1) * W + gx * 4) = y4[1];
+    const uint32_t u0 = sat_u8((kCRU * r00 + kCGU * g00 + kCBU * b00 + kHalf + (128 << kShift)) >> kShift);
+    const uint32_t u1 = sat_u8((kCRU * r02 + kCGU * g02 + kCBU * b02 + kHalf + (128 << kShift)) >> kShift);
+    const uint32_t v0 = sat_u8((kCBU * r00 + kCGV * g00 + kCBV * b00 + kHalf + (128 << kShift)) >> kShift);
+    const uint32_t v1 = sat_u8((kCBU * r02 + kCGV * g02 + kCBV * b02 + kHalf + (128 << kShift)) >> kShift);
+    const size_t cw = (size_t)(W >> 1);
+    uint8_t* uplane = dst + (size_t)H * W;
+    uint8_t* vplane = uplane + (size_t)(H >> 1) * cw;
+    *reinterpret_cast<uint16_t*>(uplane + (size_t)gy * cw + gx * 2) = (uint16_t)(u0 | (u1 << 8));
+    *reinterpret_cast<uint16_t*>(vplane + (size_t)gy * cw + gx * 2) = (uint16_t)(v0 | (v1 << 8));
+  }
+}
+
+cudaError_t launch_bgr_to_i420(const uint8_t* bgr, int N, int H, int W, uint8_t* out, cudaStream_t st) {
+  if (N <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 3)) return cudaErrorInvalidValue;   // even height, width multiple of 4
+  if ((reinterpret_cast<uintptr_t>(bgr) & 3) || (reinterpret_cast<uintptr_t>(out) & 3)) return cudaErrorInvalidValue;
+  const long long total = (long long)N * (H >> 1) * (W >> 2);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  bgr_to_i420_kernel<<<(unsigned)blocks, 256, 0, st>>>(bgr, N, H, W, out);
+  return cudaGetLastError();
+}
+
+}  // namespace ltb

@@ -205,6 +205,10 @@ class Ctx:
     def transpose_heads(self, v_ptr: int, B: int, n_keys: int, Ctot: int, heads: int, d: int, n_pad: int, vt: DevTensor):
         check(lib().ltb_op_transpose_heads(self._h, C.c_void_p(v_ptr), B, n_keys, Ctot, 0, heads, d, n_pad, C.c_void_p(vt.ptr)))
 
+    def bgr_to_i420(self, frames_u8: DevTensor, N: int, H: int, W: int, out_u8: DevTensor):
+        """uint8 BGR [N,H,W,3] -> planar I420 [N, H*3/2, W] (encoder hand-off; cv2.COLOR_BGR2YUV_I420 arithmetic)."""
+        check(lib().ltb_op_bgr_to_i420(self._h, C.c_void_p(frames_u8.ptr), N, H, W, C.c_void_p(out_u8.ptr)))
+
     def vae_post(self, x: DevTensor, npix: int, out_u8: DevTensor):
         check(lib().ltb_op_vae_post(self._h, C.c_void_p(x.ptr), npix, x.pitch, C.c_void_p(out_u8.ptr)))
 
