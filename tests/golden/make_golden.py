@@ -120,7 +120,34 @@ def make_mel():
     print("mel golden ok", win.shape, float((win == -4).mean()))
 
 
+def make_slices():
+    """Window indices of the audio-feature slicing, produced by the reference's OWN code:
+    BaseASR._get_sliced_feature (avatars/audio_features/base_asr.py:91-133) driven as WhisperASR._feature2chunks /
+    run_step do (whisper.py:35-76: win [0,5], start = stride_left/2, multiplier 2), and the Wav2Lip mel window starts of
+    MelASR.run_step (mel.py:47-63).  Pins the index arithmetic of csrc/whisper.cu::whisper_slice and csrc/mel.cu."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import stubs
+    stubs.install()
+    spec = importlib.util.spec_from_file_location("ref_base_asr", os.path.join(REF, "avatars/audio_features/base_asr.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    out = {}
+    cfgs = [(4, 10, 1500), (16, 10, 1500), (8, 5, 1500), (32, 10, 1500), (16, 10, 40), (3, 0, 7)]   # (batch, stride_left, feature rows)
+    for B, l, T in cfgs:
+        asr = ref.BaseASR(stubs.Opt(batch_size=B, l=l))
+        feat = np.arange(T, dtype=np.float32).reshape(T, 1)
+        idx = []
+        for i in range(B):                                   # WhisperASR._feature2chunks, whisper.py:48-55
+            sel, sel_idx = asr._get_sliced_feature(feature_array=feat, vid_idx=i + l / 2, audio_feat_win=[0, 5], feature_idx_multiplier=2)
+            assert sel.shape[0] == len(sel_idx) == 10
+            idx.append(sel_idx)
+        out[f"whisper_B{B}_l{l}_T{T}"] = np.asarray(idx, np.int32)
+    np.savez_compressed(os.path.join(HERE, "slice_golden.npz"), cfgs=np.asarray(cfgs, np.int32), **out)
+    print("slice golden ok", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     make_w2l()
     make_paste()
     make_mel()
+    make_slices()
