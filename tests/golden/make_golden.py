@@ -146,8 +146,28 @@ def make_slices():
     print("slice golden ok", {k: v.shape for k, v in out.items()})
 
 
+def make_pe():
+    """MuseTalk audio positional encoding from the reference's OWN class (avatars/musetalk/models/unet.py:12-27), imported by
+    file path with a stub standing in for the absent `diffusers` package (only the UNet wrapper below the class needs it)."""
+    fake = types.ModuleType("diffusers")
+    fake.UNet2DConditionModel = object
+    sys.modules.setdefault("diffusers", fake)
+    spec = importlib.util.spec_from_file_location("ref_mt_unet", os.path.join(REF, "avatars/musetalk/models/unet.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    pe = ref.PositionalEncoding(d_model=384)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 50, 384, generator=g)
+    with torch.no_grad():
+        y = pe(x)
+    # x is regenerated from the seed by the test; keep the sinusoid table and a subsample of the module's output
+    np.savez_compressed(os.path.join(HERE, "pe_golden.npz"), seed=np.int64(11), table=pe.pe[0, :50].numpy(), y_sub=y.numpy()[:, ::5, ::7])
+    print("pe golden ok", tuple(y.shape))
+
+
 if __name__ == "__main__":
     make_w2l()
     make_paste()
     make_mel()
     make_slices()
+    make_pe()
