@@ -165,9 +165,52 @@ def make_pe():
     print("pe golden ok", tuple(y.shape))
 
 
+def make_vae_glue():
+    """The pre/post-processing around the (absent) diffusers VAE, executed by the reference's OWN wrapper methods
+    (avatars/musetalk/models/vae.py:51-82 preprocess_img, :96-108 decode_latents) on an instance built without __init__
+    (AutoencoderKL.from_pretrained needs the checkpoint) and a fake `vae` whose decode returns a fixed tensor."""
+    import zlib
+    fake = types.ModuleType("diffusers")
+    fake.AutoencoderKL = object
+    sys.modules.setdefault("diffusers", fake)
+    if not hasattr(sys.modules["diffusers"], "AutoencoderKL"):
+        sys.modules["diffusers"].AutoencoderKL = object
+    spec = importlib.util.spec_from_file_location("ref_mt_vae", os.path.join(REF, "avatars/musetalk/models/vae.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    import torchvision.transforms as transforms
+    v = object.__new__(ref.VAE)
+    v._resized_img = 256
+    v._mask_tensor = v.get_mask_tensor()
+    v.transform = transforms.Normalize(mean=[0.5, 0.5, 0.5], std=[0.5, 0.5, 0.5])
+    v.scaling_factor = 0.18215
+    g = torch.Generator().manual_seed(23)
+    sample = torch.randn(2, 3, 64, 48, generator=g) * 0.8                      # decoder output, partly outside [-1, 1]
+
+    class FakeVae:
+        device = torch.device("cpu")
+        dtype = torch.float32
+
+        def decode(self, z):
+            return types.SimpleNamespace(sample=sample)
+    v.vae = FakeVae()
+    rng = np.random.default_rng(23)
+    img = rng.integers(0, 256, (256, 256, 3), dtype=np.uint8)
+    pre_full = v.preprocess_img(img, half_mask=False).numpy()
+    pre_half = v.preprocess_img(img, half_mask=True).numpy()
+    post = v.decode_latents(torch.zeros(2, 4, 8, 6))
+    np.savez_compressed(os.path.join(HERE, "vae_glue_golden.npz"), seed=np.int64(23),
+                        pre_full_crc=np.uint32(zlib.crc32(np.ascontiguousarray(pre_full).tobytes())),
+                        pre_half_crc=np.uint32(zlib.crc32(np.ascontiguousarray(pre_half).tobytes())),
+                        pre_full_sub=pre_full[0, :, ::37, ::41], pre_half_sub=pre_half[0, :, ::37, ::41],
+                        post=np.ascontiguousarray(post))
+    print("vae glue golden ok", pre_full.shape, post.shape, post.dtype)
+
+
 if __name__ == "__main__":
     make_w2l()
     make_paste()
     make_mel()
     make_slices()
     make_pe()
+    make_vae_glue()
