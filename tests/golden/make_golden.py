@@ -207,6 +207,70 @@ def make_vae_glue():
     print("vae glue golden ok", pre_full.shape, post.shape, post.dtype)
 
 
+def make_lipreal():
+    """a4 + a5 + a6 as ONE piece of reference code: LipReal.inference_batch and LipReal.paste_back_frame
+    (avatars/wav2lip_avatar.py:116-147) executed from the reference's own module (imported by path; `av`, MelASR,
+    BaseAvatar and utils.device are stubbed, utils.image and the Wav2Lip network are the real reference files) on an
+    instance built without __init__.  Pins the oracle's glue: mirror_index gather, lower-half mask, /255 in float64,
+    NCHW float32, x255, astype(uint8) truncation, cv2.resize into the bbox."""
+    import zlib
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import stubs
+    stubs.install()
+    sys.path.insert(0, REF)
+    sys.modules["avatars"].__path__ = [os.path.join(REF, "avatars")]          # real sub-packages (avatars.wav2lip.models) resolve
+    for name, rel in (("utils.image", "utils/image.py"),):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+    dev = types.ModuleType("utils.device")
+    dev.initialize_device = lambda: "cpu"
+    sys.modules["utils.device"] = dev
+    av = types.ModuleType("av")
+    av.AudioFrame = av.VideoFrame = object
+    sys.modules["av"] = av
+    af = types.ModuleType("avatars.audio_features")
+    af.__path__ = []
+    melmod = types.ModuleType("avatars.audio_features.mel")
+    melmod.MelASR = object
+    sys.modules["avatars.audio_features"], sys.modules["avatars.audio_features.mel"] = af, melmod
+    spec = importlib.util.spec_from_file_location("ref_wav2lip_avatar", os.path.join(REF, "avatars/wav2lip_avatar.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+
+    B, n = 3, 2                                                       # batch 3 over a 2-frame avatar: mirror_index wraps and reverses
+    sd = R.synth_state_dict(0)
+    mel, img = R.synth_inputs(n, seed=31)
+    faces = list((img[:, 3:6].permute(0, 2, 3, 1).numpy() * 255.0).round().astype(np.uint8))
+    rng = np.random.default_rng(31)
+    frames = [rng.integers(0, 256, (120, 160, 3), dtype=np.uint8) for _ in range(n)]
+    coords = [(10, 100, 20, 150), (5, 69, 30, 94)]                    # (y1, y2, x1, x2): a stretch and a 64x64 down-scale
+    melB = np.tile(mel.numpy().reshape(n, 80, 16), (2, 1, 1))[:B]
+    net = ref.Wav2Lip()
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    lip = object.__new__(ref.LipReal)
+    lip.face_list_cycle, lip.frame_list_cycle, lip.coord_list_cycle = faces, frames, coords
+    lip.batch_size, lip.model = B, net
+    index = 1
+    pred = lip.inference_batch(index, list(melB))
+    pasted = [lip.paste_back_frame(pred[i], ref.mirror_index(n, index + i)) for i in range(B)]
+    crops = {}
+    for i in range(B):                                                # only the pasted rectangle: the rest of the frame is the seeded input
+        y1, y2, x1, x2 = coords[ref.mirror_index(n, index + i)]
+        crops[f"crop{i}"] = pasted[i][y1:y2, x1:x2].copy()
+        outside = pasted[i].copy()
+        outside[y1:y2, x1:x2] = frames[ref.mirror_index(n, index + i)][y1:y2, x1:x2]
+        assert np.array_equal(outside, frames[ref.mirror_index(n, index + i)])
+    # CPU conv kernels pick different blockings per batch size / thread count, so float results move in the 5th digit between
+    # runs: the fixture keeps values (compared with tolerances), not checksums
+    np.savez_compressed(os.path.join(HERE, "lipreal_golden.npz"), seed=np.int64(31), index=np.int64(index), batch=np.int64(B),
+                        coords=np.asarray(coords, np.int32), pred_sub=pred[:, ::8, ::8, :].astype(np.float32),
+                        pred_u8_sub=pred.astype(np.uint8)[:, ::4, ::4, :], **crops)
+    print("lipreal golden ok", pred.shape, pred.dtype, float(pred.mean()))
+
+
 if __name__ == "__main__":
     make_w2l()
     make_paste()
@@ -214,3 +278,4 @@ if __name__ == "__main__":
     make_slices()
     make_pe()
     make_vae_glue()
+    make_lipreal()
