@@ -207,6 +207,41 @@ def make_vae_glue():
     print("vae glue golden ok", pre_full.shape, post.shape, post.dtype)
 
 
+def make_mel_windows():
+    """Window starts / tail clamping of the Wav2Lip audio features from the reference's OWN MelASR.run_step
+    (avatars/audio_features/mel.py:34-67), imported by path with a stub for the absent `librosa` and with
+    audio.melspectrogram replaced by a fake whose value IS the mel column index (80 x (1 + N // 200), librosa's centred
+    framing): the chunks the reference code queues then spell out exactly which columns each video frame gets."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import stubs
+    stubs.install()
+    sys.path.insert(0, REF)
+    sys.modules["avatars"].__path__ = [os.path.join(REF, "avatars")]
+    for k in [k for k in sys.modules if k.startswith("avatars.audio_features")]:
+        del sys.modules[k]                                            # drop stubs a previous generator may have planted
+    lib = types.ModuleType("librosa")
+    lib.filters = types.ModuleType("librosa.filters")
+    sys.modules.setdefault("librosa", lib)
+    sys.modules.setdefault("librosa.filters", lib.filters)
+    import importlib as il
+    mel_mod = il.import_module("avatars.audio_features.mel")        # the reference file itself (+ real base_asr, real audio.py)
+    audio = il.import_module("avatars.wav2lip.audio")
+    audio.melspectrogram = lambda wav: np.tile(np.arange(1 + len(wav) // 200, dtype=np.float32), (80, 1))
+    out = {}
+    cfgs = [(16, 10, 10, 25), (4, 10, 10, 25), (1, 10, 10, 25), (8, 6, 4, 25), (4, 10, 10, 50), (2, 4, 4, 25), (32, 10, 10, 25)]
+    for B, l, r, fps in cfgs:
+        asr = mel_mod.MelASR(stubs.Opt(batch_size=B, l=l, r=r, fps=fps), None)
+        for i in range(l + r + 2 * B):
+            asr.put_audio_frame(np.full(320, float(i), np.float32), {})
+        asr.warm_up()                                                 # l + r chunks of context (base_asr.py:76-82)
+        asr.run_step()                                                # 2B more chunks -> B windows
+        chunks = asr.feat_queue.get_nowait()
+        assert len(chunks) == B and all(c.shape == (80, 16) for c in chunks), [c.shape for c in chunks]
+        out[f"mel_B{B}_l{l}_r{r}_fps{fps}"] = np.asarray([c[0] for c in chunks], np.int32)      # (B, 16) column indices
+    np.savez_compressed(os.path.join(HERE, "mel_window_golden.npz"), cfgs=np.asarray(cfgs, np.int32), **out)
+    print("mel window golden ok", {k: v[:, 0].tolist()[:5] for k, v in out.items()})
+
+
 def make_lipreal():
     """a4 + a5 + a6 as ONE piece of reference code: LipReal.inference_batch and LipReal.paste_back_frame
     (avatars/wav2lip_avatar.py:116-147) executed from the reference's own module (imported by path; `av`, MelASR,
@@ -279,3 +314,4 @@ if __name__ == "__main__":
     make_pe()
     make_vae_glue()
     make_lipreal()
+    make_mel_windows()
