@@ -242,6 +242,47 @@ def make_mel_windows():
     print("mel window golden ok", {k: v[:, 0].tolist()[:5] for k, v in out.items()})
 
 
+def make_mel_chain():
+    """audio.melspectrogram from the reference's OWN audio.py + hparams.py (avatars/wav2lip/audio.py:20-23, 45-51, 92-122;
+    hparams.py:33-73): pre-emphasis, dB conversion, ref level, symmetric normalisation and clipping, the mel-basis arguments
+    and the stft arguments are the reference's code and constants.  Only the two functions of the ABSENT librosa are
+    substituted — librosa.stft and librosa.filters.mel — by the oracle's restatements, which assert the arguments the
+    reference passes.  Narrows "parity unpinned" for the Wav2Lip mel to exactly those two third-party functions."""
+    from oracle import mel_ref
+    sys.path.insert(0, REF)
+    seen = {}
+
+    def fake_stft(y, n_fft, hop_length, win_length):
+        seen["stft"] = (int(n_fft), int(hop_length), int(win_length))
+        assert seen["stft"] == (800, 200, 800), seen["stft"]
+        return mel_ref.stft_mag(np.asarray(y, np.float64))             # |D|; the reference takes np.abs() of it
+
+    def fake_mel(sr, n_fft, n_mels, fmin, fmax):
+        seen["mel"] = (float(sr), int(n_fft), int(n_mels), float(fmin), float(fmax))
+        assert seen["mel"] == (16000.0, 800, 80, 55.0, 7600.0), seen["mel"]
+        return mel_ref.mel_basis()
+
+    lib = types.ModuleType("librosa")
+    lib.stft = fake_stft
+    lib.filters = types.ModuleType("librosa.filters")
+    lib.filters.mel = fake_mel
+    sys.modules["librosa"], sys.modules["librosa.filters"] = lib, lib.filters
+    pk = types.ModuleType("refw2l")
+    pk.__path__ = [os.path.join(REF, "avatars/wav2lip")]
+    sys.modules["refw2l"] = pk
+    import importlib as il
+    audio = il.import_module("refw2l.audio")                           # the reference file (relative import of .hparams works)
+    rng = np.random.default_rng(77)
+    t = np.arange(16640) / 16000.0
+    # loud tone (upper clip), quiet noise, an impulse, then digital silence (lower clip at -4)
+    pcm = (0.95 * np.sin(2 * np.pi * 1000 * t) * (t < 0.3) + 0.01 * rng.standard_normal(t.size) * ((t >= 0.3) & (t < 0.7)) +
+           0.9 * (np.abs(t - 0.8) < 0.001)).astype(np.float32)
+    mel = np.asarray(audio.melspectrogram(pcm), np.float64)
+    assert mel.shape == (80, 84) and "stft" in seen and "mel" in seen
+    np.savez_compressed(os.path.join(HERE, "mel_chain_golden.npz"), pcm=pcm, mel=mel)
+    print("mel chain golden ok", mel.shape, float(mel.min()), float(mel.max()), float((mel == -4).mean()))
+
+
 def make_lipreal():
     """a4 + a5 + a6 as ONE piece of reference code: LipReal.inference_batch and LipReal.paste_back_frame
     (avatars/wav2lip_avatar.py:116-147) executed from the reference's own module (imported by path; `av`, MelASR,
@@ -315,3 +356,4 @@ if __name__ == "__main__":
     make_vae_glue()
     make_lipreal()
     make_mel_windows()
+    make_mel_chain()
