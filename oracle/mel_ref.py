@@ -13,8 +13,11 @@ float64 numpy restatement of
 librosa (third-party, unpinned in requirements.txt:44, NOT installed here) provides
 ``stft`` and ``filters.mel``; their published algorithms are restated below
 (centre-padded periodic-Hann STFT; Slaney mel scale with Slaney area normalisation).
-**parity unpinned** against a real librosa; cross-checked in tests against
-``torch.stft`` and ``torchaudio.functional.melscale_fbanks``.  The frames touched by
+**parity unpinned** against a real librosa for these two functions; cross-checked in tests
+against ``torch.stft`` and ``torchaudio.functional.melscale_fbanks``.  Everything around them
+(pre-emphasis, dB, normalisation, clipping, the call arguments, the window slicing) is pinned to the
+reference's own audio.py / hparams.py / MelASR.run_step executed in the build container
+(tests/golden/mel_chain_golden.npz, mel_window_golden.npz).  The frames touched by
 the centre padding (0,1,T-2,T-1) are never selected by the window slicing, so librosa's
 ``pad_mode`` default (constant vs reflect across versions) does not reach the output.
 """
