@@ -283,6 +283,74 @@ def make_mel_chain():
     print("mel chain golden ok", mel.shape, float(mel.min()), float(mel.max()), float((mel == -4).mean()))
 
 
+def make_musereal():
+    """What the reference's OWN MuseReal.inference_batch (avatars/musetalk_avatar.py:130-152) feeds the UNet and how it
+    returns the result: module imported by path (heavy imports stubbed, real utils.image / PositionalEncoding), instance
+    built without __init__, UNet and VAE replaced by recorders.  Pins the latent gather order (mirror_index), the dtype
+    / order of the positional encoding and the timestep argument that the oracle and the engine reproduce."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import stubs
+    stubs.install()
+    sys.path.insert(0, REF)
+    sys.modules["avatars"].__path__ = [os.path.join(REF, "avatars")]
+    spec = importlib.util.spec_from_file_location("utils.image", os.path.join(REF, "utils/image.py"))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules["utils.image"] = m
+    spec.loader.exec_module(m)
+    dev = types.ModuleType("utils.device")
+    dev.initialize_device = lambda: "cpu"
+    sys.modules["utils.device"] = dev
+    av = types.ModuleType("av")
+    av.AudioFrame = av.VideoFrame = object
+    sys.modules["av"] = av
+    for name, attrs in (("avatars.musetalk.utils", ()), ("avatars.musetalk.utils.utils", ("get_file_type", "get_video_fps", "datagen", "load_all_model")),
+                        ("avatars.musetalk.whisper", ()), ("avatars.musetalk.whisper.audio2feature", ("Audio2Feature",)),
+                        ("avatars.audio_features", ()), ("avatars.audio_features.whisper", ("WhisperASR",))):
+        mod = types.ModuleType(name)
+        mod.__path__ = []
+        for a in attrs:
+            setattr(mod, a, object)
+        sys.modules[name] = mod
+    fake = types.ModuleType("diffusers")
+    fake.UNet2DConditionModel = fake.AutoencoderKL = object
+    sys.modules["diffusers"] = fake
+    spec = importlib.util.spec_from_file_location("ref_mt_unet2", os.path.join(REF, "avatars/musetalk/models/unet.py"))
+    unet_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(unet_mod)
+    spec = importlib.util.spec_from_file_location("ref_musetalk_avatar", os.path.join(REF, "avatars/musetalk_avatar.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+
+    seen = {}
+
+    class FakeModel:
+        dtype = torch.float32
+
+        def __call__(self, latents, timesteps, encoder_hidden_states=None):
+            seen["latents"], seen["timesteps"], seen["ctx"] = latents.clone(), timesteps, encoder_hidden_states.clone()
+            return types.SimpleNamespace(sample=latents[:, :4] * 2.0 + 1.0)
+
+    class FakeVae:
+        def decode_latents(self, z):
+            seen["decoded_from"] = z.clone()
+            return z.numpy()
+
+    B, n = 5, 3
+    g = torch.Generator().manual_seed(41)
+    lat_list = [torch.randn(1, 8, 4, 4, generator=g) for _ in range(n)]
+    aud = [torch.randn(50, 384, generator=g).numpy() for _ in range(B)]
+    mr = object.__new__(ref.MuseReal)
+    mr.input_latent_list_cycle, mr.batch_size = lat_list, B
+    mr.unet = types.SimpleNamespace(device="cpu", model=FakeModel())
+    mr.vae, mr.pe, mr.timesteps = FakeVae(), unet_mod.PositionalEncoding(d_model=384), torch.tensor([0])
+    index = 4
+    out = mr.inference_batch(index, aud)
+    np.savez_compressed(os.path.join(HERE, "musereal_golden.npz"), seed=np.int64(41), index=np.int64(index), batch=np.int64(B), n=np.int64(n),
+                        latents=seen["latents"].numpy(), ctx_sub=seen["ctx"].numpy()[:, ::7, ::11], timesteps=seen["timesteps"].numpy(),
+                        out=np.asarray(out))
+    print("musereal golden ok", tuple(seen["latents"].shape), tuple(seen["ctx"].shape), seen["timesteps"])
+
+
 def make_lipreal():
     """a4 + a5 + a6 as ONE piece of reference code: LipReal.inference_batch and LipReal.paste_back_frame
     (avatars/wav2lip_avatar.py:116-147) executed from the reference's own module (imported by path; `av`, MelASR,
@@ -357,3 +425,4 @@ if __name__ == "__main__":
     make_lipreal()
     make_mel_windows()
     make_mel_chain()
+    make_musereal()
