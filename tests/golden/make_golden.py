@@ -11,6 +11,13 @@
                      INDEPENDENT torch pipeline (torch.stft + torchaudio Slaney filterbank + scipy.lfilter) following
                      avatars/wav2lip/audio.py:45-51; it pins oracle/mel_ref.py against a second implementation
                      ("parity unpinned" w.r.t. librosa itself, see oracle/__init__.py).
+* mel_chain_golden.npz / mel_window_golden.npz — the reference's OWN audio.py + hparams.py and MelASR.run_step executed
+                     here (only librosa.stft / filters.mel substituted): everything around the two librosa calls.
+* slice_golden.npz — Whisper window indices from the reference's own BaseASR._get_sliced_feature.
+* lipreal_golden.npz — LipReal.inference_batch + paste_back_frame run from the reference module (a4 + a5 + a6 glue).
+* pe_golden.npz, vae_glue_golden.npz, musereal_golden.npz — the reference's PositionalEncoding, VAE.preprocess_img /
+                     decode_latents and MuseReal.inference_batch (third-party networks replaced by recorders / fakes).
+Every generator is deterministic: re-running this script reproduces the committed files byte for byte.
 """
 import importlib.util
 import os
