@@ -95,3 +95,84 @@ def test_mel_asr_run_step_bookkeeping_with_fake_session():
     assert len(asr.frames) == 20 and np.array_equal(asr.frames[0], chunks[4])
     with pytest.raises(RuntimeError):
         MelASR(opt, None, None)                          # no engine session -> loud failure, never a CPU fallback
+
+
+def test_whisper_asr_run_step_bookkeeping_matches_reference():
+    """WhisperASR.run_step (whisper.py:58-76): 2B chunks forwarded, the whole l+r+2B context handed to the feature extractor,
+    one list of B (50, 384) arrays queued, l+r chunks kept.  In the build container the reference's own class runs the same
+    event sequence (its Audio2Feature replaced by a recorder) and every queue / buffer must match."""
+    from livetalking_b200.plugin.whisper_asr import WhisperASR
+
+    class FakeFeatures:                                   # stands in for livetalking_b200.whisper.WhisperFeatures
+        def __init__(self, B):
+            self.B, self.calls = B, []
+
+        def run(self, pcm):
+            self.calls.append(pcm.copy())
+            return np.zeros((self.B, 50, 384), np.float16)
+
+    B = 3
+    opt = stubs.Opt(batch_size=B)
+    fake = FakeFeatures(B)
+    ours = WhisperASR(opt, None, fake)
+    rng = np.random.default_rng(2)
+    chunks = _feed(ours, 20 + 2 * B + 2, rng)
+    ours.warm_up()
+    ours.run_step()
+    assert ours.feat_queue.qsize() == 1 and ours.output_queue.qsize() == 10 + 2 * B
+    feats = ours.feat_queue.get()
+    assert len(feats) == B and feats[0].shape == (50, 384)
+    assert fake.calls[0].dtype == np.float32 and np.array_equal(fake.calls[0], np.concatenate(chunks[:20 + 2 * B]))
+    assert len(ours.frames) == 20 and np.array_equal(ours.frames[0], chunks[2 * B])
+    with pytest.raises(RuntimeError):
+        WhisperASR(opt, None, None)                       # no engine object -> loud failure, never a CPU fallback
+
+    ref_path = "/root/reference/avatars/audio_features/whisper.py"
+    if not os.path.exists(ref_path):
+        return
+    import types
+    a2f = types.ModuleType("avatars.musetalk.whisper.audio2feature")
+    a2f.Audio2Feature = object
+    for name in ("avatars.musetalk", "avatars.musetalk.whisper"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["avatars.musetalk.whisper.audio2feature"] = a2f
+    spec = importlib.util.spec_from_file_location("ref_base_asr2", "/root/reference/avatars/audio_features/base_asr.py")
+    ref_base = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_base)
+    af = types.ModuleType("avatars.audio_features")
+    af.__path__ = []
+    sys.modules["avatars.audio_features"] = af
+    sys.modules["avatars.audio_features.base_asr"] = ref_base
+    spec = importlib.util.spec_from_file_location("ref_whisper_asr", ref_path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+
+    class Recorder:                                        # the reference's audio_processor: (T, 5, 384) hidden-state stack
+        def __init__(self):
+            self.calls = []
+
+        def audio2feat(self, pcm):
+            self.calls.append(np.asarray(pcm).copy())
+            return np.zeros((1500, 5, 384), np.float32)
+
+    rec = Recorder()
+    theirs = ref.WhisperASR(opt, None, rec)
+    _feed(theirs, 20 + 2 * B + 2, np.random.default_rng(2))
+    theirs.warm_up()
+    theirs.run_step()
+    fake2 = FakeFeatures(B)
+    again = WhisperASR(opt, None, fake2)
+    _feed(again, 20 + 2 * B + 2, np.random.default_rng(2))
+    again.warm_up()
+    again.run_step()
+    assert theirs.feat_queue.qsize() == again.feat_queue.qsize() == 1
+    assert theirs.output_queue.qsize() == again.output_queue.qsize()
+    tf, of = theirs.feat_queue.get(), again.feat_queue.get()
+    assert len(tf) == len(of) == B and tf[0].shape == of[0].shape == (50, 384)
+    assert np.array_equal(rec.calls[0], fake2.calls[0])                                # identical PCM context handed over
+    assert len(theirs.frames) == len(again.frames) and all(np.array_equal(x, y) for x, y in zip(theirs.frames, again.frames))
+    for _ in range(theirs.output_queue.qsize()):
+        a, b = theirs.output_queue.get(), again.output_queue.get()
+        assert a.type == b.type and np.array_equal(a.data, b.data)
+    for k in ("avatars.audio_features", "avatars.audio_features.base_asr", "avatars.musetalk.whisper.audio2feature"):
+        sys.modules.pop(k, None)
