@@ -213,7 +213,7 @@ def run_ours(args):
 
     # ---- value: everything resident (PCM window uploaded once, faces/frames resident), device-timed
     for s_ in [sess] + extra:
-        s_.mel_step(step_pcm(audio, 0), want_output=False)
+        s_.set_pcm(step_pcm(audio, 0))
         s_.sync()
     idx = 0
     for _ in range(args.warmup):
@@ -251,7 +251,7 @@ def run_ours(args):
     multi = None
     if args.sessions == 1 and not args.no_multi:
         s2 = engine.W2LSession(model, av, BATCH, SL, SR, FPS)
-        s2.mel_step(step_pcm(audio, 0), want_output=False)
+        s2.set_pcm(step_pcm(audio, 0))
         st2 = torch.cuda.ExternalStream(s2.cuda_stream)
         for k in range(args.warmup):
             sess.step_async(k * BATCH)

@@ -47,8 +47,8 @@ def main():
     wenc = WhisperEncoder(ctx, synth.random_whisper_state_dict())
     frames, masks, coords, crops, latents = synth.synthetic_musetalk_avatar(n=16)
     av = MuseTalkAvatar(ctx, frames, masks, coords, crops, latents)
-    sess = MuseTalkSession(net, av, B)
-    wf = WhisperFeatures(wenc, B, out=sess.audio_in, out_rows=64)          # features land directly in the UNet's audio buffer
+    sess = MuseTalkSession(net, av, B, ctx=ctx)      # one stream for the whole timed chain (device-resident benchmark)
+    wf = WhisperFeatures(wenc, B, out=sess.audio_in, out_rows=64, ctx=ctx)          # features land directly in the UNet's audio buffer
     load_s = time.time() - t0
     # encoder graph (config 3): B crops -> latents
     crops_u8 = ctx.upload(np.random.default_rng(0).integers(0, 256, (B, 256, 256, 3), dtype=np.uint8))

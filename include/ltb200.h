@@ -6,8 +6,14 @@
  *   - plain C types, host pointers unless a name ends in _dev; the library owns all device memory;
  *   - every function returns 0 on success, non-zero on failure; ltb_last_error() returns the message
  *     (thread-local).  Nothing aborts the process; the Python shim raises RuntimeError.
- *   - handles are opaque pointers; a session is bound to one CUDA device and one stream and may be driven
- *     by one thread at a time (different sessions may be driven concurrently; ctypes releases the GIL).
+ *   - handles are opaque pointers; a session is bound to one CUDA device (every entry point restores it in the calling
+ *     thread).  Threading: the reference drives ONE session from three threads (avatars/base_avatar.py:469-501: render ->
+ *     asr.run_step, inference -> inference_batch, process_frames -> paste_back_frame) and several sessions concurrently
+ *     (ctypes releases the GIL).  Every ltb_w2l_* entry point that takes a session is therefore serialised by a
+ *     per-session mutex held from its first enqueue to its synchronise; ltb_w2l_mel_step uses its own stream, device
+ *     buffers and mutex and runs concurrently with the others.  An ltb_ctx (MuseTalk op layer) is NOT internally
+ *     serialised across multi-call sequences: one ctx per session and thread role, as livetalking_b200.musetalk does
+ *     (its allocation list is guarded).  Models and avatars are immutable after creation and shared freely.
  */
 #ifndef LTB200_H_
 #define LTB200_H_
@@ -61,12 +67,16 @@ int ltb_w2l_session_destroy(ltb_w2l_session* s);
 
 /* replaces audio.melspectrogram + the window slicing of MelASR.run_step
  * (avatars/audio_features/mel.py:46-63, avatars/wav2lip/audio.py:45-51).
- * pcm: (stride_left+stride_right+2*batch)*320 float32 samples.  The B windows stay on the device as the next
- * infer's audio input; if out_mel != NULL they are also copied back as float32 [batch,80,16]. */
+ * pcm: (stride_left+stride_right+2*batch)*320 float32 samples; out_mel: float32 [batch,80,16] host buffer (or NULL).
+ * Runs on the session's feature-extractor stream with its own device buffers: it may be called from the render thread
+ * while another thread is inside ltb_w2l_infer / ltb_w2l_paste* (avatars/base_avatar.py:483-489 vs :366) and never
+ * touches the forward pass's audio input.  Synchronous. */
 int ltb_w2l_mel_step(ltb_w2l_session* s, const float* pcm, int nsamples, float* out_mel);
+/* upload the PCM window that the device-resident step (ltb_w2l_mel_resident / ltb_w2l_step_async) reads.  Synchronous. */
+int ltb_w2l_set_pcm(ltb_w2l_session* s, const float* pcm, int nsamples);
 
 /* replaces LipReal.inference_batch(index, audiofeat_batch), avatars/wav2lip_avatar.py:116-139.
- * mel: float32 [batch,80,16] host windows (NULL = use the windows left on the device by ltb_w2l_mel_step).
+ * mel: float32 [batch,80,16] host windows (NULL = use the windows ltb_w2l_mel_resident left on the device).
  * pred_out: float32 [batch,256,256,3] BGR in [0,255] (the reference's return value) or NULL to leave the
  * predictions on the device for ltb_w2l_paste*.  Synchronous. */
 int ltb_w2l_infer(ltb_w2l_session* s, int index, const float* mel, float* pred_out);
@@ -81,7 +91,7 @@ int ltb_w2l_paste_pred(ltb_w2l_session* s, const float* pred, int idx, uint8_t* 
  * out_frames: uint8 [batch,H,W,3] host buffer (pinned recommended) or NULL to keep them on the device. */
 int ltb_w2l_paste_batch(ltb_w2l_session* s, int index, uint8_t* out_frames);
 
-/* mel windows from the PCM buffer already resident on the device (uploaded by the last ltb_w2l_mel_step):
+/* mel windows from the PCM buffer already resident on the device (uploaded by ltb_w2l_set_pcm):
  * the device-resident form of MelASR.run_step's feature extraction.  Asynchronous. */
 int ltb_w2l_mel_resident(ltb_w2l_session* s);
 /* whole step with everything resident in HBM: mel (resident PCM) + forward + batched paste-back, enqueued on the
@@ -211,6 +221,7 @@ int ltb_op_whisper_slice(ltb_ctx* c, const void* const* hidden5, int T, int D, i
 typedef struct ltb_mt_paste_op {
   const void* frames; const void* coords; const void* crop; const void* masks; const void* mask_off; const void* pred; void* out;
   int nf, H, W, index, explicit_idx, slot0, count;
+  int pred_hw;   /* side of the square prediction: 256 (the reference, vae.py:15) or 512 (64x64 latents); 0 = 256 */
 } ltb_mt_paste_op;
 int ltb_op_mt_paste(ltb_ctx* c, const ltb_mt_paste_op* d);
 

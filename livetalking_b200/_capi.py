@@ -29,7 +29,7 @@ class ConvOp(C.Structure):
 
 class MtPasteOp(C.Structure):
     _fields_ = ([(n, C.c_void_p) for n in ("frames", "coords", "crop", "masks", "mask_off", "pred", "out")] +
-                [(n, C.c_int) for n in ("nf", "H", "W", "index", "explicit_idx", "slot0", "count")])
+                [(n, C.c_int) for n in ("nf", "H", "W", "index", "explicit_idx", "slot0", "count", "pred_hw")])
 
 
 class ConvDesc(C.Structure):
@@ -53,6 +53,7 @@ _SIGS = {
                                          C.POINTER(C.c_void_p)]),
     "ltb_w2l_session_destroy": (C.c_int, [C.c_void_p]),
     "ltb_w2l_mel_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ltb_w2l_set_pcm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "ltb_w2l_infer": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ltb_w2l_paste": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ltb_w2l_paste_pred": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

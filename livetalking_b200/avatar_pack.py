@@ -175,6 +175,7 @@ class PackedAvatar:
         if self.kind not in (KIND_WAV2LIP, KIND_MUSETALK) or nsec > (ALIGN - _HEAD.size) // _ENTRY.size:
             raise AvatarPackError(f"{path}: bad header")
         self.sections: Dict[str, np.ndarray] = {}
+        self._where: Dict[str, tuple] = {}
         for i in range(nsec):
             name, dcode, ndim, s0, s1, s2, s3, off, nbytes, crc = _ENTRY.unpack_from(head, _HEAD.size + i * _ENTRY.size)
             name = name.rstrip(b"\0").decode()
@@ -188,6 +189,7 @@ class PackedAvatar:
             if verify and zlib.crc32(arr.tobytes()) != crc:
                 raise AvatarPackError(f"{path}: section {name}: checksum mismatch")
             self.sections[name] = arr
+            self._where[name] = (dt, off, shape, nbytes)
         need = ("frames", "faces", "coords") if self.kind == KIND_WAV2LIP else \
             ("frames", "coords", "mask_coords", "masks", "mask_off", "mask_shape", "latents")
         missing = [k for k in need if k not in self.sections]
@@ -196,12 +198,22 @@ class PackedAvatar:
         if self.sections["frames"].shape != (self.n, self.H, self.W, 3):
             raise AvatarPackError(f"{path}: frames section does not match the header")
 
+    def host_frames(self) -> list:
+        """The ``frame_list_cycle`` the host keeps: WRITABLE per-frame arrays.  On silent frames the reference hands
+        ``frame_list_cycle[idx]`` itself to ``cv2.putText`` (avatars/base_avatar.py:417, 449), and OpenCV rejects read-only
+        arrays — so the list is a copy-on-write mapping (``mode='c'``: pages are private once written, the file is never
+        modified, untouched pages stay shared with the page cache).  The read-only mapping in ``sections`` feeds the upload."""
+        dt, off, shape, nbytes = self._where["frames"]
+        if not nbytes:
+            return []
+        return list(np.memmap(self.path, dtype=dt, mode="c", offset=off, shape=shape))
+
     # the tuples the reference's load_avatar returns (lists of per-frame arrays; views, no copies)
     def wav2lip_lists(self) -> Tuple[list, list, list]:
         if self.kind != KIND_WAV2LIP:
             raise AvatarPackError("not a wav2lip avatar pack")
         s = self.sections
-        return list(s["frames"]), list(s["faces"]), [tuple(int(v) for v in c) for c in s["coords"]]
+        return self.host_frames(), list(s["faces"]), [tuple(int(v) for v in c) for c in s["coords"]]
 
     def musetalk_lists(self):
         if self.kind != KIND_MUSETALK:
@@ -210,7 +222,7 @@ class PackedAvatar:
         off, shp = s["mask_off"], s["mask_shape"]
         masks = [s["masks"][off[i]:off[i + 1]].reshape(tuple(int(v) for v in shp[i])) for i in range(self.n)]
         latents = [s["latents"][i:i + 1] for i in range(self.n)]
-        return (list(s["frames"]), masks, [tuple(int(v) for v in c) for c in s["coords"]],
+        return (self.host_frames(), masks, [tuple(int(v) for v in c) for c in s["coords"]],
                 [tuple(int(v) for v in c) for c in s["mask_coords"]], latents)
 
 

@@ -176,15 +176,20 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
       constexpr uint32_t kADescHi = ((C::P * 128) >> 4) | (1u << 14) | (2u << 29);    // SBO = halo pitch (1280 B) / 1024 B in GEMM mode
       constexpr uint32_t kBDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);            // SBO = 1024 B
       uint32_t ai = 0, bi = 0, it = 0;
-      // per-tap constants in registers (all loops over taps below are fully unrolled): halo row offset in 16-byte units,
-      // accumulator column offset, and "accumulate" flag of the tap's first K step in the first chunk
-      constexpr int NT = C::TG * C::TG;
-      uint32_t tap_aoff[NT], tap_doff[NT], tap_acc0[NT];
+      // ConvT (NACC == 4): per-stage "fat" MMA list in registers (see HaloParams::fat): one instruction feeds every
+      // sub-pixel accumulator that reads the same halo view, N = 64..256 instead of nine N = BN instructions
+      uint32_t fat_n[3], fat_aoff[3][3], fat_doff[3][3], fat_boff[3][3], fat_idesc[3][3], fat_acc0[3][3];
 #pragma unroll
-      for (int i = 0; i < NT; ++i) {
-        tap_aoff[i] = (uint32_t)p.tap_row[i] * 8u;
-        tap_doff[i] = (uint32_t)p.tap_acc[i] * (NSUB * BN);
-        tap_acc0[i] = p.tap_first[i] ? 0u : 1u;
+      for (int j = 0; j < 3; ++j) {
+        fat_n[j] = (NACC == 4) ? (uint32_t)p.fat_n[j] : 0u;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          fat_aoff[j][q] = (uint32_t)p.fat[j][q].view * 8u;
+          fat_doff[j][q] = (uint32_t)p.fat[j][q].dcol;
+          fat_boff[j][q] = (uint32_t)p.fat[j][q].brow * 8u;
+          fat_idesc[j][q] = umma_idesc_f16(128, 8) + ((uint32_t)(p.fat[j][q].n >> 3) - 1u) * (1u << 17);
+          fat_acc0[j][q] = p.fat[j][q].first ? 0u : 1u;
+        }
       }
       if (RC) mbar_wait(smem_u32(&b_full[0]), 0);
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
@@ -208,31 +213,42 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
             tc_fence_after();
             // descriptor words: hi = {SBO, version 1, SWIZZLE_128B} is loop invariant; lo = (addr >> 4) | LBO(1) << 16
             const uint32_t b_lo0 = (((b_smem + bs * C::B_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+            if constexpr (NACC == 1) {
 #pragma unroll
-            for (int tt = 0; tt < C::TG; ++tt) {
-              uint32_t acc0, aoff, doff;
-              if (NACC == 1) {
-                aoff = (TAPS == 9) ? (uint32_t)(j * C::P + tt) * 8u : 0u;
-                doff = 0u;
-                acc0 = later | ((j | tt) ? 1u : 0u);
-              } else {
-                const int tap = j * C::TG + tt;
-                aoff = tap_aoff[tap];
-                doff = tap_doff[tap];
-                acc0 = later | tap_acc0[tap];
-              }
+              for (int tt = 0; tt < C::TG; ++tt) {
+                const uint32_t aoff = (TAPS == 9) ? (uint32_t)(j * C::P + tt) * 8u : 0u;
+                const uint32_t acc0 = later | ((j | tt) ? 1u : 0u);
 #pragma unroll
-              for (int sub = 0; sub < NSUB; ++sub) {
-                const uint32_t d = dbase + doff + sub * BN;
-                const uint32_t a_lo = a_lo0 + aoff + sub * (16 * C::P * 8);
-                const uint32_t b_lo = b_lo0 + tt * (BN * 8);
-                if (LTB_DIAG(4)) continue;
-                if (ksteps == 4) {   // warp-uniform; straight-line issue of the four K steps
-                  umma_f16_lohi_x4_if(leader, d, a_lo, kADescHi, b_lo, kBDescHi, idesc, acc0);
-                } else {             // ragged last chunk: only the K steps that carry channels
+                for (int sub = 0; sub < NSUB; ++sub) {
+                  const uint32_t d = dbase + sub * BN;
+                  const uint32_t a_lo = a_lo0 + aoff + sub * (16 * C::P * 8);
+                  const uint32_t b_lo = b_lo0 + tt * (BN * 8);
+                  if (LTB_DIAG(4)) continue;
+                  if (ksteps == 4) {   // warp-uniform; straight-line issue of the four K steps
+                    umma_f16_lohi_x4_if(leader, d, a_lo, kADescHi, b_lo, kBDescHi, idesc, acc0);
+                  } else {             // ragged last chunk: only the K steps that carry channels
 #pragma unroll 1
-                  for (int k = 0; k < ksteps; ++k)
-                    umma_f16_lohi_if(leader, d, a_lo + k * 2, kADescHi, b_lo + k * 2, kBDescHi, idesc, k ? 1u : acc0);
+                    for (int k = 0; k < ksteps; ++k)
+                      umma_f16_lohi_if(leader, d, a_lo + k * 2, kADescHi, b_lo + k * 2, kBDescHi, idesc, k ? 1u : acc0);
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 3; ++q) {
+                if (q < (int)fat_n[j]) {   // warp-uniform
+                  const uint32_t d = dbase + fat_doff[j][q];
+                  const uint32_t a_lo = a_lo0 + fat_aoff[j][q];
+                  const uint32_t b_lo = b_lo0 + fat_boff[j][q];
+                  const uint32_t acc0 = later | fat_acc0[j][q];
+                  if (LTB_DIAG(4)) continue;
+                  if (ksteps == 4) {
+                    umma_f16_lohi_x4_if(leader, d, a_lo, kADescHi, b_lo, kBDescHi, fat_idesc[j][q], acc0);
+                  } else {
+#pragma unroll 1
+                    for (int k = 0; k < ksteps; ++k)
+                      umma_f16_lohi_if(leader, d, a_lo + k * 2, kADescHi, b_lo + k * 2, kBDescHi, fat_idesc[j][q], k ? 1u : acc0);
+                  }
                 }
               }
             }
@@ -556,13 +572,30 @@ static bool pick_cfg(const ConvParams& p, int* BN, int* NSUB, int* NACC) {
     if (p.Cout % 128 == 0 && t64 > 148 && p.Cin >= 512) *BN = 128;
     return true;
   }
-  *NSUB = (p.GH % 32 == 0) ? 2 : 1;
-  *BN = (p.Cout % 128 == 0) ? 128 : (p.Cout % 64 == 0) ? 64 : 32;
-  // small problems: prefer more tiles over wider tiles so the persistent grid fills the 148 SMs
-  auto tiles = [&](int bn, int nsub) { return (long)p.N * ((p.GH + 16 * nsub - 1) / (16 * nsub)) * ((p.GW + 7) / 8) * (p.Cout / bn); };
-  if (*NSUB == 2 && tiles(*BN, 2) < 148) *NSUB = 1;
-  while (*BN > 32 && tiles(*BN, *NSUB) < 120) *BN >>= 1;
-  return true;
+  // 3x3 conv: pick the (BN, NSUB) with the lowest modelled MMA time.  One M=128,K=16 tcgen05.mma costs ~55 + 0.2*N cycles
+  // (the 4 KB A fetch dominates at small N), a tile issues ksteps*9*NSUB of them, the persistent grid walks
+  // ceil(tiles/148) waves; ~800 cycles per tile for pipeline fill / accumulator hand-off.  (384 channels @32x32, batch 16:
+  // BN=128,NSUB=2 is 192 tiles = 2 waves of 35k cycles; NSUB=1 is 384 tiles = 3 waves of 17.5k.)
+  const long ksteps = (p.Cin + 15) / 16;
+  double best = 1e30;
+  for (int bn : {128, 64, 32}) {
+    if (p.Cout % bn) continue;
+    for (int nsub : {2, 1}) {
+      if (nsub == 2 && (p.GH % 32) != 0) continue;
+      const long tiles = (long)p.N * ((p.GH + 16 * nsub - 1) / (16 * nsub)) * ((p.GW + 7) / 8) * (p.Cout / bn);
+      const long waves = (tiles + 147) / 148;
+      const double tile = (double)ksteps * 9 * nsub * (55.0 + 0.2 * bn) + 800.0;
+      // single-wave launches cannot overlap their epilogue with the next tile's MMAs
+      const double epi = (waves == 1) ? 40.0 * nsub * bn : 0.0;
+      const double cost = waves * tile + epi;
+      if (cost < best * 0.9) {   // prefer the earlier (wider) candidate unless the model predicts a clear (>10 %) win
+        best = cost;
+        *BN = bn;
+        *NSUB = nsub;
+      }
+    }
+  }
+  return best < 1e30;
 }
 
 int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan* out) {
@@ -631,21 +664,36 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
   h.relu = p.relu;
   h.halo_y0 = tr ? 0 : -1;
   h.halo_x0 = tr ? 0 : -1;
-  int t = 0;
-  for (int ph = 0; ph < p.nphases; ++ph) {
-    h.acc_oy[ph] = p.ph[ph].ooy;
-    h.acc_ox[ph] = p.ph[ph].oox;
-    for (int i = 0; i < p.ph[ph].ntaps; ++i, ++t) {
-      const int dy = p.ph[ph].dy[i] - h.halo_y0, dx = p.ph[ph].dx[i] - h.halo_x0;  // position inside the halo
-      h.tap_row[t] = dy * kHaloP + dx;
-      h.tap_acc[t] = ph;
-      h.tap_first[t] = (i == 0) ? 1 : 0;
+  if (tr) {
+    // accumulator slots p0, p1, p3, p2 (phase index = oy*2 + ox): slots that share a halo view are adjacent
+    const int slot_phase[4] = {0, 1, 3, 2};
+    for (int sl = 0; sl < 4; ++sl) {
+      h.acc_oy[sl] = p.ph[slot_phase[sl]].ooy;
+      h.acc_ox[sl] = p.ph[slot_phase[sl]].oox;
     }
+    struct G { int stage, view, slot0, brow, nslots, first; };
+    const G groups[5] = {{0, 0, 0, 0, 3, 1}, {1, 1, 1, 0, 2, 0}, {1, kHaloP + 1, 2, 2, 1, 0}, {2, 0, 3, 2, 1, 1}, {2, kHaloP, 2, 0, 2, 0}};
+    for (const G& g : groups) {
+      int done = 0;
+      while (done < g.nslots) {   // split so that N <= 256
+        int take = g.nslots - done;
+        while (take * BN > 256) --take;
+        HaloParams::FatMma& f = h.fat[g.stage][h.fat_n[g.stage]++];
+        f.view = g.view;
+        f.dcol = (g.slot0 + done) * BN;
+        f.brow = (g.brow + done) * BN;
+        f.n = take * BN;
+        f.first = g.first;
+        done += take;
+      }
+    }
+  } else {
+    h.acc_oy[0] = p.ph[0].ooy;
+    h.acc_ox[0] = p.ph[0].oox;
   }
   h.tiles_n = p.Cout / BN;
   if (gemm) {
     h.halo_y0 = h.halo_x0 = 0;
-    h.tap_row[0] = 0;
     h.tiles_x = (p.M + 128 * NSUB - 1) / (128 * NSUB);
     h.tiles_y = 1;
     h.total_tiles = h.tiles_x * h.tiles_n;
@@ -736,6 +784,25 @@ __global__ void w_tap_major_kernel(const __half* __restrict__ w, __half* __restr
 cudaError_t launch_w_tap_major(const __half* w, __half* wt, int cout, int cin, cudaStream_t st, int ntaps) {
   const size_t total = (size_t)cout * ntaps * cin;
   w_tap_major_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, wt, cout, cin, ntaps);
+  return cudaGetLastError();
+}
+
+// phase-major slice s (p0:(0,0) | p1:(0,0),(0,1) | p2:(0,0),(1,0) | p3:(0,0),(0,1),(1,0),(1,1)) -> view-major position
+__global__ void w_tap_major_convT_kernel(const __half* __restrict__ w, __half* __restrict__ wt, int cout, int cin) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)cout * 9 * cin;
+  if (i >= total) return;
+  const int ci = (int)(i % cin);
+  const int tap = (int)((i / cin) % 9);
+  const int co = (int)(i / ((size_t)cin * 9));
+  // new order: [v00p0, v00p1, v00p3 | v01p1, v01p3, v11p3 | v10p3, v10p2, v00p2] = old slices [0,1,5 | 2,6,8 | 7,4,3]
+  const int pos_of_old[9] = {0, 1, 3, 8, 7, 2, 4, 6, 5};
+  wt[((size_t)pos_of_old[tap] * cout + co) * cin + ci] = w[i];
+}
+
+cudaError_t launch_w_tap_major_convT(const __half* w, __half* wt, int cout, int cin, cudaStream_t st) {
+  const size_t total = (size_t)cout * 9 * cin;
+  w_tap_major_convT_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, wt, cout, cin);
   return cudaGetLastError();
 }
 

@@ -22,9 +22,20 @@ struct alignas(64) HaloParams {
   int GH, GW;            // tile-grid extent (= input H, W): tiles may overhang it, rows/columns beyond are masked
   int relu;
   int halo_y0, halo_x0;  // halo origin relative to the tile origin (-1 for pad-1 conv, 0 for ConvT phases)
-  int tap_row[9];        // halo row offset (dy*10 + dx) of each of the 9 K-slices
-  int tap_acc[9];        // accumulator (sub-pixel phase) the slice contributes to
-  int tap_first[9];      // 1 = first slice of its accumulator (overwrite instead of accumulate on the first K chunk)
+  // ConvT only ("fat-N" issue): the nine (sub-pixel phase, tap) weight slices are stored view-major
+  //   stage 0: v00->p0, v00->p1, v00->p3 | stage 1: v01->p1, v01->p3, v11->p3 | stage 2: v10->p3, v10->p2, v00->p2
+  // (vDYDX = halo view, accumulator slots ordered p0,p1,p3,p2), so that ONE tcgen05.mma per halo view feeds every phase that
+  // reads it: N = 3*BN / 2*BN / BN instead of nine N = BN instructions (an M=128 MMA costs ~55 + 0.2*N cycles: the 4 KB A
+  // fetch dominates at small N).  Up to 3 instructions per weight stage (N > 256 is split).
+  struct FatMma {
+    int view;   // halo row offset (dy*10 + dx) of the A view
+    int dcol;   // first accumulator column
+    int brow;   // first weight row inside the stage (rows of 128 B)
+    int n;      // MMA N (multiple of 16, <= 256)
+    int first;  // 1 = overwrite on the first K chunk (first instruction that touches these columns)
+  };
+  int fat_n[3];
+  FatMma fat[3][3];
   int acc_oy[4], acc_ox[4];
   int tiles_x, tiles_y, tiles_n, total_tiles;
   // optional fused GroupNorm statistics of the OUTPUT tensor (sum, sum of squares per (image, group)), accumulated by the
@@ -55,5 +66,8 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
 cudaError_t launch_conv_halo(const HaloPlan& pl, cudaStream_t st);
 bool conv_halo_gn_fusable(const HaloPlan& pl, int cout_total, int groups, int hw);
 cudaError_t launch_w_tap_major(const __half* w, __half* wt, int cout, int cin, cudaStream_t st, int ntaps = 9);
+// ConvT(k3,s2) weights: phase-major rows [Cout][9][Cin] (pack order of w2l_pack.py / pack_convT_w) -> the view-major slice
+// order the fat-N issue loop expects (see HaloParams::fat)
+cudaError_t launch_w_tap_major_convT(const __half* w, __half* wt, int cout, int cin, cudaStream_t st);
 
 }  // namespace ltb

@@ -33,19 +33,20 @@ __device__ __forceinline__ void cv_tap_m(int d, double scale, int src_len, bool 
   w1 = __float2int_rn(__fmul_rn(f, 2048.f));
 }
 
-// cv2.resize(pred_u8 256x256x3, (dw, dh)) sampled at (dy, dx), channel c
-__device__ __forceinline__ int resized_px(const uint8_t* __restrict__ pred, int dw, int dh, int dy, int dx, int c) {
-  if (dw == 256 && dh == 256) return pred[((size_t)dy * 256 + dx) * 3 + c];
-  if (dw == 128 && dh == 128) {
-    const uint8_t* p = pred + ((size_t)(2 * dy) * 256 + 2 * dx) * 3 + c;
-    return (p[0] + p[3] + p[768] + p[771] + 2) >> 2;
+// cv2.resize(pred_u8 SxSx3, (dw, dh)) sampled at (dy, dx), channel c   (S = 256, or 512 for BASELINE configs[4])
+__device__ __forceinline__ int resized_px(const uint8_t* __restrict__ pred, int S, int dw, int dh, int dy, int dx, int c) {
+  const size_t row = (size_t)S * 3;
+  if (dw == S && dh == S) return pred[(size_t)dy * row + dx * 3 + c];
+  if (2 * dw == S && 2 * dh == S) {   // exact 2x shrink: OpenCV's INTER_LINEAR takes the 2x2 area path
+    const uint8_t* p = pred + (size_t)(2 * dy) * row + 2 * dx * 3 + c;
+    return (p[0] + p[3] + p[row] + p[row + 3] + 2) >> 2;
   }
   int sy, b0, b1, sx, a0, a1;
-  cv_tap_m(dy, 1.0 / ((double)dh / 256.0), 256, false, sy, b0, b1);
-  cv_tap_m(dx, 1.0 / ((double)dw / 256.0), 256, true, sx, a0, a1);
-  const int sy0 = min(max(sy, 0), 255), sy1 = min(max(sy + 1, 0), 255), sx1 = min(sx + 1, 255);
-  const uint8_t* r0 = pred + (size_t)sy0 * 768;
-  const uint8_t* r1 = pred + (size_t)sy1 * 768;
+  cv_tap_m(dy, 1.0 / ((double)dh / (double)S), S, false, sy, b0, b1);
+  cv_tap_m(dx, 1.0 / ((double)dw / (double)S), S, true, sx, a0, a1);
+  const int sy0 = min(max(sy, 0), S - 1), sy1 = min(max(sy + 1, 0), S - 1), sx1 = min(sx + 1, S - 1);
+  const uint8_t* r0 = pred + (size_t)sy0 * row;
+  const uint8_t* r1 = pred + (size_t)sy1 * row;
   const int S0 = r0[sx * 3 + c] * a0 + r0[sx1 * 3 + c] * a1;
   const int S1 = r1[sx * 3 + c] * a0 + r1[sx1 * 3 + c] * a1;
   const int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
@@ -70,10 +71,10 @@ __global__ void __launch_bounds__(256) mt_paste_kernel(const MtPasteArgs a) {
     const float w2 = __fsub_rn(1.f, m);
     const float den = __fadd_rn(__fadd_rn(m, w2), 1e-5f);
     const bool in_face = (y >= y1 && y < y2 && x >= x1 && x < x2);
-    const uint8_t* pred = a.pred + (size_t)(a.slot0 + job) * 256 * 256 * 3;
+    const uint8_t* pred = a.pred + (size_t)(a.slot0 + job) * a.S * a.S * 3;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float fl = in_face ? (float)resized_px(pred, x2 - x1, y2 - y1, y - y1, x - x1, c) : (float)body[c];
+      const float fl = in_face ? (float)resized_px(pred, a.S, x2 - x1, y2 - y1, y - y1, x - x1, c) : (float)body[c];
       const float num = __fadd_rn(__fmul_rn(fl, m), __fmul_rn((float)body[c], w2));
       const int v = __float2int_rn(__fdiv_rn(num, den));
       px[c] = (uint8_t)min(max(v, 0), 255);

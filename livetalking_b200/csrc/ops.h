@@ -41,10 +41,11 @@ struct MtPasteArgs {
   const int* crop;           // [nf,4] = (x_s,y_s,x_e,y_e)       (myutil.py:7)
   const uint8_t* masks;      // concatenated 3-channel masks, frame i at mask_off[i], size (y_e-y_s) x (x_e-x_s) x 3
   const long long* mask_off;
-  const uint8_t* pred;       // [B,256,256,3] u8 BGR (VAE decode output)
+  const uint8_t* pred;       // [B,S,S,3] u8 BGR (VAE decode output)
   uint8_t* out;              // [count,H,W,3]
   int nf, H, W;
   int index, explicit_idx, slot0;
+  int S;                     // prediction side: 256 (reference), 512 for the 64x64-latent configuration
 };
 cudaError_t launch_mt_paste(const MtPasteArgs& a, int count, cudaStream_t st);
 

@@ -4,6 +4,7 @@
 // code out of these operators, captured ONCE into a CUDA graph and replayed per step.  Every op is asynchronous on the
 // context's stream; device memory is owned by the context.
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -17,6 +18,7 @@ using namespace ltb;
 struct ltb_ctx {
   int device = 0;
   cudaStream_t st = nullptr;
+  std::mutex mu;                // guards `allocs` (a model ctx is shared by every session thread that uploads / frees)
   std::vector<void*> allocs;
   float* zero_bias = nullptr;   // 16384 zeros (bias of bias-free GEMMs)
   float* gn_ws = nullptr;       // GroupNorm statistics workspace
@@ -30,6 +32,13 @@ struct ltb_graph {
   cudaGraphExec_t exec = nullptr;
   long long launches = 0;
 };
+
+// the calling thread may be a fresh render / inference / process thread whose current device is 0
+#define LTB_CTX_ENTER(c)                                                                          \
+  do {                                                                                            \
+    int _cur = -1;                                                                                \
+    if (cudaGetDevice(&_cur) != cudaSuccess || _cur != (c)->device) LTB_CUDA(cudaSetDevice((c)->device)); \
+  } while (0)
 
 static const int kZeroBias = 16384;
 static const int kGnWsFloats = 64 * 64 * 2;
@@ -57,6 +66,7 @@ int ltb_ctx_create(ltb_ctx** out) {
 
 int ltb_ctx_destroy(ltb_ctx* c) {
   if (!c) return 0;
+  cudaSetDevice(c->device);
   cudaStreamSynchronize(c->st);
   for (void* p : c->allocs) cudaFree(p);
   cudaFree(c->zero_bias);
@@ -69,53 +79,66 @@ int ltb_ctx_destroy(ltb_ctx* c) {
 
 int ltb_ctx_stream(ltb_ctx* c, void** stream) {
   if (!c || !stream) return LTB_FAIL("null argument");
+  LTB_CTX_ENTER(c);
   *stream = static_cast<void*>(c->st);
   return 0;
 }
 int ltb_ctx_sync(ltb_ctx* c) {
   if (!c) return LTB_FAIL("null ctx");
+  LTB_CTX_ENTER(c);
   LTB_CUDA(cudaStreamSynchronize(c->st));
   return 0;
 }
 int ltb_ctx_launch_count(ltb_ctx* c, long long* n) {
   if (!c || !n) return LTB_FAIL("null argument");
+  LTB_CTX_ENTER(c);
   *n = c->launches;
   return 0;
 }
 
 int ltb_dev_alloc(ltb_ctx* c, size_t bytes, int zero, void** dptr) {
   if (!c || !dptr) return LTB_FAIL("null argument");
+  LTB_CTX_ENTER(c);
   void* p = nullptr;
   LTB_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
   if (zero) LTB_CUDA(cudaMemset(p, 0, bytes ? bytes : 16));
-  c->allocs.push_back(p);
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->allocs.push_back(p);
+  }
   *dptr = p;
   return 0;
 }
 int ltb_dev_free(ltb_ctx* c, void* dptr) {
   if (!c || !dptr) return 0;
-  for (size_t i = 0; i < c->allocs.size(); ++i)
-    if (c->allocs[i] == dptr) {
-      cudaFree(dptr);
-      c->allocs.erase(c->allocs.begin() + i);
-      return 0;
-    }
-  return LTB_FAIL("dev_free: pointer not owned by this context");
+  LTB_CTX_ENTER(c);
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    size_t i = 0;
+    while (i < c->allocs.size() && c->allocs[i] != dptr) ++i;
+    if (i == c->allocs.size()) return LTB_FAIL("dev_free: pointer not owned by this context");
+    c->allocs.erase(c->allocs.begin() + i);
+  }
+  cudaFree(dptr);
+  return 0;
 }
 int ltb_h2d(ltb_ctx* c, void* dst_dev, const void* src_host, size_t bytes, int sync) {
   if (!c) return LTB_FAIL("null ctx");
+  LTB_CTX_ENTER(c);
   LTB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, c->st));
   if (sync) LTB_CUDA(cudaStreamSynchronize(c->st));
   return 0;
 }
 int ltb_d2h(ltb_ctx* c, void* dst_host, const void* src_dev, size_t bytes, int sync) {
   if (!c) return LTB_FAIL("null ctx");
+  LTB_CTX_ENTER(c);
   LTB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, c->st));
   if (sync) LTB_CUDA(cudaStreamSynchronize(c->st));
   return 0;
 }
 int ltb_set_i32(ltb_ctx* c, void* dptr, int value) {
   if (!c || !dptr) return LTB_FAIL("null argument");
+  LTB_CTX_ENTER(c);
   LTB_CUDA(launch_set_int(static_cast<int*>(dptr), value, c->st));
   c->launches += 1;
   return 0;
@@ -124,6 +147,7 @@ int ltb_set_i32(ltb_ctx* c, void* dptr, int value) {
 // ---- graph capture ------------------------------------------------------------------------------
 int ltb_capture_begin(ltb_ctx* c) {
   if (!c) return LTB_FAIL("null ctx");
+  LTB_CTX_ENTER(c);
   if (c->capturing) return LTB_FAIL("already capturing");
   LTB_CUDA(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
   c->capturing = true;
@@ -132,6 +156,7 @@ int ltb_capture_begin(ltb_ctx* c) {
 }
 int ltb_capture_end(ltb_ctx* c, ltb_graph** out) {
   if (!c || !out) return LTB_FAIL("null argument");
+  LTB_CTX_ENTER(c);
   if (!c->capturing) return LTB_FAIL("not capturing");
   c->capturing = false;
   auto* g = new ltb_graph();
@@ -149,6 +174,7 @@ int ltb_capture_end(ltb_ctx* c, ltb_graph** out) {
 }
 int ltb_graph_launch(ltb_ctx* c, ltb_graph* g) {
   if (!c || !g) return LTB_FAIL("null argument");
+  LTB_CTX_ENTER(c);
   LTB_CUDA(cudaGraphLaunch(g->exec, c->st));
   c->launches += g->launches;
   return 0;
@@ -164,6 +190,7 @@ int ltb_graph_destroy(ltb_graph* g) {
 // ---- ops ----------------------------------------------------------------------------------------
 int ltb_op_conv2d(ltb_ctx* c, const ltb_conv_op* d) {
   if (!c || !d || !d->in || !d->w || !d->out) return LTB_FAIL("conv2d: null argument");
+  LTB_CTX_ENTER(c);
   if (d->KH * d->KW > kMaxTaps) return LTB_FAIL("conv2d: kernel too large");
   pdl_set_enabled(pdl_default());   // the calling thread may have run a w2l profiling pass with PDL off
   if (d->Cout > kZeroBias && !d->bias) return LTB_FAIL("conv2d: Cout too large for the implicit zero bias");
@@ -245,6 +272,7 @@ int ltb_op_conv2d(ltb_ctx* c, const ltb_conv_op* d) {
 
 int ltb_op_w_tap_major(ltb_ctx* c, const void* w, void* wt, int cout, int cin) {
   if (!c || !w || !wt) return LTB_FAIL("null argument");
+  LTB_CTX_ENTER(c);
   LTB_CUDA(launch_w_tap_major(static_cast<const __half*>(w), static_cast<__half*>(wt), cout, cin, c->st));
   c->launches += 1;
   return 0;
@@ -253,6 +281,7 @@ int ltb_op_w_tap_major(ltb_ctx* c, const void* w, void* wt, int cout, int cin) {
 int ltb_op_groupnorm(ltb_ctx* c, const void* x, int N, int HW, int C, int Ctot, int c_off, int groups, float eps, const float* gamma,
                      const float* beta, int silu, void* out, int OCtot, int oc_off) {
   if (!c || !x || !out || !gamma || !beta) return LTB_FAIL("groupnorm: null argument");
+  LTB_CTX_ENTER(c);
   if ((size_t)N * groups * 2 > (size_t)kGnWsFloats) return LTB_FAIL("groupnorm: batch too large for the statistics workspace");
   cudaError_t e = launch_groupnorm(static_cast<const __half*>(x), N, HW, C, Ctot, c_off, groups, eps, gamma, beta, silu,
                                    static_cast<__half*>(out), OCtot, oc_off, c->gn_ws, c->st);
@@ -263,6 +292,7 @@ int ltb_op_groupnorm(ltb_ctx* c, const void* x, int N, int HW, int C, int Ctot, 
 int ltb_op_groupnorm_apply(ltb_ctx* c, const void* x, int N, int HW, int C, int Ctot, int c_off, int groups, float eps, const void* stats,
                            const float* gamma, const float* beta, int silu, void* out, int OCtot, int oc_off) {
   if (!c || !x || !out || !gamma || !beta || !stats) return LTB_FAIL("groupnorm_apply: null argument");
+  LTB_CTX_ENTER(c);
   cudaError_t e = launch_gn_apply(static_cast<const __half*>(x), N, HW, C, Ctot, c_off, groups, eps, static_cast<const float*>(stats), gamma,
                                   beta, silu, static_cast<__half*>(out), OCtot, oc_off, c->st);
   if (e != cudaSuccess) return LTB_FAIL(std::string("groupnorm_apply: ") + cudaGetErrorString(e));
@@ -271,6 +301,7 @@ int ltb_op_groupnorm_apply(ltb_ctx* c, const void* x, int N, int HW, int C, int 
 }
 int ltb_op_layernorm(ltb_ctx* c, const void* x, int rows, int C, float eps, const float* gamma, const float* beta, void* out) {
   if (!c || !x || !out) return LTB_FAIL("layernorm: null argument");
+  LTB_CTX_ENTER(c);
   cudaError_t e = launch_layernorm(static_cast<const __half*>(x), rows, C, eps, gamma, beta, static_cast<__half*>(out), c->st);
   if (e != cudaSuccess) return LTB_FAIL(std::string("layernorm: ") + cudaGetErrorString(e));
   c->launches += 1;
@@ -278,6 +309,7 @@ int ltb_op_layernorm(ltb_ctx* c, const void* x, int rows, int C, float eps, cons
 }
 int ltb_op_softmax(ltb_ctx* c, const void* x, int rows, int cols, int ld, int valid, float scale, void* out) {
   if (!c || !x || !out) return LTB_FAIL("softmax: null argument");
+  LTB_CTX_ENTER(c);
   cudaError_t e = launch_softmax(static_cast<const __half*>(x), rows, cols, ld, valid, scale, static_cast<__half*>(out), c->st);
   if (e != cudaSuccess) return LTB_FAIL(std::string("softmax: ") + cudaGetErrorString(e));
   c->launches += 1;
@@ -285,6 +317,7 @@ int ltb_op_softmax(ltb_ctx* c, const void* x, int rows, int cols, int ld, int va
 }
 int ltb_op_geglu(ltb_ctx* c, const void* h, long long rows, int H, void* out) {
   if (!c || !h || !out) return LTB_FAIL("geglu: null argument");
+  LTB_CTX_ENTER(c);
   cudaError_t e = launch_geglu(static_cast<const __half*>(h), (size_t)rows, H, static_cast<__half*>(out), c->st);
   if (e != cudaSuccess) return LTB_FAIL(std::string("geglu: ") + cudaGetErrorString(e));
   c->launches += 1;
@@ -292,6 +325,7 @@ int ltb_op_geglu(ltb_ctx* c, const void* h, long long rows, int H, void* out) {
 }
 int ltb_op_eltwise(ltb_ctx* c, const void* x, const void* y, long long n, long long period, int act, void* out) {
   if (!c || !x || !out) return LTB_FAIL("eltwise: null argument");
+  LTB_CTX_ENTER(c);
   cudaError_t e = launch_eltwise(static_cast<const __half*>(x), static_cast<const __half*>(y), (size_t)n, (size_t)period, act,
                                  static_cast<__half*>(out), c->st);
   if (e != cudaSuccess) return LTB_FAIL(std::string("eltwise: ") + cudaGetErrorString(e));
@@ -300,6 +334,7 @@ int ltb_op_eltwise(ltb_ctx* c, const void* x, const void* y, long long n, long l
 }
 int ltb_op_upsample2x(ltb_ctx* c, const void* x, int N, int H, int W, int C, void* out) {
   if (!c || !x || !out) return LTB_FAIL("upsample2x: null argument");
+  LTB_CTX_ENTER(c);
   cudaError_t e = launch_upsample2x(static_cast<const __half*>(x), N, H, W, C, static_cast<__half*>(out), c->st);
   if (e != cudaSuccess) return LTB_FAIL(std::string("upsample2x: ") + cudaGetErrorString(e));
   c->launches += 1;
@@ -307,6 +342,7 @@ int ltb_op_upsample2x(ltb_ctx* c, const void* x, int N, int H, int W, int C, voi
 }
 int ltb_op_copy_channels(ltb_ctx* c, const void* src, long long rows, int C, int SCtot, int sc_off, void* dst, int DCtot, int dc_off) {
   if (!c || !src || !dst) return LTB_FAIL("copy_channels: null argument");
+  LTB_CTX_ENTER(c);
   cudaError_t e = launch_copy_channels(static_cast<const __half*>(src), (size_t)rows, C, SCtot, sc_off, static_cast<__half*>(dst), DCtot,
                                        dc_off, c->st);
   if (e != cudaSuccess) return LTB_FAIL(std::string("copy_channels: ") + cudaGetErrorString(e));
@@ -315,6 +351,7 @@ int ltb_op_copy_channels(ltb_ctx* c, const void* src, long long rows, int C, int
 }
 int ltb_op_transpose_heads(ltb_ctx* c, const void* v, int B, int n_keys, int Ctot, int c_off, int heads, int d, int n_pad, void* vt) {
   if (!c || !v || !vt) return LTB_FAIL("transpose_heads: null argument");
+  LTB_CTX_ENTER(c);
   cudaError_t e = launch_transpose_heads(static_cast<const __half*>(v), B, n_keys, Ctot, c_off, heads, d, n_pad, static_cast<__half*>(vt),
                                          c->st);
   if (e != cudaSuccess) return LTB_FAIL(std::string("transpose_heads: ") + cudaGetErrorString(e));
@@ -323,6 +360,7 @@ int ltb_op_transpose_heads(ltb_ctx* c, const void* v, int B, int n_keys, int Cto
 }
 int ltb_op_vae_post(ltb_ctx* c, const void* x, long long npix, int Ctot, void* out_u8) {
   if (!c || !x || !out_u8) return LTB_FAIL("vae_post: null argument");
+  LTB_CTX_ENTER(c);
   cudaError_t e = launch_vae_post(static_cast<const __half*>(x), (size_t)npix, Ctot, static_cast<uint8_t*>(out_u8), c->st);
   if (e != cudaSuccess) return LTB_FAIL(std::string("vae_post: ") + cudaGetErrorString(e));
   c->launches += 1;
@@ -330,6 +368,7 @@ int ltb_op_vae_post(ltb_ctx* c, const void* x, long long npix, int Ctot, void* o
 }
 int ltb_op_bgr_to_i420(ltb_ctx* c, const void* bgr_u8, int N, int H, int W, void* out_i420) {
   if (!c || !bgr_u8 || !out_i420) return LTB_FAIL("bgr_to_i420: null argument");
+  LTB_CTX_ENTER(c);
   if (N <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 3)) return LTB_FAIL("bgr_to_i420: needs even height and a width that is a multiple of 4");
   cudaError_t e = launch_bgr_to_i420(static_cast<const uint8_t*>(bgr_u8), N, H, W, static_cast<uint8_t*>(out_i420), c->st);
   if (e != cudaSuccess) return LTB_FAIL(std::string("bgr_to_i420: ") + cudaGetErrorString(e));
@@ -338,6 +377,7 @@ int ltb_op_bgr_to_i420(ltb_ctx* c, const void* bgr_u8, int N, int H, int W, void
 }
 int ltb_op_vae_pre(ltb_ctx* c, const void* img_u8, int N, int H, int W, int half_mask, void* out) {
   if (!c || !img_u8 || !out) return LTB_FAIL("vae_pre: null argument");
+  LTB_CTX_ENTER(c);
   cudaError_t e = launch_vae_pre(static_cast<const uint8_t*>(img_u8), N, H, W, half_mask, static_cast<__half*>(out), c->st);
   if (e != cudaSuccess) return LTB_FAIL(std::string("vae_pre: ") + cudaGetErrorString(e));
   c->launches += 1;
@@ -345,6 +385,7 @@ int ltb_op_vae_pre(ltb_ctx* c, const void* img_u8, int N, int H, int W, int half
 }
 int ltb_op_gather_rows(ltb_ctx* c, const void* table, int n, const void* d_index, int B, long long row_elems, void* out) {
   if (!c || !table || !d_index || !out) return LTB_FAIL("gather_rows: null argument");
+  LTB_CTX_ENTER(c);
   cudaError_t e = launch_gather_rows(static_cast<const __half*>(table), n, static_cast<const int*>(d_index), B, (size_t)row_elems,
                                      static_cast<__half*>(out), c->st);
   if (e != cudaSuccess) return LTB_FAIL(std::string("gather_rows: ") + cudaGetErrorString(e));
@@ -354,6 +395,7 @@ int ltb_op_gather_rows(ltb_ctx* c, const void* table, int n, const void* d_index
 int ltb_op_whisper_logmel(ltb_ctx* c, const void* pcm_f32, int n, const void* fb_f32, void* logspec_ws, void* gmax_ws, void* out_f16,
                           void* out_f32) {
   if (!c || !pcm_f32 || !fb_f32 || !logspec_ws || !gmax_ws || !out_f16) return LTB_FAIL("whisper_logmel: null argument");
+  LTB_CTX_ENTER(c);
   cudaError_t e = launch_whisper_logmel(static_cast<const float*>(pcm_f32), n, static_cast<const float*>(fb_f32),
                                         static_cast<float*>(logspec_ws), static_cast<int*>(gmax_ws), static_cast<__half*>(out_f16),
                                         static_cast<float*>(out_f32), c->st);
@@ -364,6 +406,7 @@ int ltb_op_whisper_logmel(ltb_ctx* c, const void* pcm_f32, int n, const void* fb
 int ltb_op_whisper_slice(ltb_ctx* c, const void* const* hidden5, int T, int D, int B, float start, float mult, void* out,
                          int out_rows_per_frame) {
   if (!c || !hidden5 || !out) return LTB_FAIL("whisper_slice: null argument");
+  LTB_CTX_ENTER(c);
   if (D % 8 != 0 || out_rows_per_frame < 50) return LTB_FAIL("whisper_slice: bad shape");
   cudaError_t e = launch_whisper_slice(reinterpret_cast<const __half* const*>(hidden5), T, D, B, start, mult, static_cast<__half*>(out),
                                        out_rows_per_frame, c->st);
@@ -373,6 +416,7 @@ int ltb_op_whisper_slice(ltb_ctx* c, const void* const* hidden5, int T, int D, i
 }
 int ltb_op_mt_paste(ltb_ctx* c, const ltb_mt_paste_op* d) {
   if (!c || !d) return LTB_FAIL("mt_paste: null argument");
+  LTB_CTX_ENTER(c);
   MtPasteArgs a;
   a.frames = static_cast<const uint8_t*>(d->frames);
   a.coords = static_cast<const int*>(d->coords);
@@ -387,6 +431,7 @@ int ltb_op_mt_paste(ltb_ctx* c, const ltb_mt_paste_op* d) {
   a.index = d->index;
   a.explicit_idx = d->explicit_idx;
   a.slot0 = d->slot0;
+  a.S = d->pred_hw > 0 ? d->pred_hw : 256;
   cudaError_t e = launch_mt_paste(a, d->count, c->st);
   if (e != cudaSuccess) return LTB_FAIL(std::string("mt_paste: ") + cudaGetErrorString(e));
   c->launches += 1;

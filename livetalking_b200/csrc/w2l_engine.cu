@@ -232,11 +232,23 @@ struct ltb_w2l_session {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<void*> allocs;
   __half* img_pad = nullptr;
-  float* mel = nullptr;
-  float* pcm = nullptr;
+  // Threading (avatars/base_avatar.py:469-501): the reference drives one session from three threads — render() calls
+  // asr.run_step (-> ltb_w2l_mel_step), inference() calls inference_batch (-> ltb_w2l_infer / paste_batch), process_frames()
+  // calls paste_back_frame (-> ltb_w2l_paste*).  `mu` serialises every entry point that enqueues on `st` (each holds it
+  // from its first enqueue to its synchronise, so multi-call sequences such as H2D(mel) -> set_int -> graph launch cannot be
+  // interleaved); the feature extractor has its OWN stream, buffers and mutex (`mu_asr`), so run_step never touches the
+  // forward's mel input and never waits for a forward pass.
+  std::mutex mu, mu_asr;
+  float* mel = nullptr;           // forward input: written by ltb_w2l_infer (host windows) or by the in-graph mel kernels
+  float* pcm = nullptr;           // resident PCM window of the in-graph mel (step_async / step_e2e_async)
   int pcm_cap = 0;
   double* mel_spec = nullptr;
   double* mel_mel = nullptr;
+  cudaStream_t st_asr = nullptr;  // ltb_w2l_mel_step only
+  float* asr_pcm = nullptr;
+  float* asr_mel = nullptr;
+  double* asr_spec = nullptr;
+  double* asr_melf = nullptr;
   float* pred = nullptr;
   float* pred_scratch = nullptr;  // one host-supplied prediction (ltb_w2l_paste_pred)
   uint8_t* frames_out = nullptr;
@@ -255,7 +267,8 @@ struct ltb_w2l_session {
   cudaGraphExec_t gexec = nullptr;
   cudaGraph_t graph_mel = nullptr;       // same forward with the mel kernels heading the audio branch
   cudaGraphExec_t gexec_mel = nullptr;
-  long long launches = 0;
+  long long launches = 0;      // guarded by mu
+  long long launches_asr = 0;  // guarded by mu_asr
   int graph_nodes = 0;
   bool pdl = true;   // conv kernels use programmatic dependent launch
 };
@@ -268,6 +281,14 @@ static int dev_alloc(ltb_w2l_session* s, size_t bytes, void** out, bool zero) {
   if (zero) LTB_CUDA(cudaMemset(p, 0, bytes));
   s->allocs.push_back(p);
   *out = p;
+  return 0;
+}
+
+// Every entry point may be called from a thread whose current CUDA device is not the session's (the reference starts
+// fresh render / inference / process threads, which default to device 0).
+static inline int enter(const ltb_w2l_session* s) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != s->m->device) LTB_CUDA(cudaSetDevice(s->m->device));
   return 0;
 }
 
@@ -713,7 +734,9 @@ static int model_from(ltb_w2l_model* m, const uint8_t* header_host, size_t nbyte
     if (!conv3 && !convt) continue;
     const size_t bytes = (size_t)L.cout * 9 * L.cin * 2;
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->wt[i]), bytes);
-    if (e == cudaSuccess) e = launch_w_tap_major(m->w[i], m->wt[i], L.cout, L.cin, nullptr);
+    if (e == cudaSuccess)
+      e = convt ? launch_w_tap_major_convT(m->w[i], m->wt[i], L.cout, L.cin, nullptr)
+                : launch_w_tap_major(m->w[i], m->wt[i], L.cout, L.cin, nullptr);
     if (e != cudaSuccess) {
       model_free(m);
       return LTB_FAIL(std::string("tap-major weight copy: ") + cudaGetErrorString(e));
@@ -813,7 +836,12 @@ int ltb_w2l_avatar_destroy(ltb_w2l_avatar* a) {
 
 int ltb_w2l_session_destroy(ltb_w2l_session* s) {
   if (!s) return 0;
+  if (s->m) cudaSetDevice(s->m->device);
   if (s->st) cudaStreamSynchronize(s->st);
+  if (s->st_asr) {
+    cudaStreamSynchronize(s->st_asr);
+    cudaStreamDestroy(s->st_asr);
+  }
   if (s->gexec) cudaGraphExecDestroy(s->gexec);
   if (s->graph) cudaGraphDestroy(s->graph);
   if (s->gexec_mel) cudaGraphExecDestroy(s->gexec_mel);
@@ -851,8 +879,11 @@ int ltb_w2l_session_create(ltb_w2l_model* m, ltb_w2l_avatar* a, int batch, int s
     ltb_w2l_session_destroy(s);
     return 1;
   };
+  if (m->device != a->device) return bail(LTB_FAIL("model and avatar live on different devices"));
+  if (cudaSetDevice(m->device) != cudaSuccess) return bail(LTB_FAIL("cudaSetDevice failed"));
   if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) return bail(LTB_FAIL("stream create failed"));
   if (cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking) != cudaSuccess) return bail(LTB_FAIL("stream create failed"));
+  if (cudaStreamCreateWithFlags(&s->st_asr, cudaStreamNonBlocking) != cudaSuccess) return bail(LTB_FAIL("stream create failed"));
   if (cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess)
     return bail(LTB_FAIL("event create failed"));
@@ -868,6 +899,14 @@ int ltb_w2l_session_create(ltb_w2l_model* m, ltb_w2l_avatar* a, int batch, int s
   s->mel_spec = static_cast<double*>(p);
   if (dev_alloc(s, mel_scratch_mel_doubles(s->pcm_cap) * 8, &p, true)) return bail(1);
   s->mel_mel = static_cast<double*>(p);
+  if (dev_alloc(s, (size_t)batch * 80 * 16 * 4, &p, true)) return bail(1);
+  s->asr_mel = static_cast<float*>(p);
+  if (dev_alloc(s, (size_t)s->pcm_cap * 4, &p, true)) return bail(1);
+  s->asr_pcm = static_cast<float*>(p);
+  if (dev_alloc(s, mel_scratch_spec_doubles(s->pcm_cap) * 8, &p, true)) return bail(1);
+  s->asr_spec = static_cast<double*>(p);
+  if (dev_alloc(s, mel_scratch_mel_doubles(s->pcm_cap) * 8, &p, true)) return bail(1);
+  s->asr_melf = static_cast<double*>(p);
   if (dev_alloc(s, (size_t)batch * 65536 * 3 * 4, &p, true)) return bail(1);
   s->pred = static_cast<float*>(p);
   if (dev_alloc(s, (size_t)65536 * 3 * 4, &p, true)) return bail(1);
@@ -932,14 +971,27 @@ int ltb_w2l_mel_step(ltb_w2l_session* s, const float* pcm, int nsamples, float* 
   if (!s || !pcm) return LTB_FAIL("null argument");
   const int expect = (s->l + s->r + 2 * s->B) * 320;
   if (nsamples != expect) return LTB_FAIL("mel_step: expected " + std::to_string(expect) + " samples, got " + std::to_string(nsamples));
-  LTB_CUDA(cudaMemcpyAsync(s->pcm, pcm, (size_t)nsamples * 4, cudaMemcpyHostToDevice, s->st));
-  cudaError_t e = launch_mel_step(s->pcm, nsamples, s->B, s->l, s->fps, s->mel_spec, s->mel_mel, s->mel, s->st);
+  if (enter(s)) return 1;
+  // MelASR.run_step runs on the render thread, concurrently with inference_batch on the inference thread: own stream,
+  // own PCM / scratch / output buffers — nothing here is read or written by the forward pass
+  std::lock_guard<std::mutex> lk(s->mu_asr);
+  LTB_CUDA(cudaMemcpyAsync(s->asr_pcm, pcm, (size_t)nsamples * 4, cudaMemcpyHostToDevice, s->st_asr));
+  cudaError_t e = launch_mel_step(s->asr_pcm, nsamples, s->B, s->l, s->fps, s->asr_spec, s->asr_melf, s->asr_mel, s->st_asr);
   if (e != cudaSuccess) return LTB_FAIL(std::string("mel kernels: ") + cudaGetErrorString(e));
-  s->launches += 3;
-  if (out_mel) {
-    LTB_CUDA(cudaMemcpyAsync(out_mel, s->mel, (size_t)s->B * 1280 * 4, cudaMemcpyDeviceToHost, s->st));
-    LTB_CUDA(cudaStreamSynchronize(s->st));
-  }
+  s->launches_asr += 3;
+  if (out_mel) LTB_CUDA(cudaMemcpyAsync(out_mel, s->asr_mel, (size_t)s->B * 1280 * 4, cudaMemcpyDeviceToHost, s->st_asr));
+  LTB_CUDA(cudaStreamSynchronize(s->st_asr));
+  return 0;
+}
+
+int ltb_w2l_set_pcm(ltb_w2l_session* s, const float* pcm, int nsamples) {
+  if (!s || !pcm) return LTB_FAIL("null argument");
+  const int expect = (s->l + s->r + 2 * s->B) * 320;
+  if (nsamples != expect) return LTB_FAIL("set_pcm: expected " + std::to_string(expect) + " samples, got " + std::to_string(nsamples));
+  if (enter(s)) return 1;
+  std::lock_guard<std::mutex> lk(s->mu);
+  LTB_CUDA(cudaMemcpyAsync(s->pcm, pcm, (size_t)nsamples * 4, cudaMemcpyHostToDevice, s->st));
+  LTB_CUDA(cudaStreamSynchronize(s->st));
   return 0;
 }
 
@@ -957,6 +1009,8 @@ static int forward_enqueue(ltb_w2l_session* s, int index, bool with_mel) {
 
 int ltb_w2l_infer(ltb_w2l_session* s, int index, const float* mel, float* pred_out) {
   if (!s) return LTB_FAIL("null session");
+  if (enter(s)) return 1;
+  std::lock_guard<std::mutex> lk(s->mu);
   if (mel) LTB_CUDA(cudaMemcpyAsync(s->mel, mel, (size_t)s->B * 1280 * 4, cudaMemcpyHostToDevice, s->st));
   if (forward_enqueue(s, index, false)) return 1;
   if (pred_out) LTB_CUDA(cudaMemcpyAsync(pred_out, s->pred, (size_t)s->B * 65536 * 3 * 4, cudaMemcpyDeviceToHost, s->st));
@@ -968,6 +1022,8 @@ int ltb_w2l_paste(ltb_w2l_session* s, int slot, int idx, uint8_t* out_frame) {
   if (!s || !out_frame) return LTB_FAIL("null argument");
   if (slot < 0 || slot >= s->B) return LTB_FAIL("paste: slot out of range");
   if (idx < 0 || idx >= s->a->n) return LTB_FAIL("paste: idx out of range");
+  if (enter(s)) return 1;
+  std::lock_guard<std::mutex> lk(s->mu);
   const size_t fb = (size_t)s->a->H * s->a->W * 3;
   cudaError_t e = launch_w2l_paste(s->a->frames, s->a->coords, s->a->n, s->a->H, s->a->W, s->pred, slot, 0, idx, 1,
                                    s->frames_out + (size_t)slot * fb, s->st);
@@ -981,6 +1037,8 @@ int ltb_w2l_paste(ltb_w2l_session* s, int slot, int idx, uint8_t* out_frame) {
 int ltb_w2l_paste_pred(ltb_w2l_session* s, const float* pred, int idx, uint8_t* out_frame) {
   if (!s || !pred || !out_frame) return LTB_FAIL("null argument");
   if (idx < 0 || idx >= s->a->n) return LTB_FAIL("paste: idx out of range");
+  if (enter(s)) return 1;
+  std::lock_guard<std::mutex> lk(s->mu);
   const size_t fb = (size_t)s->a->H * s->a->W * 3;
   LTB_CUDA(cudaMemcpyAsync(s->pred_scratch, pred, (size_t)65536 * 3 * 4, cudaMemcpyHostToDevice, s->st));
   cudaError_t e = launch_w2l_paste(s->a->frames, s->a->coords, s->a->n, s->a->H, s->a->W, s->pred_scratch, 0, 0, idx, 1,
@@ -1003,6 +1061,8 @@ static int paste_batch_enqueue(ltb_w2l_session* s, int index, uint8_t* dst = nul
 int ltb_w2l_paste_batch(ltb_w2l_session* s, int index, uint8_t* out_frames) {
   if (!s) return LTB_FAIL("null session");
   if (index < 0) return LTB_FAIL("negative index");
+  if (enter(s)) return 1;
+  std::lock_guard<std::mutex> lk(s->mu);
   if (paste_batch_enqueue(s, index)) return 1;
   if (out_frames) {
     LTB_CUDA(cudaMemcpyAsync(out_frames, s->frames_out, (size_t)s->B * s->a->H * s->a->W * 3, cudaMemcpyDeviceToHost, s->st));
@@ -1013,6 +1073,8 @@ int ltb_w2l_paste_batch(ltb_w2l_session* s, int index, uint8_t* out_frames) {
 
 int ltb_w2l_mel_resident(ltb_w2l_session* s) {
   if (!s) return LTB_FAIL("null session");
+  if (enter(s)) return 1;
+  std::lock_guard<std::mutex> lk(s->mu);
   cudaError_t e = launch_mel_step(s->pcm, s->pcm_cap, s->B, s->l, s->fps, s->mel_spec, s->mel_mel, s->mel, s->st);
   if (e != cudaSuccess) return LTB_FAIL(std::string("mel kernels: ") + cudaGetErrorString(e));
   s->launches += 3;
@@ -1021,12 +1083,16 @@ int ltb_w2l_mel_resident(ltb_w2l_session* s) {
 
 int ltb_w2l_step_async(ltb_w2l_session* s, int index) {
   if (!s) return LTB_FAIL("null session");
+  if (enter(s)) return 1;
+  std::lock_guard<std::mutex> lk(s->mu);
   if (forward_enqueue(s, index, true)) return 1;
   return paste_batch_enqueue(s, index);
 }
 
 int ltb_w2l_forward_async(ltb_w2l_session* s, int index) {
   if (!s) return LTB_FAIL("null session");
+  if (enter(s)) return 1;
+  std::lock_guard<std::mutex> lk(s->mu);
   return forward_enqueue(s, index, false);
 }
 
@@ -1036,6 +1102,8 @@ int ltb_w2l_profile_ops(ltb_w2l_session* s, int index, int max_ops, int* n_ops, 
   *n_ops = n;
   if (!ms) return 0;
   if (max_ops < n) return LTB_FAIL("profile_ops: buffer too small");
+  if (enter(s)) return 1;
+  std::lock_guard<std::mutex> lk(s->mu);
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) LTB_CUDA(cudaEventCreate(&e));
   if (launch_set_int(s->d_index, index, s->st) != cudaSuccess) return LTB_FAIL("set_int launch failed");
@@ -1059,8 +1127,14 @@ int ltb_w2l_profile_ops(ltb_w2l_session* s, int index, int max_ops, int* n_ops, 
 
 int ltb_w2l_e2e_acquire(ltb_w2l_session* s) {
   if (!s) return LTB_FAIL("null session");
-  const int slot = (int)(s->e2e_seq & 1u);
-  if (s->copied_valid[slot]) LTB_CUDA(cudaEventSynchronize(s->ev_copied[slot]));   // step seq-2 (same host buffers) fully drained
+  if (enter(s)) return 1;
+  cudaEvent_t ev = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    const int slot = (int)(s->e2e_seq & 1u);
+    if (s->copied_valid[slot]) ev = s->ev_copied[slot];
+  }
+  if (ev) LTB_CUDA(cudaEventSynchronize(ev));   // step seq-2 (same host buffers) fully drained
   return 0;
 }
 
@@ -1068,6 +1142,8 @@ int ltb_w2l_step_e2e_async(ltb_w2l_session* s, int index, const float* pcm_host,
   if (!s || !pcm_host || !frames_host) return LTB_FAIL("null argument");
   const int expect = (s->l + s->r + 2 * s->B) * 320;
   if (nsamples != expect) return LTB_FAIL("step_e2e: expected " + std::to_string(expect) + " samples");
+  if (enter(s)) return 1;
+  std::lock_guard<std::mutex> lk(s->mu);
   if (!s->st_copy) {
     LTB_CUDA(cudaStreamCreateWithFlags(&s->st_copy, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
@@ -1096,6 +1172,8 @@ int ltb_w2l_step_e2e_async(ltb_w2l_session* s, int index, const float* pcm_host,
 
 int ltb_w2l_sync(ltb_w2l_session* s) {
   if (!s) return LTB_FAIL("null session");
+  if (enter(s)) return 1;
+  std::lock_guard<std::mutex> lk(s->mu);
   LTB_CUDA(cudaStreamSynchronize(s->st));
   if (s->st_copy) LTB_CUDA(cudaStreamSynchronize(s->st_copy));
   return 0;
@@ -1109,7 +1187,14 @@ int ltb_w2l_stream(ltb_w2l_session* s, void** cuda_stream) {
 
 int ltb_w2l_launch_count(ltb_w2l_session* s, long long* n) {
   if (!s || !n) return LTB_FAIL("null argument");
-  *n = s->launches;
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    *n = s->launches;
+  }
+  {
+    std::lock_guard<std::mutex> lk(s->mu_asr);
+    *n += s->launches_asr;
+  }
   return 0;
 }
 
@@ -1215,7 +1300,8 @@ int ltb_conv2d_f16(const ltb_conv_desc* d, const void* in_f16, const float* w_f3
   }
   if (d->force_path != 1 && can_halo) {
     CK(cudaMalloc(&dwt, wp.size() * 2));
-    if (d->KH == 3) CK(launch_w_tap_major(dw, dwt, d->Cout, d->Cin, nullptr));
+    if (d->KH == 3)
+      CK(d->transposed ? launch_w_tap_major_convT(dw, dwt, d->Cout, d->Cin, nullptr) : launch_w_tap_major(dw, dwt, d->Cout, d->Cin, nullptr));
     HaloPlan pl;
     if (conv_halo_make_plan(p, dwt, &pl) != 0) {
       cleanup();

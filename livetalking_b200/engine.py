@@ -134,6 +134,11 @@ class W2LSession:
         check(lib().ltb_w2l_mel_step(self._h, _ptr(pcm), pcm.size, _ptr(out)))
         return out
 
+    def set_pcm(self, pcm: np.ndarray) -> None:
+        """Upload the PCM window read by the device-resident step (mel_resident / step_async)."""
+        pcm = _carr(pcm, np.float32).reshape(-1)
+        check(lib().ltb_w2l_set_pcm(self._h, _ptr(pcm), pcm.size))
+
     # --- wav2lip_avatar.py:116-139
     def infer(self, index: int, mel: Optional[np.ndarray] = None, want_pred: bool = True) -> Optional[np.ndarray]:
         if mel is not None:

@@ -421,7 +421,7 @@ class MuseTalkModel:
                 taps[f"dec_up{i}"] = h
         img = b.conv3(b.groupnorm(h, self.v_dec_norm_out, G, eps, True), self.v_dec_out)   # (B,H,W,16), RGB in channels 0..2
         N, H, W, _ = img.shape
-        self.ctx.vae_post(img, N * H * W, out_u8)
+        b.ctx.vae_post(img, N * H * W, out_u8)
         return img
 
     def emit_vae_encode(self, b: Builder, img_u8: DevTensor, out_latents16: DevTensor):
@@ -431,8 +431,8 @@ class MuseTalkModel:
         G, eps = cfg.norm_groups, cfg.norm_eps
         B, H, W, _ = img_u8.shape
         x = b.new(2 * B, H, W, 16)
-        self.ctx.vae_pre(img_u8, B, H, W, True, DevTensor(x.ptr, (B, H, W, 16)))                                  # masked copies
-        self.ctx.vae_pre(img_u8, B, H, W, False, DevTensor(x.offset(B * H * W * 16), (B, H, W, 16)))              # reference copies
+        b.ctx.vae_pre(img_u8, B, H, W, True, DevTensor(x.ptr, (B, H, W, 16)))                                  # masked copies
+        b.ctx.vae_pre(img_u8, B, H, W, False, DevTensor(x.offset(B * H * W * 16), (B, H, W, 16)))              # reference copies
         h = b.conv3(x, self.v_enc_in, stats=True)
         for blk in self.v_enc_down:
             for r in blk["res"]:
@@ -488,9 +488,13 @@ class MuseTalkAvatar:
 class MuseTalkSession:
     """One avatar stream at a fixed batch size: the captured UNet + VAE-decode graph and the paste-back buffers."""
 
-    def __init__(self, model: MuseTalkModel, avatar: MuseTalkAvatar, batch: int, keep_taps: bool = False):
+    def __init__(self, model: MuseTalkModel, avatar: MuseTalkAvatar, batch: int, keep_taps: bool = False, ctx: Optional[Ctx] = None):
+        """ctx: the session's own stream + scratch (created here unless given).  Sessions never share a ctx: the reference
+        opens up to max_session of them concurrently (app.py:76-100), each driven by its own three threads, and capturing /
+        synchronising a stream another session is using would corrupt both."""
         self.model, self.avatar, self.B = model, avatar, int(batch)
-        ctx = self.ctx = model.ctx
+        self._own_ctx = ctx is None
+        ctx = self.ctx = Ctx() if ctx is None else ctx
         B, hw = self.B, avatar.lat_hw
         self.builder = Builder(ctx)
         self.d_index = ctx.alloc((4,), np.int32, zero=True)
@@ -500,6 +504,7 @@ class MuseTalkSession:
         self.image_u8 = ctx.alloc((B, hw * 8, hw * 8, 3), np.uint8, zero=True)
         self.frames_out = ctx.alloc((B, avatar.H, avatar.W, 3), np.uint8, zero=True)
         self.taps = {} if keep_taps else None
+        self._paste_ctx = None
         self._audio_host = np.zeros((B, KEY_PAD, model.ucfg.cross_attention_dim), np.float16)
 
         def emit():
@@ -529,44 +534,79 @@ class MuseTalkSession:
         self.graph.launch()
 
     def infer(self, index: int, audio_feats: Optional[np.ndarray] = None, want_pred: bool = True):
-        self.infer_async(index, audio_feats)
-        if want_pred:
-            return self.ctx.download(self.image_u8)          # uint8 (B,256,256,3) BGR, as vae.decode_latents returns
-        self.ctx.sync()
-        return None
+        with self.ctx.lock:       # h2d -> index -> graph -> d2h is one critical section (inference vs process_frames thread)
+            self.infer_async(index, audio_feats)
+            if want_pred:
+                return self.ctx.download(self.image_u8)          # uint8 (B,hw*8,hw*8,3) BGR, as vae.decode_latents returns
+            self.ctx.sync()
+            return None
 
     # ---- MuseReal.paste_back_frame (musetalk_avatar.py:154-164)
-    def _paste_op(self, pred: DevTensor, slot0: int, index: int, explicit_idx: int, count: int):
+    def _make_paste_op(self, pred: DevTensor, out: DevTensor, slot0: int, index: int, explicit_idx: int, count: int):
         a = self.avatar
         op = _capi.MtPasteOp()
         op.frames, op.coords, op.crop, op.masks, op.mask_off = a.frames.ptr, a.coords.ptr, a.crop.ptr, a.masks.ptr, a.mask_off.ptr
-        op.pred, op.out = pred.ptr, self.frames_out.ptr
+        op.pred, op.out = pred.ptr, out.ptr
         op.nf, op.H, op.W = a.n, a.H, a.W
         op.index, op.explicit_idx, op.slot0, op.count = index, explicit_idx, slot0, count
-        self.ctx.mt_paste(op)
+        op.pred_hw = a.lat_hw * 8
+        return op
+
+    def _paste_op(self, pred: DevTensor, slot0: int, index: int, explicit_idx: int, count: int):
+        self.ctx.mt_paste(self._make_paste_op(pred, self.frames_out, slot0, index, explicit_idx, count))
 
     def paste(self, slot: int, idx: int) -> np.ndarray:
         if not (0 <= slot < self.B and 0 <= idx < self.avatar.n):
             raise ValueError("paste: slot / idx out of range")
-        self._paste_op(self.image_u8, slot, 0, idx, 1)
-        one = DevTensor(self.frames_out.ptr, (self.avatar.H, self.avatar.W, 3), np.uint8)
-        return self.ctx.download(one)
+        with self.ctx.lock:
+            self._paste_op(self.image_u8, slot, 0, idx, 1)
+            one = DevTensor(self.frames_out.ptr, (self.avatar.H, self.avatar.W, 3), np.uint8)
+            return self.ctx.download(one)
 
     def paste_pred(self, pred_u8: np.ndarray, idx: int) -> np.ndarray:
-        """paste_back_frame for a host prediction (256,256,3) uint8 — the reference's exact argument."""
-        if not hasattr(self, "_pred_scratch"):
-            self._pred_scratch = self.ctx.alloc((1, 256, 256, 3), np.uint8)
-        self.ctx.h2d(self._pred_scratch, np.ascontiguousarray(pred_u8, np.uint8), sync=False)
-        self._paste_op(self._pred_scratch, 0, 0, idx, 1)
-        one = DevTensor(self.frames_out.ptr, (self.avatar.H, self.avatar.W, 3), np.uint8)
-        return self.ctx.download(one)
+        """paste_back_frame for a host prediction (S,S,3) uint8 — the reference's exact argument.  Runs on its own small
+        ctx (stream + scratch prediction + output frame): process_frames calls it while inference_batch is in flight."""
+        S = self.avatar.lat_hw * 8
+        pred_u8 = np.ascontiguousarray(pred_u8, np.uint8)
+        if pred_u8.shape != (S, S, 3):
+            raise ValueError(f"paste_pred: prediction must be ({S},{S},3) uint8, got {pred_u8.shape}")
+        if not 0 <= idx < self.avatar.n:
+            raise ValueError("paste_pred: idx out of range")
+        if self._paste_ctx is None:
+            self._paste_ctx = Ctx()
+            self._pred_scratch = self._paste_ctx.alloc((1, S, S, 3), np.uint8)
+            self._paste_out = self._paste_ctx.alloc((self.avatar.H, self.avatar.W, 3), np.uint8)
+        pc = self._paste_ctx
+        with pc.lock:
+            pc.h2d(self._pred_scratch, pred_u8, sync=False)
+            pc.mt_paste(self._make_paste_op(self._pred_scratch, self._paste_out, 0, 0, idx, 1))
+            return pc.download(self._paste_out)
 
     def paste_batch_async(self, index: int):
         self._paste_op(self.image_u8, 0, index, -1, self.B)
 
     def paste_batch(self, index: int, out: Optional[np.ndarray] = None) -> np.ndarray:
-        self.paste_batch_async(index)
-        return self.ctx.download(self.frames_out, out)
+        with self.ctx.lock:
+            self.paste_batch_async(index)
+            return self.ctx.download(self.frames_out, out)
+
+    def close(self):
+        """Release the session's graph, streams and device buffers (one WebRTC connection = one session: no HBM leak)."""
+        if getattr(self, "graph", None) is not None:
+            self.graph.close()
+            self.graph = None
+        if self._paste_ctx is not None:
+            self._paste_ctx.close()
+            self._paste_ctx = None
+        if self._own_ctx and self.ctx is not None:
+            self.ctx.close()
+        self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def step_async(self, index: int):
         """Everything resident (audio features already on the device): UNet + VAE decode + blend paste-back."""

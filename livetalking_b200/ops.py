@@ -59,9 +59,15 @@ class Graph:
 
 
 class Ctx:
+    """One CUDA stream + scratch workspaces + a list of owned allocations.  Not internally serialised across multi-call
+    sequences: a ctx belongs to ONE session and thread role (``lock`` is what a session holds around h2d -> launch -> d2h);
+    weights uploaded through a model's ctx are immutable and may be read from any other ctx's stream."""
+
     def __init__(self):
+        import threading
         self._h = C.c_void_p()
         check(lib().ltb_ctx_create(C.byref(self._h)))
+        self.lock = threading.RLock()
 
     # ---- memory
     def alloc(self, shape, dtype=np.float16, zero: bool = False) -> DevTensor:

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .base_asr import BaseASR
+from .base_asr import BaseASR, fixed_chunk
 
 
 class MelASR(BaseASR):
@@ -20,6 +20,7 @@ class MelASR(BaseASR):
     def run_step(self):
         for _ in range(self.batch_size * 2):
             audioframe = self.get_audio_frame()
+            audioframe.data = fixed_chunk(audioframe.data, self.chunk)     # short tail chunk of a custom-action clip
             self.frames.append(audioframe.data)
             self.output_queue.put(audioframe)
         if len(self.frames) <= self.stride_left_size + self.stride_right_size:   # context not enough (mel.py:43-44)
@@ -27,8 +28,9 @@ class MelASR(BaseASR):
         inputs = np.concatenate(self.frames)
         n_expected = (self.stride_left_size + self.stride_right_size + 2 * self.batch_size) * self.chunk
         if inputs.size != n_expected:
-            # only possible before warm_up(): the reference would run librosa on a short buffer; we refuse loudly
-            raise RuntimeError(f"MelASR.run_step: buffer holds {inputs.size} samples, expected {n_expected}; call warm_up() first")
+            # run_step before warm_up(): the reference would run librosa on a short buffer; mirror its early return
+            # (no features, audio already forwarded) instead of raising inside the render loop
+            return
         mel = self.session.mel_step(inputs.astype(np.float32, copy=False))        # (B, 80, 16) float32
         self.feat_queue.put([mel[i] for i in range(self.batch_size)])
         self.frames = self.frames[-(self.stride_left_size + self.stride_right_size):]

@@ -112,12 +112,30 @@ class MuseReal(BaseAvatar):
         self.frame_list_cycle, self.mask_list_cycle, self.coord_list_cycle, self.mask_coords_list_cycle, self.input_latent_list_cycle = avatar
         eng_avatar = getattr(avatar, "engine_avatar", None)
         if eng_avatar is None:
+            # app.py:86-91 calls load_avatar(avatar_id) without the model and shares the payload between sessions: upload once,
+            # cache on the payload (a plain tuple from elsewhere cannot carry it and is uploaded per session)
             eng_avatar = MuseTalkAvatar(model.ctx, self.frame_list_cycle, self.mask_list_cycle, self.coord_list_cycle,
                                         self.mask_coords_list_cycle, self.input_latent_list_cycle)
+            if isinstance(avatar, AvatarPayload):
+                avatar.engine_avatar = eng_avatar
+        # every session owns its stream + scratch (two: UNet/VAE graph, Whisper graph); weights / avatar assets are shared
         self.engine_session = MuseTalkSession(model.net, eng_avatar, self.batch_size)
         self.audio_processor = WhisperFeatures(model.whisper, self.batch_size, opt.l, opt.r)
         self.asr = WhisperASR(opt, self, self.audio_processor)
         self.asr.warm_up()
+
+    def close(self):
+        """Release this session's graphs, streams and device buffers (one WebRTC connection = one session)."""
+        for o in (getattr(self, "engine_session", None), getattr(self, "audio_processor", None)):
+            if o is not None:
+                o.close()
+        self.engine_session = self.audio_processor = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def inference_batch(self, index, audiofeat_batch):
         whisper_batch = np.stack(audiofeat_batch)                                   # (B, 50, 384)

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .base_asr import BaseASR
+from .base_asr import BaseASR, fixed_chunk
 
 
 class WhisperASR(BaseASR):
@@ -20,11 +20,15 @@ class WhisperASR(BaseASR):
     def run_step(self):
         for _ in range(self.batch_size * 2):
             audio_frame = self.get_audio_frame()
+            audio_frame.data = fixed_chunk(audio_frame.data, self.chunk)    # short tail chunk of a custom-action clip
             self.frames.append(audio_frame.data)
             self.output_queue.put(audio_frame)
         if len(self.frames) <= self.stride_left_size + self.stride_right_size:
             return
         inputs = np.concatenate(self.frames)
+        n_expected = (self.stride_left_size + self.stride_right_size + 2 * self.batch_size) * self.chunk
+        if inputs.size != n_expected:                  # run_step before warm_up(): no features yet, as the early return above
+            return
         feats = self.audio_processor.run(inputs.astype(np.float32, copy=False))       # (B, 50, 384) float16
         self.feat_queue.put([feats[i] for i in range(self.batch_size)])
         self.frames = self.frames[-(self.stride_left_size + self.stride_right_size):]

@@ -73,8 +73,9 @@ class WhisperEncoder:
         ctx.sync()
 
     def emit(self, b: Builder, feats16: DevTensor):
-        """feats16: fp16 (3000, 80) log-mel features -> the 5 hidden states HF returns, each (1500, D) fp16."""
-        ctx, D = self.ctx, self.D
+        """feats16: fp16 (3000, 80) log-mel features -> the 5 hidden states HF returns, each (1500, D) fp16.
+        Ops are enqueued on the builder's ctx (the session's own stream); the weights live in self.ctx (read-only)."""
+        ctx, D = b.ctx, self.D
         T = N_FRAMES
         x = DevTensor(feats16.ptr, (1, 1, T, N_MELS))
         h = b.new(1, 1, T, D)
@@ -101,9 +102,12 @@ class WhisperFeatures:
     """audio2feat + WhisperASR slicing for one session: PCM buffer -> (B, 50, D) features, one CUDA graph."""
 
     def __init__(self, enc: WhisperEncoder, batch: int, stride_left: int = 10, stride_right: int = 10, out: Optional[DevTensor] = None,
-                 out_rows: int = 50, keep_hidden: bool = False):
+                 out_rows: int = 50, keep_hidden: bool = False, ctx: Optional[Ctx] = None):
+        """ctx: this extractor's own stream + scratch (created here unless given): WhisperASR.run_step runs on the render
+        thread concurrently with inference_batch on the inference thread (avatars/base_avatar.py:483-489 vs :366)."""
         self.enc, self.B = enc, int(batch)
-        ctx = self.ctx = enc.ctx
+        self._own_ctx = ctx is None
+        ctx = self.ctx = Ctx() if ctx is None else ctx
         self.n = (stride_left + stride_right + 2 * self.B) * 320
         if self.n > N_SAMPLES:
             raise ValueError("audio window longer than 30 s")
@@ -145,6 +149,21 @@ class WhisperFeatures:
 
     def run(self, pcm: np.ndarray) -> np.ndarray:
         """-> (B, 50, D) float16, the list WhisperASR.run_step queues (stacked)."""
-        self.run_async(pcm)
-        full = self.ctx.download(self.out)
+        with self.ctx.lock:
+            self.run_async(pcm)
+            full = self.ctx.download(self.out)
         return full[:, :50]
+
+    def close(self):
+        if getattr(self, "graph", None) is not None:
+            self.graph.close()
+            self.graph = None
+        if self._own_ctx and self.ctx is not None:
+            self.ctx.close()
+        self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -79,3 +79,57 @@ class Opt:
         self.sessionid = 0
         for k, v in kw.items():
             setattr(self, k, v)
+
+
+def run_three_threads(avatar, sink, quit_event):
+    """Test harness for boxes without the reference checkout: drives a plugin avatar with the SAME thread roles and queue
+    hand-offs as the reference's render() (avatars/base_avatar.py:469-501) — thread 1 calls asr.run_step in a loop, thread 2
+    pairs one feature batch with 2*B audio chunks, skips the model for an all-silent batch and calls inference_batch, thread 3
+    calls paste_back_frame (or takes the plain avatar frame for a silent frame) and pushes to the sink.  Blocks until
+    quit_event is set.  (tests/test_base_avatar_threads.py runs the real render() where the checkout exists.)"""
+    import queue
+    import threading
+
+    B, n = avatar.batch_size, len(avatar.frame_list_cycle)
+    mirror = sys.modules["utils.image"].mirror_index
+    stop2, stop3 = threading.Event(), threading.Event()
+
+    def infer_loop():
+        index = 0
+        while not stop2.is_set():
+            try:
+                feats = avatar.asr.feat_queue.get(block=True, timeout=0.5)
+            except queue.Empty:
+                continue
+            audio = [avatar.asr.output_queue.get() for _ in range(2 * B)]
+            if all(a.type != 0 for a in audio):
+                results = [None] * B
+            else:
+                results = list(avatar.inference_batch(index, feats))
+            for i, r in enumerate(results):
+                avatar.res_frame_queue.put((r, audio[2 * i:2 * i + 2], mirror(n, index)))
+                index += 1
+
+    def frame_loop():
+        while not stop3.is_set():
+            try:
+                res, audio, idx = avatar.res_frame_queue.get(block=True, timeout=0.5)
+            except queue.Empty:
+                continue
+            if audio[0].type != 0 and audio[1].type != 0:
+                frame = np.array(avatar.frame_list_cycle[idx], copy=True)
+            else:
+                frame = avatar.paste_back_frame(res, idx)
+            sink.push_video_frame(frame)
+            for a in audio:
+                sink.push_audio_frame((np.asarray(a.data) * 32767).astype(np.int16), a.userdata)
+
+    t2, t3 = threading.Thread(target=infer_loop), threading.Thread(target=frame_loop)
+    t2.start()
+    t3.start()
+    while not quit_event.is_set():
+        avatar.asr.run_step()
+    stop2.set()
+    t2.join()
+    stop3.set()
+    t3.join()

@@ -51,7 +51,15 @@ def test_wav2lip_pack_round_trip(tmp_path):
     for i in range(5):
         assert np.array_equal(fr[i], d_frames[i]) and np.array_equal(fa[i], d_faces[i])
         assert tuple(co[i]) == tuple(d_coords[i])                         # (y1, y2, x1, x2) order kept
-    assert not fr[0].flags.writeable                                      # shared, read-only views (app.py:86-91)
+    # the host's frame list must be WRITABLE: on silent frames the reference draws its watermark straight into
+    # frame_list_cycle[idx] (avatars/base_avatar.py:417, 449) and OpenCV rejects read-only arrays.  Copy-on-write mapping:
+    # the write is private, the file (and the read-only section that feeds the GPU upload) stays intact.
+    assert fr[0].flags.writeable and not fa[0].flags.writeable
+    before = fr[0].copy()
+    cv2.putText(fr[0], "LiveTalking", (10, 20), cv2.FONT_HERSHEY_SIMPLEX, 0.3, (128, 128, 128), 1)
+    assert not np.array_equal(fr[0], before)
+    assert np.array_equal(p.sections["frames"][0], before)
+    assert np.array_equal(AP.load_packed(out, verify=True).wav2lip_lists()[0][0], before)
     for name, arr in p.sections.items():
         if isinstance(arr, np.memmap):
             assert arr.offset % AP.ALIGN == 0, name
