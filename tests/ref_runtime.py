@@ -152,4 +152,8 @@ def feed_bursts(avatar, bursts, chunk=320, seed=0, gap_s=0.25):
             data = (tone + 0.05 * rng.standard_normal(chunk)).astype(np.float32)
             avatar.put_audio_frame(data, {"cid": cid})
             cid += 1
-        time.sleep(gap_s)
+        asr = getattr(avatar, "asr", None) or avatar.avatar.asr
+        t0 = time.time()
+        while not asr.queue.empty() and time.time() - t0 < 30:      # let the session drain the burst, however loaded the box is ...
+            time.sleep(0.01)
+        time.sleep(gap_s)                                            # ... then stay silent for a while
