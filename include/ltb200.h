@@ -58,6 +58,8 @@ int ltb_w2l_avatar_destroy(ltb_w2l_avatar* a);
 #define LTB_SESSION_NO_GRAPH 2    /* launch kernels eagerly instead of replaying a CUDA graph */
 #define LTB_SESSION_NO_HALO 4     /* route every conv to the generic gather kernel (A/B testing of the TMA halo kernel) */
 #define LTB_SESSION_NO_PDL 8      /* launch the conv kernels without programmatic dependent launch (A/B testing) */
+#define LTB_SESSION_SLOTS 16      /* cross-session batch: per-slot avatar / index / mel (ltb_w2l_infer_slots) */
+#define LTB_SESSION_MEL_ONLY 32   /* feature extractor only (ltb_w2l_mel_step): no activation arena / plan / graphs */
 /* replaces LipReal.__init__ (avatars/wav2lip_avatar.py:101-114) + warm_up (:90-96): allocates the activation
  * arena for `batch` frames, builds the layer plan and (unless NO_GRAPH) captures it into a CUDA graph.
  * stride_left/right = opt.l / opt.r (20 ms chunks), fps = opt.fps. */
@@ -90,6 +92,19 @@ int ltb_w2l_paste_pred(ltb_w2l_session* s, const float* pred, int idx, uint8_t* 
 /* all `batch` frames of the last infer at once (frame i uses mirror_index(n, index+i), utils/image.py:26-32).
  * out_frames: uint8 [batch,H,W,3] host buffer (pinned recommended) or NULL to keep them on the device. */
 int ltb_w2l_paste_batch(ltb_w2l_session* s, int index, uint8_t* out_frames);
+
+/* Cross-session batching (app.py:76-100 runs up to max_session sessions against one shared model): ONE
+ * forward + paste launch whose `batch` slots carry frames of DIFFERENT sessions.  The session must have been created with
+ * LTB_SESSION_SLOTS (its own avatar only fixes the frame size H x W; every slot's avatar must have the same size and live
+ * on the same device).  Slot i: face / frame / rectangle of avatar->frame idx (the caller applies mirror_index,
+ * utils/image.py:26-32) and the (80,16) mel window MelASR queued for that frame.  out_frames: uint8 [nslots,H,W,3] host
+ * buffer.  Replaces nslots/B calls of inference_batch + nslots calls of paste_back_frame.  Synchronous. */
+typedef struct ltb_w2l_slot {
+  ltb_w2l_avatar* avatar;
+  int idx;
+  const float* mel;   /* host float32 [80,16] */
+} ltb_w2l_slot;
+int ltb_w2l_infer_slots(ltb_w2l_session* s, const ltb_w2l_slot* slots, int nslots, uint8_t* out_frames);
 
 /* mel windows from the PCM buffer already resident on the device (uploaded by ltb_w2l_set_pcm):
  * the device-resident form of MelASR.run_step's feature extraction.  Asynchronous. */

@@ -12,6 +12,8 @@ LTB_SESSION_KEEP_LAYERS = 1
 LTB_SESSION_NO_GRAPH = 2
 LTB_SESSION_NO_HALO = 4
 LTB_SESSION_NO_PDL = 8
+LTB_SESSION_SLOTS = 16
+LTB_SESSION_MEL_ONLY = 32
 
 
 class LtbError(RuntimeError):
@@ -30,6 +32,10 @@ class ConvOp(C.Structure):
 class MtPasteOp(C.Structure):
     _fields_ = ([(n, C.c_void_p) for n in ("frames", "coords", "crop", "masks", "mask_off", "pred", "out")] +
                 [(n, C.c_int) for n in ("nf", "H", "W", "index", "explicit_idx", "slot0", "count", "pred_hw")])
+
+
+class W2LSlot(C.Structure):
+    _fields_ = [("avatar", C.c_void_p), ("idx", C.c_int), ("mel", C.c_void_p)]
 
 
 class ConvDesc(C.Structure):
@@ -58,6 +64,7 @@ _SIGS = {
     "ltb_w2l_paste": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ltb_w2l_paste_pred": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ltb_w2l_paste_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "ltb_w2l_infer_slots": (C.c_int, [C.c_void_p, C.POINTER(W2LSlot), C.c_int, C.c_void_p]),
     "ltb_w2l_mel_resident": (C.c_int, [C.c_void_p]),
     "ltb_w2l_step_async": (C.c_int, [C.c_void_p, C.c_int]),
     "ltb_w2l_forward_async": (C.c_int, [C.c_void_p, C.c_int]),

@@ -550,6 +550,23 @@ bool conv_halo_supported(const ConvParams& p) {
   return get_encode() != nullptr;
 }
 
+// Narrow 3x3 layers (Cout = 32 / 64, one N tile) go to the y-stacked kernel (conv_ystack.cu: N = 3*BN per instruction) when
+// the two overlap rows per tile cost at most 35 % extra MMA rows.  LTB_NO_YSTACK=1 keeps them on the halo kernel (A/B tests).
+static bool pick_ystack(const ConvParams& p, int* BN, int* NSUB) {
+  static const bool off = [] {
+    const char* e = std::getenv("LTB_NO_YSTACK");
+    return e && e[0] && e[0] != '0';
+  }();
+  if (off || !is_conv3x3(p) || (p.Cout != 32 && p.Cout != 64) || p.zbatch > 1) return false;
+  const int nsub = p.Cout == 32 ? 2 : 1;
+  const int valid = 16 * nsub - 2;
+  const int tiles_y = (p.GH + valid - 1) / valid;
+  if (tiles_y * 16 * nsub > (p.GH * 135) / 100) return false;
+  *BN = p.Cout;
+  *NSUB = nsub;
+  return true;
+}
+
 // picks (BN, NSUB, NACC) ; returns false if unsupported
 static bool pick_cfg(const ConvParams& p, int* BN, int* NSUB, int* NACC) {
   if (is_gemm(p)) {
@@ -604,6 +621,8 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
   std::memset(&h, 0, sizeof(h));
   int BN, NSUB, NACC;
   if (!pick_cfg(p, &BN, &NSUB, &NACC)) return 1;
+  const bool ys = pick_ystack(p, &BN, &NSUB);
+  out->YS = ys ? 1 : 0;
   out->BN = BN;
   out->NSUB = NSUB;
   out->NACC = NACC;
@@ -625,11 +644,17 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
   {
     cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.IW, (cuuint64_t)p.IH, (cuuint64_t)p.N};
     cuuint64_t strides[3] = {(cuuint64_t)p.ICtot * 2, (cuuint64_t)p.IW * p.ICtot * 2, (cuuint64_t)p.IH * p.IW * p.ICtot * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)kHaloP, (cuuint32_t)(16 * NSUB + 2), 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)kHaloP, (cuuint32_t)(ys ? 16 * NSUB : 16 * NSUB + 2), 1};
     if (!encode(&h.tm_in, 4, p.in + p.ic_off, dims, strides, box)) return 2;
   }
   // weights: 3-D (k = Cin, n = Cout, tap = 9) view of the tap-major copy [9][Cout][Cin]
-  if (!gemm) {
+  if (ys) {
+    // 4-D (k, n, dx, dy) view of the tap-major copy [dy*3+dx][Cout][Cin]: box (64, BN, 1, 3) = the three taps of one column
+    cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, 3, 3};
+    cuuint64_t strides[3] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Cout * p.Cin * 2, (cuuint64_t)3 * p.Cout * p.Cin * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)BN, 1, 3};
+    if (!encode(&h.tm_w, 4, w_tap_major, dims, strides, box)) return 2;
+  } else if (!gemm) {
     cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, 9};
     cuuint64_t strides[2] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Cout * p.Cin * 2};
     cuuint32_t box[3] = {64, (cuuint32_t)BN, 3};
@@ -700,7 +725,8 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
     return 0;
   }
   h.tiles_x = (p.GW + 7) / 8;
-  h.tiles_y = (p.GH + 16 * NSUB - 1) / (16 * NSUB);
+  h.tile_rows = ys ? 16 * NSUB - 2 : 16 * NSUB;
+  h.tiles_y = (p.GH + h.tile_rows - 1) / h.tile_rows;
   h.total_tiles = h.tiles_x * h.tiles_y * p.N * h.tiles_n;
   return 0;
 }
@@ -724,6 +750,7 @@ cudaError_t launch_conv_halo(const HaloPlan& pl, cudaStream_t st) {
     if (sms <= 0) sms = 148;
     sms_cached.store(sms);
   }
+  if (pl.YS) return launch_conv_ystack(pl, sms, st);
   const int key = pl.BN * 100 + pl.NSUB * 10 + pl.NACC;
   if (pl.TAPS == 1) {
     switch (key) {
@@ -763,7 +790,7 @@ cudaError_t launch_conv_halo(const HaloPlan& pl, cudaStream_t st) {
 // can the epilogue of this plan accumulate GroupNorm statistics of its output?  (power-of-two channels per group >= 4,
 // whole 32-row groups inside one image)
 bool conv_halo_gn_fusable(const HaloPlan& pl, int cout_total, int groups, int hw) {
-  if (pl.NACC != 1 || groups <= 0 || cout_total % groups) return false;
+  if (pl.YS || pl.NACC != 1 || groups <= 0 || cout_total % groups) return false;
   const int cpg = cout_total / groups;
   if (cpg < 4 || (cpg & (cpg - 1))) return false;
   if (pl.TAPS == 1 && (hw % 128) != 0) return false;

@@ -38,6 +38,7 @@ struct alignas(64) HaloParams {
   FatMma fat[3][3];
   int acc_oy[4], acc_ox[4];
   int tiles_x, tiles_y, tiles_n, total_tiles;
+  int tile_rows;         // output rows per tile: 16*NSUB, or 16*NSUB - 2 for the y-stacked kernel (tiles overlap by two MMA rows)
   // optional fused GroupNorm statistics of the OUTPUT tensor (sum, sum of squares per (image, group)), accumulated by the
   // epilogue from the fp16-rounded values: saves the separate statistics pass of the following GroupNorm
   float* gn_stats;
@@ -58,12 +59,14 @@ struct alignas(64) HaloParams {
 struct HaloPlan {
   HaloParams hp;
   int BN, NSUB, NACC, TAPS;  // TAPS = 9 (3x3 conv / ConvT halo mode) or 1 (TMA GEMM mode: 1x1 conv / linear)
+  int YS;                    // 1: y-stacked narrow-layer kernel (conv_ystack.cu), tm_w is the 4-D (k, n, dx, dy) view
 };
 
 bool conv_halo_supported(const ConvParams& p);
 // w_tap_major: device pointer to the [9][Cout][Cin] copy of the layer's weights (unused in GEMM mode). returns 0 on success.
 int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan* out);
 cudaError_t launch_conv_halo(const HaloPlan& pl, cudaStream_t st);
+cudaError_t launch_conv_ystack(const HaloPlan& pl, int sms, cudaStream_t st);   // conv_ystack.cu (called by launch_conv_halo)
 bool conv_halo_gn_fusable(const HaloPlan& pl, int cout_total, int groups, int hw);
 cudaError_t launch_w_tap_major(const __half* w, __half* wt, int cout, int cin, cudaStream_t st, int ntaps = 9);
 // ConvT(k3,s2) weights: phase-major rows [Cout][9][Cin] (pack order of w2l_pack.py / pack_convT_w) -> the view-major slice

@@ -61,6 +61,14 @@ inline cudaError_t launch_kernel_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// cross-session batching: one descriptor per batch slot (device memory, rewritten before every step), so that ONE forward /
+// paste launch serves frames of different sessions (different avatars, unrelated frame indices)
+struct SlotDesc {
+  const uint8_t* face;    // u8 [256,256,3] BGR crop of this slot
+  const uint8_t* frame;   // u8 [H,W,3] full frame the prediction is pasted into
+  int y1, y2, x1, x2;     // paste rectangle (wav2lip coords.pkl order)
+};
+
 // ---- kernel launchers ----
 // splitk_ws: optional zero-initialised fp32 workspace (one per stream) enabling split-K for small-M deep-K layers
 cudaError_t launch_conv_gather(const ConvParams& p, cudaStream_t st, float* splitk_ws = nullptr, size_t splitk_ws_floats = 0);
@@ -69,7 +77,8 @@ int conv_gather_pick_bn(const ConvParams& p);
 // wav2lip-specific small kernels (w2l_small.cu)
 // faces u8 [nf,256,256,3] BGR -> padded fp16 [B,262,264,8]: ch0-2 = face/255 with rows >= 128 zeroed, ch3-5 = face/255
 // the first avatar index of the step is read from device memory (*d_index) so that a captured CUDA graph can be replayed
-cudaError_t launch_w2l_prep_faces(const uint8_t* faces, int nfaces, const int* d_index, int B, __half* img_pad, cudaStream_t st);
+cudaError_t launch_w2l_prep_faces(const uint8_t* faces, int nfaces, const int* d_index, int B, __half* img_pad, cudaStream_t st,
+                                  const SlotDesc* slots = nullptr);   // slots != nullptr: face of slot b = slots[b].face
 cudaError_t launch_set_int(int* p, int v, cudaStream_t st);
 // mel f32 [B,80,16] -> fp16 NHWC [B,80,16,32]: conv3x3 p1 (1->32) + folded BN + ReLU
 cudaError_t launch_w2l_audio_conv0(const float* mel, const float* w9x32, const float* bias, __half* out, int B, cudaStream_t st);
@@ -85,6 +94,6 @@ size_t mel_scratch_mel_doubles(int nsamp);
 // paste.cu : wav2lip paste-back for `count` frames in one launch.
 //   frame index of job i = explicit_idx (>= 0, count must be 1) or mirror_index(nf, index + i); prediction slot = slot0 + i
 cudaError_t launch_w2l_paste(const uint8_t* frames, const int* coords, int nf, int H, int W, const float* pred, int slot0,
-                             int index, int explicit_idx, int count, uint8_t* out, cudaStream_t st);
+                             int index, int explicit_idx, int count, uint8_t* out, cudaStream_t st, const SlotDesc* slots = nullptr);
 
 }  // namespace ltb

@@ -45,6 +45,7 @@ struct PasteArgs {
   int index;         // first avatar index (mirror_index applied) when explicit_idx < 0
   int explicit_idx;  // >= 0: use this frame index for the (single) job
   int slot0;         // first prediction slot
+  const SlotDesc* slots;  // != nullptr: job j pastes into slots[j].frame at slots[j]'s rectangle (cross-session batch)
 };
 
 __global__ void __launch_bounds__(256) w2l_paste_kernel(const PasteArgs a) {
@@ -52,9 +53,17 @@ __global__ void __launch_bounds__(256) w2l_paste_kernel(const PasteArgs a) {
   const int y = blockIdx.y;
   const int xg = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (xg >= a.W) return;
-  const int idx = a.explicit_idx >= 0 ? a.explicit_idx : mirror_index_p(a.nf, a.index + job);
-  const int y1 = a.coords[idx * 4 + 0], y2 = a.coords[idx * 4 + 1], x1 = a.coords[idx * 4 + 2], x2 = a.coords[idx * 4 + 3];
-  const uint8_t* frow = a.frames + ((size_t)idx * a.H + y) * a.W * 3;
+  int y1, y2, x1, x2;
+  const uint8_t* frow;
+  if (a.slots) {
+    const SlotDesc sd = a.slots[job];
+    y1 = sd.y1, y2 = sd.y2, x1 = sd.x1, x2 = sd.x2;
+    frow = sd.frame + (size_t)y * a.W * 3;
+  } else {
+    const int idx = a.explicit_idx >= 0 ? a.explicit_idx : mirror_index_p(a.nf, a.index + job);
+    y1 = a.coords[idx * 4 + 0], y2 = a.coords[idx * 4 + 1], x1 = a.coords[idx * 4 + 2], x2 = a.coords[idx * 4 + 3];
+    frow = a.frames + ((size_t)idx * a.H + y) * a.W * 3;
+  }
   uint8_t* orow = a.out + ((size_t)job * a.H + y) * a.W * 3;
   const float* pred = a.pred + (size_t)(a.slot0 + job) * 256 * 256 * 3;
   const int dw = x2 - x1, dh = y2 - y1;
@@ -115,10 +124,18 @@ __global__ void __launch_bounds__(256) w2l_paste_vec_kernel(const PasteArgs a, i
     const int xg = (gidx % groups_per_row) * 16;
     const int yj = gidx / groups_per_row;
     const int y = yj % a.H, job = yj / a.H;
-    const int idx = a.explicit_idx >= 0 ? a.explicit_idx : mirror_index_p(a.nf, a.index + job);
-    const int4 cb = __ldg(reinterpret_cast<const int4*>(a.coords) + idx);   // (y1, y2, x1, x2)
-    const int y1 = cb.x, y2 = cb.y, x1 = cb.z, x2 = cb.w;
-    const uint4* frow = reinterpret_cast<const uint4*>(a.frames + ((size_t)idx * a.H + y) * a.W * 3 + (size_t)xg * 3);
+    int y1, y2, x1, x2;
+    const uint4* frow;
+    if (a.slots) {
+      const SlotDesc sd = a.slots[job];
+      y1 = sd.y1, y2 = sd.y2, x1 = sd.x1, x2 = sd.x2;
+      frow = reinterpret_cast<const uint4*>(sd.frame + (size_t)y * a.W * 3 + (size_t)xg * 3);
+    } else {
+      const int idx = a.explicit_idx >= 0 ? a.explicit_idx : mirror_index_p(a.nf, a.index + job);
+      const int4 cb = __ldg(reinterpret_cast<const int4*>(a.coords) + idx);   // (y1, y2, x1, x2)
+      y1 = cb.x, y2 = cb.y, x1 = cb.z, x2 = cb.w;
+      frow = reinterpret_cast<const uint4*>(a.frames + ((size_t)idx * a.H + y) * a.W * 3 + (size_t)xg * 3);
+    }
     uint4* orow = reinterpret_cast<uint4*>(a.out + ((size_t)job * a.H + y) * a.W * 3 + (size_t)xg * 3);
     uint32_t w[12];
 #pragma unroll
@@ -181,8 +198,9 @@ __global__ void __launch_bounds__(256) w2l_paste_vec_kernel(const PasteArgs a, i
 }
 
 cudaError_t launch_w2l_paste(const uint8_t* frames, const int* coords, int nf, int H, int W, const float* pred, int slot0,
-                             int index, int explicit_idx, int count, uint8_t* out, cudaStream_t st) {
+                             int index, int explicit_idx, int count, uint8_t* out, cudaStream_t st, const SlotDesc* slots) {
   PasteArgs a;
+  a.slots = slots;
   a.frames = frames;
   a.coords = coords;
   a.pred = pred;

@@ -258,6 +258,9 @@ struct ltb_w2l_session {
   bool copied_valid[2] = {false, false};
   unsigned e2e_seq = 0;
   int* d_index = nullptr;
+  SlotDesc* d_slots = nullptr;      // LTB_SESSION_SLOTS: per-slot (face, frame, rectangle) descriptors, rewritten before every step
+  float* h_mel_stage = nullptr;     // pinned staging for the B mel windows of a cross-session batch
+  SlotDesc* h_slots = nullptr;      // pinned staging for the descriptors
   float* splitk_ws[2] = {nullptr, nullptr};  // one fp32 split-K workspace per stream (main, audio branch)
   std::vector<Op> ops;
   std::vector<HaloPlan> halo_plans;
@@ -668,7 +671,7 @@ static int run_ops(ltb_w2l_session* s, bool with_mel, cudaEvent_t* events = null
     cudaError_t e = cudaSuccess;
     switch (o.type) {
       case 0: e = launch_conv_gather(o.cp, st, s->splitk_ws[st == s->st2 ? 1 : 0], kSplitKFloats); break;
-      case 1: e = launch_w2l_prep_faces(s->a->faces, s->a->n, s->d_index, s->B, s->img_pad, st); break;
+      case 1: e = launch_w2l_prep_faces(s->a->faces, s->a->n, s->d_index, s->B, s->img_pad, st, s->d_slots); break;
       case 2: e = launch_w2l_audio_conv0(s->mel, s->m->w0, s->m->bias[0], o.cp.out, s->B, st); break;
       case 3: e = launch_w2l_head(o.cp.in, s->m->head_w, s->m->head_b, s->pred, s->B * 65536, st); break;
       case 4: e = launch_conv_halo(s->halo_plans[o.halo], st); break;
@@ -847,6 +850,8 @@ int ltb_w2l_session_destroy(ltb_w2l_session* s) {
   if (s->gexec_mel) cudaGraphExecDestroy(s->gexec_mel);
   if (s->graph_mel) cudaGraphDestroy(s->graph_mel);
   for (void* p : s->allocs) cudaFree(p);
+  if (s->h_slots) cudaFreeHost(s->h_slots);
+  if (s->h_mel_stage) cudaFreeHost(s->h_mel_stage);
   if (s->st_copy) cudaStreamSynchronize(s->st_copy);
   for (int i = 0; i < 2; ++i) {
     if (s->ev_paste[i]) cudaEventDestroy(s->ev_paste[i]);
@@ -888,11 +893,25 @@ int ltb_w2l_session_create(ltb_w2l_model* m, ltb_w2l_avatar* a, int batch, int s
       cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess)
     return bail(LTB_FAIL("event create failed"));
   void* p;
+  s->pcm_cap = (stride_left + stride_right + 2 * batch) * 320;
+  if (flags & LTB_SESSION_MEL_ONLY) {
+    // feature extractor only (sessions whose frames are produced by a shared cross-session batch): no activation arena, no
+    // layer plan, no graphs — a few hundred KB instead of ~0.9 GB
+    if (dev_alloc(s, (size_t)batch * 80 * 16 * 4, &p, true)) return bail(1);
+    s->asr_mel = static_cast<float*>(p);
+    if (dev_alloc(s, (size_t)s->pcm_cap * 4, &p, true)) return bail(1);
+    s->asr_pcm = static_cast<float*>(p);
+    if (dev_alloc(s, mel_scratch_spec_doubles(s->pcm_cap) * 8, &p, true)) return bail(1);
+    s->asr_spec = static_cast<double*>(p);
+    if (dev_alloc(s, mel_scratch_mel_doubles(s->pcm_cap) * 8, &p, true)) return bail(1);
+    s->asr_melf = static_cast<double*>(p);
+    *out = s;
+    return 0;
+  }
   if (dev_alloc(s, (size_t)batch * 262 * 264 * 8 * 2, &p, true)) return bail(1);
   s->img_pad = static_cast<__half*>(p);
   if (dev_alloc(s, (size_t)batch * 80 * 16 * 4, &p, true)) return bail(1);
   s->mel = static_cast<float*>(p);
-  s->pcm_cap = (stride_left + stride_right + 2 * batch) * 320;
   if (dev_alloc(s, (size_t)s->pcm_cap * 4, &p, true)) return bail(1);
   s->pcm = static_cast<float*>(p);
   if (dev_alloc(s, mel_scratch_spec_doubles(s->pcm_cap) * 8, &p, true)) return bail(1);
@@ -915,6 +934,18 @@ int ltb_w2l_session_create(ltb_w2l_model* m, ltb_w2l_avatar* a, int batch, int s
   s->frames_out = static_cast<uint8_t*>(p);
   if (dev_alloc(s, 256, &p, true)) return bail(1);
   s->d_index = static_cast<int*>(p);
+  if (flags & LTB_SESSION_SLOTS) {
+    // every slot starts on the session avatar's frame 0 (the warm-up pass and the graph capture read the table)
+    if (dev_alloc(s, (size_t)batch * sizeof(SlotDesc), &p, true)) return bail(1);
+    s->d_slots = static_cast<SlotDesc*>(p);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&s->h_slots), (size_t)batch * sizeof(SlotDesc), cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc(reinterpret_cast<void**>(&s->h_mel_stage), (size_t)batch * 1280 * sizeof(float), cudaHostAllocDefault) != cudaSuccess)
+      return bail(LTB_FAIL("pinned staging allocation failed"));
+    for (int i = 0; i < batch; ++i)
+      s->h_slots[i] = SlotDesc{a->faces, a->frames, a->coords_host[0], a->coords_host[1], a->coords_host[2], a->coords_host[3]};
+    if (cudaMemcpy(s->d_slots, s->h_slots, (size_t)batch * sizeof(SlotDesc), cudaMemcpyHostToDevice) != cudaSuccess)
+      return bail(LTB_FAIL("slot table upload failed"));
+  }
   for (int i = 0; i < 2; ++i) {
     if (dev_alloc(s, kSplitKFloats * sizeof(float), &p, true)) return bail(1);
     s->splitk_ws[i] = static_cast<float*>(p);
@@ -986,6 +1017,7 @@ int ltb_w2l_mel_step(ltb_w2l_session* s, const float* pcm, int nsamples, float* 
 
 int ltb_w2l_set_pcm(ltb_w2l_session* s, const float* pcm, int nsamples) {
   if (!s || !pcm) return LTB_FAIL("null argument");
+  if (s->ops.empty()) return LTB_FAIL("this session was created with LTB_SESSION_MEL_ONLY: it has no network");
   const int expect = (s->l + s->r + 2 * s->B) * 320;
   if (nsamples != expect) return LTB_FAIL("set_pcm: expected " + std::to_string(expect) + " samples, got " + std::to_string(nsamples));
   if (enter(s)) return 1;
@@ -997,6 +1029,7 @@ int ltb_w2l_set_pcm(ltb_w2l_session* s, const float* pcm, int nsamples) {
 
 static int forward_enqueue(ltb_w2l_session* s, int index, bool with_mel) {
   if (index < 0) return LTB_FAIL("negative index");
+  if (s->ops.empty()) return LTB_FAIL("this session was created with LTB_SESSION_MEL_ONLY: it has no network");
   if (launch_set_int(s->d_index, index, s->st) != cudaSuccess) return LTB_FAIL("set_int launch failed");
   if (s->gexec) {
     LTB_CUDA(cudaGraphLaunch(with_mel ? s->gexec_mel : s->gexec, s->st));
@@ -1020,6 +1053,7 @@ int ltb_w2l_infer(ltb_w2l_session* s, int index, const float* mel, float* pred_o
 
 int ltb_w2l_paste(ltb_w2l_session* s, int slot, int idx, uint8_t* out_frame) {
   if (!s || !out_frame) return LTB_FAIL("null argument");
+  if (s->ops.empty()) return LTB_FAIL("this session was created with LTB_SESSION_MEL_ONLY: it has no network");
   if (slot < 0 || slot >= s->B) return LTB_FAIL("paste: slot out of range");
   if (idx < 0 || idx >= s->a->n) return LTB_FAIL("paste: idx out of range");
   if (enter(s)) return 1;
@@ -1036,6 +1070,7 @@ int ltb_w2l_paste(ltb_w2l_session* s, int slot, int idx, uint8_t* out_frame) {
 
 int ltb_w2l_paste_pred(ltb_w2l_session* s, const float* pred, int idx, uint8_t* out_frame) {
   if (!s || !pred || !out_frame) return LTB_FAIL("null argument");
+  if (s->ops.empty()) return LTB_FAIL("this session was created with LTB_SESSION_MEL_ONLY: it has no network");
   if (idx < 0 || idx >= s->a->n) return LTB_FAIL("paste: idx out of range");
   if (enter(s)) return 1;
   std::lock_guard<std::mutex> lk(s->mu);
@@ -1060,6 +1095,7 @@ static int paste_batch_enqueue(ltb_w2l_session* s, int index, uint8_t* dst = nul
 
 int ltb_w2l_paste_batch(ltb_w2l_session* s, int index, uint8_t* out_frames) {
   if (!s) return LTB_FAIL("null session");
+  if (s->ops.empty()) return LTB_FAIL("this session was created with LTB_SESSION_MEL_ONLY: it has no network");
   if (index < 0) return LTB_FAIL("negative index");
   if (enter(s)) return 1;
   std::lock_guard<std::mutex> lk(s->mu);
@@ -1071,8 +1107,41 @@ int ltb_w2l_paste_batch(ltb_w2l_session* s, int index, uint8_t* out_frames) {
   return 0;
 }
 
+int ltb_w2l_infer_slots(ltb_w2l_session* s, const ltb_w2l_slot* slots, int nslots, uint8_t* out_frames) {
+  if (!s || !slots || !out_frames) return LTB_FAIL("null argument");
+  if (!s->d_slots) return LTB_FAIL("infer_slots: session was not created with LTB_SESSION_SLOTS");
+  if (nslots < 1 || nslots > s->B) return LTB_FAIL("infer_slots: 1 <= nslots <= batch");
+  const int H = s->a->H, W = s->a->W;
+  for (int i = 0; i < nslots; ++i) {
+    const ltb_w2l_avatar* a = slots[i].avatar;
+    if (!a || !slots[i].mel) return LTB_FAIL("infer_slots: slot " + std::to_string(i) + " has a null avatar / mel");
+    if (a->device != s->m->device) return LTB_FAIL("infer_slots: avatar lives on another device");
+    if (a->H != H || a->W != W) return LTB_FAIL("infer_slots: all avatars of a batch must share the frame size of the session's avatar");
+    if (slots[i].idx < 0 || slots[i].idx >= a->n) return LTB_FAIL("infer_slots: frame index out of range");
+  }
+  if (enter(s)) return 1;
+  std::lock_guard<std::mutex> lk(s->mu);
+  for (int i = 0; i < s->B; ++i) {
+    const ltb_w2l_slot& q = slots[i < nslots ? i : nslots - 1];   // unused slots repeat the last request (results discarded)
+    const ltb_w2l_avatar* a = q.avatar;
+    const int* c = &a->coords_host[(size_t)q.idx * 4];
+    s->h_slots[i] = SlotDesc{a->faces + (size_t)q.idx * 65536 * 3, a->frames + (size_t)q.idx * H * W * 3, c[0], c[1], c[2], c[3]};
+    std::memcpy(s->h_mel_stage + (size_t)i * 1280, q.mel, 1280 * sizeof(float));
+  }
+  LTB_CUDA(cudaMemcpyAsync(s->d_slots, s->h_slots, (size_t)s->B * sizeof(SlotDesc), cudaMemcpyHostToDevice, s->st));
+  LTB_CUDA(cudaMemcpyAsync(s->mel, s->h_mel_stage, (size_t)s->B * 1280 * 4, cudaMemcpyHostToDevice, s->st));
+  if (forward_enqueue(s, 0, false)) return 1;
+  cudaError_t e = launch_w2l_paste(nullptr, nullptr, 0, H, W, s->pred, 0, 0, -1, nslots, s->frames_out, s->st, s->d_slots);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("paste kernel: ") + cudaGetErrorString(e));
+  s->launches += 1;
+  LTB_CUDA(cudaMemcpyAsync(out_frames, s->frames_out, (size_t)nslots * H * W * 3, cudaMemcpyDeviceToHost, s->st));
+  LTB_CUDA(cudaStreamSynchronize(s->st));
+  return 0;
+}
+
 int ltb_w2l_mel_resident(ltb_w2l_session* s) {
   if (!s) return LTB_FAIL("null session");
+  if (s->ops.empty()) return LTB_FAIL("this session was created with LTB_SESSION_MEL_ONLY: it has no network");
   if (enter(s)) return 1;
   std::lock_guard<std::mutex> lk(s->mu);
   cudaError_t e = launch_mel_step(s->pcm, s->pcm_cap, s->B, s->l, s->fps, s->mel_spec, s->mel_mel, s->mel, s->st);

@@ -21,12 +21,17 @@ constexpr int kPadW = 264;  // 256 + 3 + 5 (row pitch multiple of 8 pixels)
 
 __global__ void __launch_bounds__(256) w2l_prep_faces_kernel(const uint8_t* __restrict__ faces, int nfaces,
                                                              const int* __restrict__ d_index,
-                                                             __half* __restrict__ img_pad) {
+                                                             __half* __restrict__ img_pad, const SlotDesc* __restrict__ slots) {
   const int b = blockIdx.y;
   const int pix = blockIdx.x * 256 + threadIdx.x;  // 0..65535
   const int y = pix >> 8, x = pix & 255;
-  const int fidx = mirror_index_dev(nfaces, __ldg(d_index) + b);
-  const uint8_t* src = faces + ((size_t)fidx * 65536 + pix) * 3;
+  const uint8_t* src;
+  if (slots) {   // cross-session batch: every slot names its own face crop
+    src = slots[b].face + (size_t)pix * 3;
+  } else {
+    const int fidx = mirror_index_dev(nfaces, __ldg(d_index) + b);
+    src = faces + ((size_t)fidx * 65536 + pix) * 3;
+  }
   const float inv = 1.0f / 255.0f;
   const float c0 = src[0] * inv, c1 = src[1] * inv, c2 = src[2] * inv;
   const bool upper = y < 128;  // img_masked[:, face.shape[0]//2:] = 0
@@ -41,9 +46,9 @@ __global__ void __launch_bounds__(256) w2l_prep_faces_kernel(const uint8_t* __re
 }
 
 cudaError_t launch_w2l_prep_faces(const uint8_t* faces, int nfaces, const int* d_index, int B, __half* img_pad,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, const SlotDesc* slots) {
   dim3 grid(256, B);
-  w2l_prep_faces_kernel<<<grid, 256, 0, st>>>(faces, nfaces, d_index, img_pad);
+  w2l_prep_faces_kernel<<<grid, 256, 0, st>>>(faces, nfaces, d_index, img_pad, slots);
   return cudaGetLastError();
 }
 

@@ -118,11 +118,13 @@ class W2LSession:
     """One avatar stream: activation arena + stream + layer plan for a fixed batch size."""
 
     def __init__(self, model: W2LModel, avatar: W2LAvatar, batch: int, stride_left: int = 10, stride_right: int = 10,
-                 fps: int = 25, keep_layers: bool = False, no_graph: bool = False, no_halo: bool = False, no_pdl: bool = False):
+                 fps: int = 25, keep_layers: bool = False, no_graph: bool = False, no_halo: bool = False, no_pdl: bool = False,
+                 slots: bool = False, mel_only: bool = False):
         self.model, self.avatar = model, avatar
         self.batch, self.l, self.r, self.fps = int(batch), int(stride_left), int(stride_right), int(fps)
         flags = ((_capi.LTB_SESSION_KEEP_LAYERS if keep_layers else 0) | (_capi.LTB_SESSION_NO_GRAPH if no_graph else 0) |
-                 (_capi.LTB_SESSION_NO_HALO if no_halo else 0) | (_capi.LTB_SESSION_NO_PDL if no_pdl else 0))
+                 (_capi.LTB_SESSION_NO_HALO if no_halo else 0) | (_capi.LTB_SESSION_NO_PDL if no_pdl else 0) |
+                 (_capi.LTB_SESSION_SLOTS if slots else 0) | (_capi.LTB_SESSION_MEL_ONLY if mel_only else 0))
         self._h = C.c_void_p()
         check(lib().ltb_w2l_session_create(model._h, avatar._h, self.batch, self.l, self.r, self.fps, flags,
                                            C.byref(self._h)))
@@ -170,6 +172,23 @@ class W2LSession:
         if to_host and out is None:
             out = np.empty((self.batch, self.avatar.H, self.avatar.W, 3), np.uint8)
         check(lib().ltb_w2l_paste_batch(self._h, int(index), _ptr(out) if to_host else None))
+        return out
+
+    def infer_slots(self, requests, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Cross-session batch: requests = [(W2LAvatar, frame_idx, mel (80,16) float32), ...] (1..batch of them, any mix of
+        avatars of this session's frame size) -> composited frames uint8 (n, H, W, 3).  One forward + paste launch."""
+        n = len(requests)
+        arr = (_capi.W2LSlot * n)()
+        keep = []
+        for i, (av, idx, mel) in enumerate(requests):
+            m = _carr(mel, np.float32)
+            if m.size != 1280:
+                raise ValueError(f"slot {i}: mel window must be (80,16), got {m.shape}")
+            keep.append(m)
+            arr[i].avatar, arr[i].idx, arr[i].mel = av._h, int(idx), m.ctypes.data_as(C.c_void_p)
+        if out is None:
+            out = np.empty((n, self.avatar.H, self.avatar.W, 3), np.uint8)
+        check(lib().ltb_w2l_infer_slots(self._h, arr, n, _ptr(out)))
         return out
 
     def mel_resident(self) -> None:

@@ -11,6 +11,11 @@ By default the per-frame result is an opaque ``EngineFrame`` (the reference trea
 base_avatar.py:374-376, 433): the whole batch is composited on the GPU right after the forward pass and copied back
 once; ``paste_back_frame`` then only hands out the finished frame.  With ``opt.ltb_return_pred = True`` the plugin
 returns the reference's exact data instead (float32 (B,256,256,3) predictions; paste on demand).
+
+Cross-session batching (``opt.ltb_cross_session = True`` or ``LTB_CROSS_SESSION=1``): the session owns no network; its
+frames are slot requests to a scheduler shared by all sessions of the model (plugin/batcher.py), which packs up to
+``LTB_MUX_BATCH`` (16) frames of different sessions into one forward + paste launch.  The session's own ``batch_size`` can
+then be small (low latency) without under-filling the GPU.
 """
 from __future__ import annotations
 
@@ -21,6 +26,7 @@ import pickle
 import numpy as np
 
 from .. import avatar_pack, engine
+from .batcher import CrossSessionBatcher
 from .mel_asr import MelASR
 
 try:
@@ -82,6 +88,22 @@ def warm_up(batch_size, model, modelres):
     logger.info("warmup model... (engine sessions warm up at creation)")
 
 
+_BATCHER_LOCK = __import__("threading").Lock()
+
+
+def shared_batcher(model, eng_avatar) -> CrossSessionBatcher:
+    """One scheduler per (model, frame size): created by the first session that asks, shared by all later ones."""
+    with _BATCHER_LOCK:
+        table = getattr(model, "_ltb_batchers", None)
+        if table is None:
+            table = model._ltb_batchers = {}
+        key = (eng_avatar.H, eng_avatar.W)
+        if key not in table:
+            mux = engine.W2LSession(model, eng_avatar, int(os.environ.get("LTB_MUX_BATCH", "16")), slots=True)
+            table[key] = CrossSessionBatcher(mux, float(os.environ.get("LTB_MUX_WAIT_MS", "4")))
+        return table[key]
+
+
 @register("avatar", "wav2lip")
 class LipReal(BaseAvatar):
     def __init__(self, opt, model, avatar):
@@ -92,18 +114,29 @@ class LipReal(BaseAvatar):
         if eng_avatar is None:   # a plain tuple from somewhere else: upload now
             eng_avatar = engine.W2LAvatar(self.face_list_cycle, self.frame_list_cycle, self.coord_list_cycle)
         self._engine_avatar = eng_avatar
-        self.engine_session = engine.W2LSession(model, eng_avatar, self.batch_size, opt.l, opt.r, opt.fps)
         self._return_pred = bool(getattr(opt, "ltb_return_pred", False))
+        cross = bool(getattr(opt, "ltb_cross_session", False)) or os.environ.get("LTB_CROSS_SESSION", "0") == "1"
+        self._batcher = None
+        if cross and not self._return_pred:
+            self._batcher = shared_batcher(model, eng_avatar)
+            # feature extractor only: the forward pass of this session's frames runs in the shared cross-session batch
+            self.engine_session = engine.W2LSession(model, eng_avatar, self.batch_size, opt.l, opt.r, opt.fps, mel_only=True)
+        else:
+            self.engine_session = engine.W2LSession(model, eng_avatar, self.batch_size, opt.l, opt.r, opt.fps)
         self.asr = MelASR(opt, self, self.engine_session)
         self.asr.warm_up()
 
     def inference_batch(self, index, audiofeat_batch):
         mel = np.asarray(audiofeat_batch, dtype=np.float32)                      # (B, 80, 16)
+        length = len(self.face_list_cycle)
+        if self._batcher is not None:
+            idxs = [mirror_index(length, index + i) for i in range(self.batch_size)]
+            frames = self._batcher.submit([(self._engine_avatar, idxs[i], mel[i]) for i in range(self.batch_size)])
+            return [EngineFrame(frames[i], idxs[i]) for i in range(self.batch_size)]
         if self._return_pred:
             return self.engine_session.infer(index, mel, want_pred=True)        # float32 (B,256,256,3), as the reference
         self.engine_session.infer(index, mel, want_pred=False)
         frames = self.engine_session.paste_batch(index)                          # (B,H,W,3) uint8, one D2H
-        length = len(self.face_list_cycle)
         return [EngineFrame(frames[i], mirror_index(length, index + i)) for i in range(self.batch_size)]
 
     def paste_back_frame(self, pred_frame, idx: int):

@@ -56,6 +56,7 @@ class FakeSession:
     def __init__(self, model, avatar, batch, l=10, r=10, fps=25, **kw):
         self.avatar, self.batch, self.l, self.r, self.fps = avatar, batch, l, r, fps
         self._pred = None
+        self.slot_batches = []
         self._mu = threading.Lock()
         self.concurrent_mel_during_infer = 0
         self._in_infer = False
@@ -88,6 +89,15 @@ class FakeSession:
     def paste_pred(self, pred, idx, out=None):
         from oracle import paste_ref as P
         return P.w2l_paste_back(np.asarray(pred, np.float32), self.avatar.frames[idx], self.avatar.coords[idx])
+
+    def infer_slots(self, requests, out=None):
+        """cross-session batch (engine.W2LSession.infer_slots): every slot names its own avatar / frame / mel window"""
+        from oracle import paste_ref as P
+        assert 1 <= len(requests) <= self.batch
+        time.sleep(0.004)
+        self.slot_batches.append(len({id(av) for av, _i, _m in requests}))
+        return np.stack([P.w2l_paste_back(fake_net(av.faces[idx], np.asarray(mel, np.float32).reshape(80, 16)), av.frames[idx], av.coords[idx])
+                         for av, idx, mel in requests])
 
     def close(self):
         pass
@@ -236,3 +246,58 @@ def test_silent_frames_of_a_packed_avatar_take_the_watermark(tmp_path, monkeypat
         assert len(sink.frames) >= 2 * B, "process_frames died on the first silent frame"
         for j, f in enumerate(sink.frames[:2 * B]):
             assert np.array_equal(f, watermark(frames[rt.mirror_index(N_AV, j)].copy()))
+
+
+def test_cross_session_batching_under_the_real_render_loops(tmp_path, monkeypatch):
+    """SURVEY §8 f1: three sessions, each with the reference's own three threads, share ONE forward launch per batch of slots;
+    every session still gets exactly its own frames."""
+    import types
+    n_sess = 3
+    assets = [make_assets(10 + s) for s in range(n_sess)]
+    pristine = [[f.copy() for f in a[1]] for a in assets]
+    with RR.reference_runtime(str(tmp_path)) as rt:
+        from livetalking_b200 import engine
+        monkeypatch.setattr(engine, "W2LSession", FakeSession)
+        monkeypatch.setattr(engine, "W2LAvatar", FakeAvatar)
+        monkeypatch.setenv("LTB_MUX_BATCH", "8")
+        model = types.SimpleNamespace()                            # shared by the sessions, as app.py:99 shares the model
+        avatars, sinks, pulled = [], [], []
+        for s in range(n_sess):
+            faces, frames, coords = assets[s]
+            opt = RR.make_opt(batch_size=2, ltb_cross_session=True, sessionid=s)
+            av = rt.registry.create("avatar", "wav2lip", opt=opt, model=model, avatar=rt.plugin_w2l.make_avatar(frames, faces, coords))
+            sink = RR.RecordingSink()
+            av.output, av.tts = sink, RR.NullTTS()
+            log = [rt.AudioFrameData(data=np.zeros(320, np.float32), type=1, userdata={}) for _ in range(20)]
+            RR.spy_audio_frames(av.asr, log)
+            avatars.append(av)
+            sinks.append(sink)
+            pulled.append(log)
+        batcher = avatars[0]._batcher
+        assert batcher is not None and all(a._batcher is batcher for a in avatars)
+        quit_event = threading.Event()
+        renders = [threading.Thread(target=a.render, args=(quit_event,)) for a in avatars]
+        feeders = [threading.Thread(target=RR.feed_bursts, args=(a, [60, 50], 320, 100 + i)) for i, a in enumerate(avatars)]
+        for t in renders + feeders:
+            t.start()
+        t0 = time.time()
+        while min(len(s.frames) for s in sinks) < 70 and time.time() - t0 < 120:
+            time.sleep(0.02)
+        quit_event.set()
+        for t in renders + feeders:
+            t.join(timeout=30)
+        batcher.close()
+        global B
+        old_B, B = B, 2                                            # replay_expected reads the module-level batch size
+        try:
+            for s in range(n_sess):
+                n = len(sinks[s].frames)
+                assert n >= 60
+                exp, _aud = replay_expected(pulled[s], n, assets[s][0], pristine[s], assets[s][2], fake_net)
+                for j in range(min(n, len(exp))):
+                    assert np.array_equal(sinks[s].frames[j], exp[j]), f"session {s} frame {j}"
+        finally:
+            B = old_B
+        mux = batcher.mux
+        assert max(mux.slot_batches) >= 2, "no batch ever mixed frames of different sessions"
+        assert batcher.slots > batcher.batches                      # requests were packed

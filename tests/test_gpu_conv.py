@@ -31,6 +31,13 @@ CASES = [
     (2, 8, 8, 256, 512, 3, (2, 2), 1, False, False),     # split-K with stride 2 (M = 32)
     (16, 16, 16, 768, 384, 3, (2, 2), 1, True, False),   # ConvT with 128-wide N tiles: fat-N issue splits N = 384 into 256 + 128
     (16, 32, 32, 384, 384, 3, (1, 1), 1, False, True),   # 384 channels @32x32, batch 16: the cost model picks BN=128, NSUB=1 (3 waves)
+    # y-stacked narrow-layer kernel (conv_ystack.cu): N = 3*BN per instruction, rows combined in the epilogue
+    (2, 64, 64, 64, 64, 3, (1, 1), 1, False, True),      # BN=64 NSUB=1: 5 overlapping row tiles, residual, streamed weights
+    (5, 256, 64, 64, 64, 3, (1, 1), 1, False, True),     # same, enough tiles for the weights-resident variant (19 x 8 x 5 = 760 tiles)
+    (1, 96, 40, 80, 32, 3, (1, 1), 1, False, False),     # BN=32 NSUB=2: 80 -> 32 (ragged second K chunk), rows cross the sub-tile boundary
+    (3, 128, 128, 32, 32, 3, (1, 1), 1, False, True),    # 32 -> 32 + residual @128: resident weights, 5 row tiles of 30
+    (2, 50, 21, 64, 64, 3, (1, 1), 1, False, False),     # ragged height and width: masked last row tile / column tile
+    (4, 256, 256, 80, 32, 3, (1, 1), 1, False, False),   # the output conv's geometry (2 chunks resident), 9 row tiles
 ]
 
 

@@ -231,3 +231,47 @@ def test_paste_batch_and_odd_width(model):
     av.close()
     with pytest.raises(engine.LtbError):
         engine.W2LAvatar(faces, frames, [(0, 500, 0, 10)] * 3)     # bbox outside the frame
+
+
+def test_cross_session_slots_match_single_session(w2l_state_dict):
+    """ltb_w2l_infer_slots: slots carrying frames of DIFFERENT avatars in one launch.  (1) a batch whose slots
+    are one avatar's consecutive frames is bit-identical to that avatar's own session; (2) in a mixed batch every slot is
+    bit-identical to the same request in a homogeneous batch — slots do not influence each other."""
+    from livetalking_b200 import engine
+    from oracle import paste_ref as P
+    engine.set_device(0)
+    rng = np.random.default_rng(11)
+    H, W, Bm = 96, 160, 8
+    model = engine.W2LModel.from_state_dict(w2l_state_dict)
+    avs = []
+    for n in (5, 3):
+        faces = rng.integers(0, 256, (n, 256, 256, 3), dtype=np.uint8)
+        frames = rng.integers(0, 256, (n, H, W, 3), dtype=np.uint8)
+        coords = [(4 + i, 84 + i, 10 + 3 * i, 110 + 3 * i) for i in range(n)]
+        avs.append(engine.W2LAvatar(list(faces), frames, coords))
+    mels = np.clip(rng.standard_normal((Bm, 80, 16)), -4, 4).astype(np.float32)
+    own = engine.W2LSession(model, avs[0], Bm)
+    mux = engine.W2LSession(model, avs[1], Bm, slots=True)          # its own avatar only fixes the frame size
+    index = 3
+    own.infer(index, mels, want_pred=False)
+    want = own.paste_batch(index)
+    got = mux.infer_slots([(avs[0], P.mirror_index(5, index + i), mels[i]) for i in range(Bm)])
+    assert np.array_equal(got, want)
+    mixed = [(avs[i % 2], (2 * i + 1) % avs[i % 2].n, mels[i]) for i in range(Bm)]
+    got = mux.infer_slots(mixed)
+    for i in (0, 1, 4, 7):
+        solo = mux.infer_slots([mixed[i]] * Bm)
+        assert np.array_equal(got[i], solo[i]), f"slot {i} was influenced by its neighbours"
+    part = mux.infer_slots(mixed[:3])                               # partially filled batch
+    assert part.shape == (3, H, W, 3) and np.array_equal(part, got[:3])
+    with pytest.raises(Exception):
+        own.infer_slots(mixed)                                      # not a slots session
+    # a mel-only session extracts features but owns no network
+    asr = engine.W2LSession(model, avs[0], 4, mel_only=True)
+    pcm = (0.3 * rng.standard_normal((10 + 10 + 8) * 320)).astype(np.float32)
+    from oracle import mel_ref
+    np.testing.assert_allclose(asr.mel_step(pcm), mel_ref.mel_step(pcm, 4), atol=1e-5)
+    with pytest.raises(Exception):
+        asr.infer(0, np.zeros((4, 80, 16), np.float32))
+    for o in (asr, mux, own, *avs, model):
+        o.close()
