@@ -240,17 +240,6 @@ typedef struct ltb_mt_paste_op {
 } ltb_mt_paste_op;
 int ltb_op_mt_paste(ltb_ctx* c, const ltb_mt_paste_op* d);
 
-/* hardware probe (test hook): D[128x64] = A * B^T with A = 16 groups of 8 consecutive 128-byte rows of a swizzled
- * shared-memory buffer, first group at row `start_row`, groups `sbo_rows` rows apart, descriptor base_offset as given. */
-int ltb_umma_probe(const void* halo_f16, int halo_rows, const void* b_f16, int start_row, int sbo_rows, int base_offset,
-                   float* out_128x64);
-
-/* same probe for SWIZZLE_NONE K-major operands: buffer copied linearly; row m, k-chunk j (8 halves) of A is read at
- * start_bytes + (m/8)*sbo_bytes + (m%8)*16 + j*lbo_bytes — lbo_bytes = 16 makes consecutive rows overlap (im2col of an
- * 8-channel image without materialising it). */
-int ltb_umma_probe_noswz(const void* buf_f16, int buf_rows, const void* b_f16, int start_bytes, int lbo_bytes, int sbo_bytes,
-                         float* out_128x64);
-
 #ifdef __cplusplus
 }
 #endif

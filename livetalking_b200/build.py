@@ -36,8 +36,13 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; libltb200 cannot be built")
 
 
-def sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+def sources(diag: bool = False):
+    """Product sources = csrc/*.cu; csrc/diag/*.cu (hardware probes) go only into the diagnostic library."""
+    src = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    if diag:
+        d = os.path.join(CSRC, "diag")
+        src += sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(".cu"))
+    return src
 
 
 def _deps_mtime() -> float:
@@ -60,7 +65,7 @@ def build(force: bool = False, verbose: bool = False, defines=(), tag: str = "")
     hdr_mt = _deps_mtime()
     jobs = []
     objs = []
-    for src in sources():
+    for src in sources(diag=bool(tag)):
         obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_mt):
@@ -86,5 +91,8 @@ def build(force: bool = False, verbose: bool = False, defines=(), tag: str = "")
 
 
 if __name__ == "__main__":
+    if "--diag" in sys.argv:     # diagnostic library: product kernels + LTB_HALO_DIAG knock-outs + the csrc/diag probes
+        print(build(force="--force" in sys.argv, defines=("LTB_HALO_DIAG",), tag="_diag"))
+        sys.exit(0)
     path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(path)

@@ -550,14 +550,22 @@ bool conv_halo_supported(const ConvParams& p) {
   return get_encode() != nullptr;
 }
 
-// Narrow 3x3 layers (Cout = 32 / 64, one N tile) go to the y-stacked kernel (conv_ystack.cu: N = 3*BN per instruction) when
-// the two overlap rows per tile cost at most 35 % extra MMA rows.  LTB_NO_YSTACK=1 keeps them on the halo kernel (A/B tests).
+// The 32-channel output conv (80 -> 32 + fused head @256x256) goes to the y-stacked kernel (conv_ystack.cu: N = 3*BN = 96 per
+// instruction instead of nine N = 32 instructions) when the two overlap rows per tile cost at most 35 % extra MMA rows.
+// Measured on B200 (profiles/r02c_per_op.json vs r02a): 108.5 -> 93.7 us for that layer; the same trick LOSES on the 64-channel
+// layers (84 -> 157 us: three accumulators per output triple the TMEM read volume, 1536 cycles per 112-pixel tile against
+// 1116 cycles of MMAs, and the epilogue handles half as many pixels per pass) and on the 32->32 encoder convs (one ragged K
+// chunk: nothing to amortise), so those stay on the halo kernel.  LTB_YSTACK=0 disables it, LTB_YSTACK=all forces every
+// eligible narrow layer (A/B tests, tests/test_gpu_conv.py).
 static bool pick_ystack(const ConvParams& p, int* BN, int* NSUB) {
-  static const bool off = [] {
-    const char* e = std::getenv("LTB_NO_YSTACK");
-    return e && e[0] && e[0] != '0';
+  static const int mode = [] {
+    const char* e = std::getenv("LTB_YSTACK");
+    if (!e || !e[0]) return 1;
+    if (e[0] == '0') return 0;
+    return (e[0] == 'a') ? 2 : 1;
   }();
-  if (off || !is_conv3x3(p) || (p.Cout != 32 && p.Cout != 64) || p.zbatch > 1) return false;
+  if (mode == 0 || !is_conv3x3(p) || (p.Cout != 32 && p.Cout != 64) || p.zbatch > 1) return false;
+  if (mode == 1 && !(p.Cout == 32 && p.Cin > 64)) return false;
   const int nsub = p.Cout == 32 ? 2 : 1;
   const int valid = 16 * nsub - 2;
   const int tiles_y = (p.GH + valid - 1) / valid;

@@ -2,9 +2,9 @@
 // start address is NOT aligned to the 1024-byte swizzle repeat, and whose 8-row groups are SBO bytes apart with SBO not a
 // multiple of 1024?  The halo-resident 3x3 conv (conv_halo.cu) relies on the answer: it keeps ONE (TH+2)x(TW+2) input halo
 // in shared memory and addresses the nine shifted im2col views of it purely through descriptor start/SBO fields.
-#include "ltb_internal.h"
-#include "ptx_sm100.cuh"
-#include "../../include/ltb200.h"
+#include "../ltb_internal.h"
+#include "../ptx_sm100.cuh"
+#include "../../../include/ltb200_diag.h"
 
 namespace ltb {
 

@@ -1,9 +1,12 @@
-"""Hardware probe (run manually on the GPU box): unaligned-start / odd-SBO behaviour of tcgen05 smem descriptors."""
+"""Hardware probe (run manually on the GPU box): unaligned-start / odd-SBO behaviour of tcgen05 smem descriptors.
+Needs the diagnostic library: `python -m livetalking_b200.build --diag` (the probes are not part of libltb200.so)."""
 import ctypes as C
 import sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from livetalking_b200 import _capi, engine
+from livetalking_b200 import _capi
+_capi.LIB_PATH = os.path.join(os.path.dirname(_capi.LIB_PATH), "libltb200_diag.so")
+from livetalking_b200 import engine
 
 engine.set_device(0)
 lib = _capi.lib()

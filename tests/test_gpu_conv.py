@@ -31,7 +31,8 @@ CASES = [
     (2, 8, 8, 256, 512, 3, (2, 2), 1, False, False),     # split-K with stride 2 (M = 32)
     (16, 16, 16, 768, 384, 3, (2, 2), 1, True, False),   # ConvT with 128-wide N tiles: fat-N issue splits N = 384 into 256 + 128
     (16, 32, 32, 384, 384, 3, (1, 1), 1, False, True),   # 384 channels @32x32, batch 16: the cost model picks BN=128, NSUB=1 (3 waves)
-    # y-stacked narrow-layer kernel (conv_ystack.cu): N = 3*BN per instruction, rows combined in the epilogue
+    # y-stacked narrow-layer kernel (conv_ystack.cu): N = 3*BN per instruction, rows combined in the epilogue.  By default only the
+    # 80->32 geometry takes it (see pick_ystack); test_ystack_all_variants runs every case below with LTB_YSTACK=all in a subprocess
     (2, 64, 64, 64, 64, 3, (1, 1), 1, False, True),      # BN=64 NSUB=1: 5 overlapping row tiles, residual, streamed weights
     (5, 256, 64, 64, 64, 3, (1, 1), 1, False, True),     # same, enough tiles for the weights-resident variant (19 x 8 x 5 = 760 tiles)
     (1, 96, 40, 80, 32, 3, (1, 1), 1, False, False),     # BN=32 NSUB=2: 80 -> 32 (ragged second K chunk), rows cross the sub-tile boundary
@@ -187,3 +188,16 @@ def test_tma_gemm_mode_matches_torch_fp32(case):
     assert (err <= 2e-2 + 1e-2 * np.abs(ref)).all(), f"max err {err.max():.4f} at {np.unravel_index(err.argmax(), err.shape)}"
     out_g = engine.conv2d_f16(xn, w.numpy(), b.numpy(), relu=False, res=rn, force_path=1).astype(np.float32)
     assert np.abs(out - out_g).max() <= 2e-2
+
+
+def test_ystack_all_variants():
+    """conv_ystack.cu's (64,1) and (32,2) variants incl. resident / streamed weights: the geometry list above, forced with
+    LTB_YSTACK=all (the selector is read once per process, hence the subprocess)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, LTB_YSTACK="all")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_conv.py"), "-q", "-m", "gpu", "-x",
+                        "-k", "matches_torch", "-p", "no:cacheprovider"], env=env, cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
