@@ -93,6 +93,10 @@ int ltb_w2l_paste_pred(ltb_w2l_session* s, const float* pred, int idx, uint8_t* 
  * out_frames: uint8 [batch,H,W,3] host buffer (pinned recommended) or NULL to keep them on the device. */
 int ltb_w2l_paste_batch(ltb_w2l_session* s, int index, uint8_t* out_frames);
 
+/* inference_batch in the plugin's fused mode, one call: H2D of the mel windows, forward, batched paste-back, D2H of the `batch`
+ * composited frames (uint8 [batch,H,W,3]; pinned memory recommended), ONE lock / synchronise instead of two.  Synchronous. */
+int ltb_w2l_infer_paste(ltb_w2l_session* s, int index, const float* mel, uint8_t* out_frames);
+
 /* Cross-session batching (app.py:76-100 runs up to max_session sessions against one shared model): ONE
  * forward + paste launch whose `batch` slots carry frames of DIFFERENT sessions.  The session must have been created with
  * LTB_SESSION_SLOTS (its own avatar only fixes the frame size H x W; every slot's avatar must have the same size and live
@@ -152,6 +156,9 @@ typedef struct ltb_conv_desc {
 } ltb_conv_desc;
 int ltb_conv2d_f16(const ltb_conv_desc* d, const void* in_f16, const float* w_f32, const float* bias_f32,
                    const void* res_f16, void* out_f16);
+/* same, then `reps` more back-to-back launches of the same plan between two CUDA events: *ms_per_launch (kernel development aid) */
+int ltb_conv2d_f16_timed(const ltb_conv_desc* d, const void* in_f16, const float* w_f32, const float* bias_f32,
+                         const void* res_f16, void* out_f16, int reps, float* ms_per_launch);
 
 /* ==== generic device-op layer (MuseTalk path) ==========================================================================
  * The MuseTalk networks are third-party graphs the reference only wraps: diffusers.UNet2DConditionModel

@@ -20,7 +20,10 @@ int fail(const char* file, int line, const std::string& msg);
 #define LTB_CUDA(expr)                                                                         \
   do {                                                                                         \
     cudaError_t _e = (expr);                                                                   \
-    if (_e != cudaSuccess) return LTB_FAIL(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    if (_e != cudaSuccess) {                                                                   \
+      cudaGetLastError(); /* clear the (non-sticky) error: the next launch check must not see it */ \
+      return LTB_FAIL(std::string(#expr) + ": " + cudaGetErrorString(_e));                     \
+    }                                                                                          \
   } while (0)
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: configure each kernel once per device, thread-safely

@@ -18,15 +18,44 @@ namespace ltb {
 
 constexpr int kNfft = 800, kHop = 200, kBins = 401, kMels = 80, kMelStep = 16;
 
-size_t mel_scratch_spec_doubles(int nsamp) { return (size_t)(1 + nsamp / kHop) * kBins; }
-size_t mel_scratch_mel_doubles(int nsamp) { return (size_t)(1 + nsamp / kHop) * kMels; }
+// (the three-kernel version kept its spectrum / mel frames in global scratch; the fused kernel needs none)
+size_t mel_scratch_spec_doubles(int) { return 2; }
+size_t mel_scratch_mel_doubles(int) { return 2; }
 
-// one block per STFT frame
-__global__ void __launch_bounds__(256) mel_stft_kernel(const float* __restrict__ pcm, int nsamp, double* __restrict__ spec) {
+// ONE kernel for the whole front-end: one block per STFT frame t.
+//   phase 1: pre-emphasis + Hann window of the frame into shared memory, twiddle table
+//   phase 2: 401-bin DFT magnitude -> shared memory
+//   phase 3: 80 mel bands (thread m), dB, normalise, clip
+//   phase 4: the value of (band m, frame t) is written straight into every output window that contains frame t
+//            (window i covers frames [start_i, start_i + 16), start_i = int(left + i * mult), tail-clamped: mel.py:50-63)
+// Frames that no window reads exit immediately (20 of 84 at B = 16).  No global scratch, one launch instead of three.
+__global__ void __launch_bounds__(256) mel_fused_kernel(const float* __restrict__ pcm, int nsamp, const double* __restrict__ fb, int T,
+                                                        int B, double left, double mult, float* __restrict__ out) {
   __shared__ double fr[kNfft];
   __shared__ double tc[kNfft];
   __shared__ double ts[kNfft];
+  __shared__ double sp[kBins];
+  __shared__ int win_lo, win_hi;   // windows [win_lo, win_hi) may contain frame t
   const int t = blockIdx.x;
+  auto start_of = [&](int i) {
+    int s0 = (int)__dadd_rn(left, __dmul_rn((double)i, mult));
+    if (s0 + kMelStep > T) s0 = T - kMelStep;
+    return s0;
+  };
+  if (threadIdx.x == 0) {
+    int lo = B, hi = 0;
+    for (int i = 0; i < B; ++i) {
+      const int s0 = start_of(i);
+      if (t >= s0 && t < s0 + kMelStep) {
+        lo = min(lo, i);
+        hi = max(hi, i + 1);
+      }
+    }
+    win_lo = lo;
+    win_hi = hi;
+  }
+  __syncthreads();
+  if (win_lo >= win_hi) return;   // block-uniform: nobody reads this frame
   for (int i = threadIdx.x; i < kNfft; i += 256) {
     const int n = t * kHop + i - kNfft / 2;  // centre padding with zeros
     double y = 0.0;
@@ -50,37 +79,21 @@ __global__ void __launch_bounds__(256) mel_stft_kernel(const float* __restrict__
       idx += k;
       if (idx >= kNfft) idx -= kNfft;
     }
-    spec[(size_t)t * kBins + k] = sqrt(re * re + im * im);
+    sp[k] = sqrt(re * re + im * im);
   }
-}
-
-// one block per frame, one thread per mel band
-__global__ void __launch_bounds__(96) mel_fb_kernel(const double* __restrict__ spec, const double* __restrict__ fb,
-                                                    double* __restrict__ mel, int T) {
-  __shared__ double s[kBins];
-  const int t = blockIdx.x;
-  for (int i = threadIdx.x; i < kBins; i += 96) s[i] = spec[(size_t)t * kBins + i];
   __syncthreads();
   const int m = threadIdx.x;
   if (m >= kMels) return;
   const double* f = fb + (size_t)m * kBins;
   double acc = 0.0;
-  for (int k = 0; k < kBins; ++k) acc = fma(f[k], s[k], acc);
+  for (int k = 0; k < kBins; ++k) acc = fma(f[k], sp[k], acc);
   const double min_level = 1e-5;  // exp(-100/20 * ln 10)
-  double db = 20.0 * log10(fmax(min_level, acc)) - 20.0;
+  const double db = 20.0 * log10(fmax(min_level, acc)) - 20.0;
   double v = 8.0 * ((db + 100.0) / 100.0) - 4.0;
   v = fmin(4.0, fmax(-4.0, v));
-  mel[(size_t)m * T + t] = v;
-}
-
-// window slicing of MelASR.run_step (mel.py:50-63)
-__global__ void mel_window_kernel(const double* __restrict__ mel, int T, int B, double left, double mult, float* __restrict__ out) {
-  const int i = blockIdx.x;
-  int start = (int)__dadd_rn(left, __dmul_rn((double)i, mult));
-  if (start + kMelStep > T) start = T - kMelStep;
-  for (int e = threadIdx.x; e < kMels * kMelStep; e += blockDim.x) {
-    const int m = e / kMelStep, c = e % kMelStep;
-    out[((size_t)i * kMels + m) * kMelStep + c] = (float)mel[(size_t)m * T + start + c];
+  for (int i = win_lo; i < win_hi; ++i) {
+    const int s0 = start_of(i);
+    if (t >= s0 && t < s0 + kMelStep) out[((size_t)i * kMels + m) * kMelStep + (t - s0)] = (float)v;
   }
 }
 
@@ -137,11 +150,11 @@ cudaError_t launch_mel_step(const float* pcm, int nsamp, int B, int stride_left_
   if (e != cudaSuccess) return e;
   const int T = 1 + nsamp / kHop;
   if (T < kMelStep) return cudaErrorInvalidValue;
-  mel_stft_kernel<<<T, 256, 0, st>>>(pcm, nsamp, scratch_spec);
-  mel_fb_kernel<<<T, 96, 0, st>>>(scratch_spec, fb, scratch_mel, T);
+  (void)scratch_spec;   // the fused kernel keeps the spectrum / mel frame in shared memory
+  (void)scratch_mel;
   const double left = (double)(stride_left_chunks * 80) / 50.0;  // mel.py:50
   const double mult = 80.0 / (double)fps;                        // mel.py:52
-  mel_window_kernel<<<B, 128, 0, st>>>(scratch_mel, T, B, left, mult, out);
+  mel_fused_kernel<<<T, 256, 0, st>>>(pcm, nsamp, fb, T, B, left, mult, out);
   return cudaGetLastError();
 }
 

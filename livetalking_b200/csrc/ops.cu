@@ -312,9 +312,77 @@ __global__ void __launch_bounds__(256) softmax_kernel(const __half* __restrict__
   }
 }
 
+// Wide rows (cols > 1536: self-attention over the 64x64-latent maps of BASELINE configs[4], 4096 keys): one block per row,
+// values in registers (cols <= 256*8*4 = 8192), block-wide max / sum through shared memory.
+constexpr int kSMWideVec = 4;
+__global__ void __launch_bounds__(256) softmax_wide_kernel(const __half* __restrict__ x, int cols, int ld, int valid, float scale,
+                                                           __half* __restrict__ out) {
+  __shared__ float red[8];
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int nvec = cols / 8;
+  const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)row * ld);
+  float v[kSMWideVec][8];
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < kSMWideVec; ++k) {
+    const int i = tid + k * 256;
+    if (i < nvec) {
+      const uint4 u = src[i];
+      const __half* h = reinterpret_cast<const __half*>(&u);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = (i * 8 + j) < valid;
+        v[k][j] = ok ? __half2float(h[j]) * scale : -INFINITY;
+        m = fmaxf(m, v[k][j]);
+      }
+    }
+  }
+  m = warp_max(m);
+  if (lane == 0) red[w] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kSMWideVec; ++k) {
+    const int i = tid + k * 256;
+    if (i < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[k][j] = (v[k][j] == -INFINITY) ? 0.f : __expf(v[k][j] - m);
+        s += v[k][j];
+      }
+    }
+  }
+  s = warp_sum(s);
+  if (lane == 0) red[w] = s;
+  __syncthreads();
+  s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += red[i];
+  const float inv = 1.f / s;
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)row * ld);
+#pragma unroll
+  for (int k = 0; k < kSMWideVec; ++k) {
+    const int i = tid + k * 256;
+    if (i < nvec) {
+      uint4 o;
+      __half* oh = reinterpret_cast<__half*>(&o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) oh[j] = __float2half_rn(v[k][j] * inv);
+      dst[i] = o;
+    }
+  }
+}
+
 cudaError_t launch_softmax(const __half* x, int rows, int cols, int ld, int valid, float scale, __half* out, cudaStream_t st) {
-  if (cols % 8 != 0 || cols > 32 * 8 * kSMMaxVec || ld % 8 != 0 || valid > cols || valid < 1) return cudaErrorInvalidValue;
-  softmax_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, cols, ld, valid, scale, out);
+  if (cols % 8 != 0 || cols > 256 * 8 * kSMWideVec || ld % 8 != 0 || valid > cols || valid < 1) return cudaErrorInvalidValue;
+  if (cols > 32 * 8 * kSMMaxVec)
+    softmax_wide_kernel<<<rows, 256, 0, st>>>(x, cols, ld, valid, scale, out);
+  else
+    softmax_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, cols, ld, valid, scale, out);
   return cudaGetLastError();
 }
 

@@ -1009,7 +1009,7 @@ int ltb_w2l_mel_step(ltb_w2l_session* s, const float* pcm, int nsamples, float* 
   LTB_CUDA(cudaMemcpyAsync(s->asr_pcm, pcm, (size_t)nsamples * 4, cudaMemcpyHostToDevice, s->st_asr));
   cudaError_t e = launch_mel_step(s->asr_pcm, nsamples, s->B, s->l, s->fps, s->asr_spec, s->asr_melf, s->asr_mel, s->st_asr);
   if (e != cudaSuccess) return LTB_FAIL(std::string("mel kernels: ") + cudaGetErrorString(e));
-  s->launches_asr += 3;
+  s->launches_asr += 1;
   if (out_mel) LTB_CUDA(cudaMemcpyAsync(out_mel, s->asr_mel, (size_t)s->B * 1280 * 4, cudaMemcpyDeviceToHost, s->st_asr));
   LTB_CUDA(cudaStreamSynchronize(s->st_asr));
   return 0;
@@ -1036,12 +1036,13 @@ static int forward_enqueue(ltb_w2l_session* s, int index, bool with_mel) {
   } else {
     if (run_ops(s, with_mel)) return 1;
   }
-  s->launches += (long long)s->ops.size() + (with_mel ? 3 : 0);   // set_int + every op but the mel slot (+ 3 mel kernels)
+  s->launches += (long long)s->ops.size() + (with_mel ? 1 : 0);   // set_int + every op but the mel slot (+ the fused mel kernel)
   return 0;
 }
 
 int ltb_w2l_infer(ltb_w2l_session* s, int index, const float* mel, float* pred_out) {
   if (!s) return LTB_FAIL("null session");
+  if (s->ops.empty()) return LTB_FAIL("this session was created with LTB_SESSION_MEL_ONLY: it has no network");
   if (enter(s)) return 1;
   std::lock_guard<std::mutex> lk(s->mu);
   if (mel) LTB_CUDA(cudaMemcpyAsync(s->mel, mel, (size_t)s->B * 1280 * 4, cudaMemcpyHostToDevice, s->st));
@@ -1107,6 +1108,19 @@ int ltb_w2l_paste_batch(ltb_w2l_session* s, int index, uint8_t* out_frames) {
   return 0;
 }
 
+int ltb_w2l_infer_paste(ltb_w2l_session* s, int index, const float* mel, uint8_t* out_frames) {
+  if (!s || !mel || !out_frames) return LTB_FAIL("null argument");
+  if (s->ops.empty()) return LTB_FAIL("this session was created with LTB_SESSION_MEL_ONLY: it has no network");
+  if (enter(s)) return 1;
+  std::lock_guard<std::mutex> lk(s->mu);
+  LTB_CUDA(cudaMemcpyAsync(s->mel, mel, (size_t)s->B * 1280 * 4, cudaMemcpyHostToDevice, s->st));
+  if (forward_enqueue(s, index, false)) return 1;
+  if (paste_batch_enqueue(s, index)) return 1;
+  LTB_CUDA(cudaMemcpyAsync(out_frames, s->frames_out, (size_t)s->B * s->a->H * s->a->W * 3, cudaMemcpyDeviceToHost, s->st));
+  LTB_CUDA(cudaStreamSynchronize(s->st));
+  return 0;
+}
+
 int ltb_w2l_infer_slots(ltb_w2l_session* s, const ltb_w2l_slot* slots, int nslots, uint8_t* out_frames) {
   if (!s || !slots || !out_frames) return LTB_FAIL("null argument");
   if (!s->d_slots) return LTB_FAIL("infer_slots: session was not created with LTB_SESSION_SLOTS");
@@ -1146,7 +1160,7 @@ int ltb_w2l_mel_resident(ltb_w2l_session* s) {
   std::lock_guard<std::mutex> lk(s->mu);
   cudaError_t e = launch_mel_step(s->pcm, s->pcm_cap, s->B, s->l, s->fps, s->mel_spec, s->mel_mel, s->mel, s->st);
   if (e != cudaSuccess) return LTB_FAIL(std::string("mel kernels: ") + cudaGetErrorString(e));
-  s->launches += 3;
+  s->launches += 1;
   return 0;
 }
 
@@ -1289,8 +1303,22 @@ int ltb_w2l_layer_read(ltb_w2l_session* s, int layer, void* out_f16, size_t nbyt
   return 0;
 }
 
+static int conv2d_f16_impl(const ltb_conv_desc* d, const void* in_f16, const float* w_f32, const float* bias_f32,
+                           const void* res_f16, void* out_f16, int reps, float* ms_out);
+
 int ltb_conv2d_f16(const ltb_conv_desc* d, const void* in_f16, const float* w_f32, const float* bias_f32,
                    const void* res_f16, void* out_f16) {
+  return conv2d_f16_impl(d, in_f16, w_f32, bias_f32, res_f16, out_f16, 0, nullptr);
+}
+
+int ltb_conv2d_f16_timed(const ltb_conv_desc* d, const void* in_f16, const float* w_f32, const float* bias_f32,
+                         const void* res_f16, void* out_f16, int reps, float* ms_per_launch) {
+  if (reps < 1 || !ms_per_launch) return LTB_FAIL("conv2d_f16_timed: reps >= 1 and a result pointer are required");
+  return conv2d_f16_impl(d, in_f16, w_f32, bias_f32, res_f16, out_f16, reps, ms_per_launch);
+}
+
+static int conv2d_f16_impl(const ltb_conv_desc* d, const void* in_f16, const float* w_f32, const float* bias_f32,
+                           const void* res_f16, void* out_f16, int reps, float* ms_out) {
   if (!d || !in_f16 || !w_f32 || !bias_f32 || !out_f16) return LTB_FAIL("null argument");
   if (d->has_res && !res_f16) return LTB_FAIL("has_res set but res is null");
   int OH, OW, Ktot;
@@ -1377,10 +1405,39 @@ int ltb_conv2d_f16(const ltb_conv_desc* d, const void* in_f16, const float* w_f3
       return LTB_FAIL("halo plan / tensor map creation failed");
     }
     CK(launch_conv_halo(pl, nullptr));
+    if (reps > 0) {   // back-to-back launches of the same plan between two events (kernel development aid)
+      cudaEvent_t e0, e1;
+      CK(cudaEventCreate(&e0));
+      CK(cudaEventCreate(&e1));
+      for (int i = 0; i < 3; ++i) CK(launch_conv_halo(pl, nullptr));
+      CK(cudaEventRecord(e0, nullptr));
+      for (int i = 0; i < reps; ++i) CK(launch_conv_halo(pl, nullptr));
+      CK(cudaEventRecord(e1, nullptr));
+      CK(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      *ms_out = ms / reps;
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
   } else {
     CK(cudaMalloc(&dws, ((size_t)1 << 22) * sizeof(float)));
     CK(cudaMemset(dws, 0, ((size_t)1 << 22) * sizeof(float)));
     CK(launch_conv_gather(p, nullptr, dws, (size_t)1 << 22));
+    if (reps > 0) {
+      cudaEvent_t e0, e1;
+      CK(cudaEventCreate(&e0));
+      CK(cudaEventCreate(&e1));
+      CK(cudaEventRecord(e0, nullptr));
+      for (int i = 0; i < reps; ++i) CK(launch_conv_gather(p, nullptr, dws, (size_t)1 << 22));
+      CK(cudaEventRecord(e1, nullptr));
+      CK(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      *ms_out = ms / reps;
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
   }
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out_f16, dout, out_b, cudaMemcpyDeviceToHost));

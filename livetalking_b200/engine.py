@@ -174,6 +174,16 @@ class W2LSession:
         check(lib().ltb_w2l_paste_batch(self._h, int(index), _ptr(out) if to_host else None))
         return out
 
+    def infer_paste(self, index: int, mel: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """inference_batch in fused mode: mel windows in, `batch` composited frames out (one engine call)."""
+        mel = _carr(mel, np.float32)
+        if mel.size != self.batch * 80 * 16:
+            raise ValueError(f"mel must hold {self.batch}x80x16 values, got shape {mel.shape}")
+        if out is None:
+            out = np.empty((self.batch, self.avatar.H, self.avatar.W, 3), np.uint8)
+        check(lib().ltb_w2l_infer_paste(self._h, int(index), _ptr(mel), _ptr(out)))
+        return out
+
     def infer_slots(self, requests, out: Optional[np.ndarray] = None) -> np.ndarray:
         """Cross-session batch: requests = [(W2LAvatar, frame_idx, mel (80,16) float32), ...] (1..batch of them, any mix of
         avatars of this session's frame size) -> composited frames uint8 (n, H, W, 3).  One forward + paste launch."""
@@ -255,8 +265,9 @@ class W2LSession:
 
 
 def conv2d_f16(x_nhwc: np.ndarray, w: np.ndarray, bias: np.ndarray, *, stride=(1, 1), pad: int = 0, transposed: bool = False,
-               relu: bool = True, res: Optional[np.ndarray] = None, force_path: int = 0) -> np.ndarray:
-    """Stand-alone tensor-core conv (test hook).  x: (N,H,W,Cin) fp16; w: PyTorch layout float32."""
+               relu: bool = True, res: Optional[np.ndarray] = None, force_path: int = 0, reps: int = 0):
+    """Stand-alone tensor-core conv (test hook).  x: (N,H,W,Cin) fp16; w: PyTorch layout float32.
+    reps > 0: also time `reps` back-to-back launches -> (out, ms_per_launch)."""
     x = _carr(x_nhwc, np.float16)
     w = _carr(w, np.float32)
     bias = _carr(bias, np.float32)
@@ -274,5 +285,9 @@ def conv2d_f16(x_nhwc: np.ndarray, w: np.ndarray, bias: np.ndarray, *, stride=(1
     if res is not None:
         res = _carr(res, np.float16)
         assert res.shape == out.shape
+    if reps > 0:
+        ms = C.c_float(0.0)
+        check(lib().ltb_conv2d_f16_timed(C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(res), _ptr(out), int(reps), C.byref(ms)))
+        return out, ms.value
     check(lib().ltb_conv2d_f16(C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(res), _ptr(out)))
     return out

@@ -125,6 +125,24 @@ class LipReal(BaseAvatar):
             self.engine_session = engine.W2LSession(model, eng_avatar, self.batch_size, opt.l, opt.r, opt.fps)
         self.asr = MelASR(opt, self, self.engine_session)
         self.asr.warm_up()
+        # page-locked output ring for the fused mode: a D2H into pageable memory runs at a few GB/s, pinned at PCIe speed.  A buffer
+        # is reused after `ring` more batches; res_frame_queue holds at most 2 batches (base_avatar.py:86) plus the one being
+        # produced and the one being pasted, so 4 is the minimum safe depth.
+        self._ring, self._ring_pos = [], 0
+        if self._batcher is None and not self._return_pred:
+            shape = (self.batch_size, eng_avatar.H, eng_avatar.W, 3)
+            try:
+                self._ring = [engine.PinnedBuffer(shape, np.uint8) for _ in range(max(4, int(os.environ.get("LTB_PIN_RING", "4"))))]
+            except Exception as e:   # pinned memory exhausted: fall back to pageable output buffers
+                logger.warning("pinned output ring unavailable (%r): using pageable buffers", e)
+                self._ring = []
+
+    def _next_out(self):
+        if not self._ring:
+            return None
+        buf = self._ring[self._ring_pos % len(self._ring)].array
+        self._ring_pos += 1
+        return buf
 
     def inference_batch(self, index, audiofeat_batch):
         mel = np.asarray(audiofeat_batch, dtype=np.float32)                      # (B, 80, 16)
@@ -135,8 +153,7 @@ class LipReal(BaseAvatar):
             return [EngineFrame(frames[i], idxs[i]) for i in range(self.batch_size)]
         if self._return_pred:
             return self.engine_session.infer(index, mel, want_pred=True)        # float32 (B,256,256,3), as the reference
-        self.engine_session.infer(index, mel, want_pred=False)
-        frames = self.engine_session.paste_batch(index)                          # (B,H,W,3) uint8, one D2H
+        frames = self.engine_session.infer_paste(index, mel, out=self._next_out())   # (B,H,W,3) uint8: one engine call, one D2H
         return [EngineFrame(frames[i], mirror_index(length, index + i)) for i in range(self.batch_size)]
 
     def paste_back_frame(self, pred_frame, idx: int):

@@ -90,6 +90,14 @@ class FakeSession:
         from oracle import paste_ref as P
         return P.w2l_paste_back(np.asarray(pred, np.float32), self.avatar.frames[idx], self.avatar.coords[idx])
 
+    def infer_paste(self, index, mel, out=None):
+        self.infer(index, mel, want_pred=False)
+        frames = self.paste_batch(index)
+        if out is not None:
+            out[...] = frames
+            return out
+        return frames
+
     def infer_slots(self, requests, out=None):
         """cross-session batch (engine.W2LSession.infer_slots): every slot names its own avatar / frame / mel window"""
         from oracle import paste_ref as P

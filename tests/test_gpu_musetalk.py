@@ -90,6 +90,44 @@ def test_small_unet_vae_decode_parity_and_blend(small_nets):
     ctx.close()
 
 
+def test_small_nets_at_64x64_latents_512_images(small_nets):
+    """BASELINE configs[4]: 512x512 crops = 64x64 latents (the reference hard-wires 256, avatars/musetalk/models/vae.py:15; the
+    engine is parametrised on the avatar's latent size).  UNet + VAE decode parity, then the blend paste-back of a 512x512
+    prediction (resize source side 512) against the oracle."""
+    from livetalking_b200 import engine
+    from livetalking_b200.musetalk import MuseTalkModel, MuseTalkSession
+    from livetalking_b200.ops import Ctx
+    from oracle import musetalk_ref as M
+    from oracle import paste_ref as P
+    from oracle.wav2lip_ref import psnr_u8
+    ucfg, vcfg, us, vs = small_nets
+    engine.set_device(0)
+    B = 2
+    lat, aud = M.synth_latents_and_audio(B, hw=64, seed=12)
+    with torch.no_grad():
+        pred = M.unet_forward(us, ucfg, lat, M.positional_encoding(aud))
+        want_u8 = M.decode_latents_u8(vs, vcfg, pred)
+    assert want_u8.shape == (B, 512, 512, 3)
+    ctx = Ctx()
+    model = MuseTalkModel(ctx, us, vs, ucfg, vcfg, with_encoder=False)
+    av, frames, coords, crops, masks = _avatar(ctx, lat.numpy(), B, H=700, W=900)
+    assert av.lat_hw == 64
+    s = MuseTalkSession(model, av, B)
+    got_u8 = s.infer(0, aud.numpy())
+    assert got_u8.shape == (B, 512, 512, 3)
+    got_lat = ctx.download(s.pred16).astype(np.float32)[..., :4]
+    np.testing.assert_allclose(got_lat, pred.permute(0, 2, 3, 1).numpy(), atol=6e-2)
+    assert psnr_u8(got_u8, want_u8) >= 40.0, psnr_u8(got_u8, want_u8)
+    allf = s.paste_batch(0)
+    for slot in range(B):
+        idx = P.mirror_index(B, slot)
+        assert np.array_equal(allf[slot], P.mt_paste_back(got_u8[slot], frames[idx], coords[idx], masks[idx], crops[idx]))
+    host_pred = np.random.default_rng(3).integers(0, 256, (512, 512, 3), dtype=np.uint8)
+    assert np.array_equal(s.paste_pred(host_pred, 1), P.mt_paste_back(host_pred, frames[1], coords[1], masks[1], crops[1]))
+    s.close()
+    ctx.close()
+
+
 def test_small_vae_encode_parity(small_nets):
     from livetalking_b200 import engine
     from livetalking_b200.musetalk import MuseTalkModel, encode_avatar_latents
@@ -111,8 +149,10 @@ def test_small_vae_encode_parity(small_nets):
     ctx.close()
 
 
-def test_full_width_networks_once():
-    """The real MuseTalk widths (UNet 320/640/1280/1280 with head_dim 40 -> padded 48, sd-vae 128/256/512/512), B = 1."""
+@pytest.mark.parametrize("B", [1, 8], ids=["B1", "B8_configs2"])
+def test_full_width_networks(B):
+    """The real MuseTalk widths (UNet 320/640/1280/1280 with head_dim 40 -> padded 48, sd-vae 128/256/512/512) at B = 1 and at
+    BASELINE configs[2]'s batch 8 (different tile / split-K / wave configurations than B = 1)."""
     from livetalking_b200 import engine
     from livetalking_b200.musetalk import MuseTalkModel, MuseTalkSession
     from livetalking_b200.ops import Ctx
@@ -122,14 +162,16 @@ def test_full_width_networks_once():
     us = M.synth_unet_state_dict(M.UNET_FULL, fast=True)
     vs = M.synth_vae_state_dict(M.VAE_FULL, fast=True)
     assert M.count_params(us) == 849_947_844 and M.count_params(vs) == 83_653_863     # published parameter counts
-    lat, aud = M.synth_latents_and_audio(1, seed=9)
-    pred = M.unet_forward(us, M.UNET_FULL, lat, M.positional_encoding(aud))
-    want_u8 = M.decode_latents_u8(vs, M.VAE_FULL, pred)
+    lat, aud = M.synth_latents_and_audio(B, seed=9)
+    with torch.no_grad():
+        pred = M.unet_forward(us, M.UNET_FULL, lat, M.positional_encoding(aud))
+        want_u8 = M.decode_latents_u8(vs, M.VAE_FULL, pred)
     ctx = Ctx()
     model = MuseTalkModel(ctx, us, vs, M.UNET_FULL, M.VAE_FULL, with_encoder=False)
-    av, *_ = _avatar(ctx, lat.numpy(), 1)
-    s = MuseTalkSession(model, av, 1)
+    av, *_ = _avatar(ctx, lat.numpy(), B)
+    s = MuseTalkSession(model, av, B)
     got_u8 = s.infer(0, aud.numpy())
+    assert got_u8.shape == (B, 256, 256, 3)
     got_lat = ctx.download(s.pred16).astype(np.float32)[..., :4]
     want_lat = pred.permute(0, 2, 3, 1).numpy()
     assert np.abs(got_lat - want_lat).max() <= 0.08 * max(1.0, np.abs(want_lat).max())
