@@ -16,6 +16,7 @@ Extra keys on the same JSON line (all measured in this run):
   e2e_plugin        fps through the reference-facing hooks exactly as avatars/base_avatar.py calls them:
                     MelASR features -> LipReal.inference_batch -> 16 x paste_back_frame (host arrays in and out)
   sessions32        BASELINE configs[3]: 32 concurrent sessions on this GPU, each batch 16 (per-session fps, arena bytes)
+  cross_session     the batching scheduler's engine call: 16 slots from 8 different sessions in one forward + paste launch
   musetalk          BASELINE configs[2] (MuseTalk 256x256 batch 8, fp16): value / e2e / roofline of its own
   musetalk512       BASELINE configs[4] (64x64 latents), with --musetalk512
   torch_eager_b200  the reference network in stock PyTorch on THIS GPU (fp32 = TF32 cuDNN as the reference runs it, and fp16
@@ -377,6 +378,38 @@ def sessions_leg(torch, engine, model, av, audio, n_sessions, steps):
             "what": "BASELINE configs[3] on one GPU: every session has its own stream, activation arena and CUDA graph; weights / avatar shared"}
 
 
+def cross_session_leg(engine, model, steps):
+    """the batching scheduler's engine call — 16 slots taken from 8 DIFFERENT sessions' avatars (2 frames each,
+    as sessions running with batch_size 2 would submit them), one forward + paste launch, frames back on the host."""
+    from livetalking_b200 import synth
+    n_av, per = 8, 2
+    avs = []
+    for a in range(n_av):
+        faces, frames, coords = synth.synthetic_avatar(n=8, H=FRAME_H, W=FRAME_W, bbox=BBOX, seed=100 + a)
+        avs.append(engine.W2LAvatar(faces, frames, coords))
+    mux = engine.W2LSession(model, avs[0], BATCH, SL, SR, FPS, slots=True)
+    rng = np.random.default_rng(0)
+    mels = np.clip(rng.standard_normal((BATCH, 80, 16)), -4, 4).astype(np.float32)
+    out = engine.PinnedBuffer((BATCH, FRAME_H, FRAME_W, 3), np.uint8)
+
+    def one(k):
+        reqs = [(avs[i // per], (k * per + i % per) % 8, mels[i]) for i in range(BATCH)]
+        return mux.infer_slots(reqs, out=out.array)
+
+    for k in range(3):
+        one(k)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        one(k)
+    dt = time.perf_counter() - t0
+    mux.close()
+    for a in avs:
+        a.close()
+    return {"value": round(BATCH * steps / dt, 1), "unit": "frames/s", "ms_per_batch": round(1000.0 * dt / steps, 3), "slots": BATCH,
+            "sessions_in_batch": n_av, "sessions_at_25fps": int(BATCH * steps / dt // 25),
+            "how": "ltb_w2l_infer_slots: 16 slots from 8 avatars per call, host mel windows in, 16 composited 720p frames out (pinned), synchronous"}
+
+
 def musetalk_leg(torch, engine, args, peaks, hw: int, B: int = 8):
     """BASELINE configs[2] (hw = 32: 256x256) / configs[4] (hw = 64: 512x512): the online path the reference runs per step
     (avatars/musetalk_avatar.py:130-164): Whisper features -> PE -> UNet -> VAE decode -> blend paste-back."""
@@ -625,6 +658,7 @@ def run_ours(args):
         guarded("e2e_plugin", lambda: plugin_e2e(engine, model, (list(frames), list(faces), [tuple(c) for c in coords]), audio,
                                                   max(5, min(args.steps, 20)), 3))
         guarded("sessions32", lambda: sessions_leg(torch, engine, model, av, audio, 32, max(5, min(args.steps, 20))))
+        guarded("cross_session", lambda: cross_session_leg(engine, model, max(5, min(args.steps, 20))))
         guarded("torch_eager_b200", lambda: torch_eager_b200(torch))
     if rank == 0 and not args.no_musetalk and not args.quick:
         guarded("musetalk", lambda: musetalk_leg(torch, engine, args, peaks, 32))

@@ -271,6 +271,8 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
     const int row = q * 32 + lane;       // 0..127 inside a sub-tile
     const int ry = row >> 3, rx = row & 7;
     uint32_t it = 0;
+    float4 bb[8];        // bias of channels [bb_col, bb_col + 32)
+    int bb_col = -1;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       const int nt = t / tiles_m;
       int mt = t - nt * tiles_m;
@@ -342,10 +344,14 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
           __half* optr = p.out + opix * p.OCtot + p.oc_off + n0;
           {
             if (LTB_DIAG(2)) continue;
-            // bias first: its L1 latency overlaps the TMEM read instead of stalling the first add of every group
-            float4 bb[8];
+            // bias first: its L1 latency overlaps the TMEM read instead of stalling the first add of every group.  The 32
+            // values stay in registers while consecutive items use the same channels (ConvT: the four sub-pixel phases of a
+            // warp share c0, so the bias is loaded once per kernel instead of once per item)
+            if (bb_col != n0 + c0) {
+              bb_col = n0 + c0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) bb[u] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0) + u);
+              for (int u = 0; u < 8; ++u) bb[u] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0) + u);
+            }
             uint32_t v[32];
             tmem_ld32(tbase + ci * 32, v);
             tmem_ld_wait();
@@ -369,19 +375,29 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
                 const int g = g16 + hh * 8;
                 const float4 b0 = bb[g / 4], b1 = bb[g / 4 + 1];
                 __half2* oh = reinterpret_cast<__half2*>(&ovv[hh]);
-                oh[0] = __floats2half2_rn(__uint_as_float(v[g + 0]) + b0.x, __uint_as_float(v[g + 1]) + b0.y);
-                oh[1] = __floats2half2_rn(__uint_as_float(v[g + 2]) + b0.z, __uint_as_float(v[g + 3]) + b0.w);
-                oh[2] = __floats2half2_rn(__uint_as_float(v[g + 4]) + b1.x, __uint_as_float(v[g + 5]) + b1.y);
-                oh[3] = __floats2half2_rn(__uint_as_float(v[g + 6]) + b1.z, __uint_as_float(v[g + 7]) + b1.w);
-                if (has_res) {
-                  const __half2* rh = reinterpret_cast<const __half2*>(&rcur[(g16 >> 3) + hh]);
+                uint32_t* ow = reinterpret_cast<uint32_t*>(&ovv[hh]);
+                const float f0 = __uint_as_float(v[g + 0]) + b0.x, f1 = __uint_as_float(v[g + 1]) + b0.y;
+                const float f2 = __uint_as_float(v[g + 2]) + b0.z, f3 = __uint_as_float(v[g + 3]) + b0.w;
+                const float f4 = __uint_as_float(v[g + 4]) + b1.x, f5 = __uint_as_float(v[g + 5]) + b1.y;
+                const float f6 = __uint_as_float(v[g + 6]) + b1.z, f7 = __uint_as_float(v[g + 7]) + b1.w;
+                if (!has_res && p.relu) {   // warp-uniform: convert + ReLU + saturation in one instruction per channel pair
+                  ow[0] = f32x2_to_f16x2_sat_relu(f0, f1);
+                  ow[1] = f32x2_to_f16x2_sat_relu(f2, f3);
+                  ow[2] = f32x2_to_f16x2_sat_relu(f4, f5);
+                  ow[3] = f32x2_to_f16x2_sat_relu(f6, f7);
+                } else {
+                  ow[0] = f32x2_to_f16x2_sat(f0, f1);
+                  ow[1] = f32x2_to_f16x2_sat(f2, f3);
+                  ow[2] = f32x2_to_f16x2_sat(f4, f5);
+                  ow[3] = f32x2_to_f16x2_sat(f6, f7);
+                  if (has_res) {
+                    const __half2* rh = reinterpret_cast<const __half2*>(&rcur[(g16 >> 3) + hh]);
+                    const __half2 hmax = __floats2half2_rn(65504.f, 65504.f);
+                    const __half2 lo = p.relu ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(-65504.f, -65504.f);
 #pragma unroll
-                  for (int u = 0; u < 4; ++u) oh[u] = __hadd2(oh[u], rh[u]);
+                    for (int u = 0; u < 4; ++u) oh[u] = __hmin2(__hmax2(__hadd2(oh[u], rh[u]), lo), hmax);
+                  }
                 }
-                const __half2 hmax = __floats2half2_rn(65504.f, 65504.f);
-                const __half2 lo = p.relu ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(-65504.f, -65504.f);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) oh[u] = __hmin2(__hmax2(oh[u], lo), hmax);
                 if (kHeadOk && head) {
 #pragma unroll
                   for (int u = 0; u < 4; ++u) {

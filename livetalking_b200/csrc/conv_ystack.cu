@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(320, 1) conv_ystack_umma_kernel(const __grid_c
         v1[c] = __float_as_uint(__uint_as_float(v1[c]) + up + dn);
       }
       // ---- bias / residual / ReLU / (head) / store: same arithmetic and order as conv_halo.cu's epilogue
-      float4 bb[8];
+      float4 bb[8];   // (hoisting these 32 registers out of the tile loop spills: 168-register cap at 320 threads)
 #pragma unroll
       for (int u = 0; u < 8; ++u) bb[u] = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + u);
       __half* optr = p.out + opix * p.OCtot + p.oc_off;
@@ -297,19 +297,29 @@ __global__ void __launch_bounds__(320, 1) conv_ystack_umma_kernel(const __grid_c
           const int g = g16 + hh * 8;
           const float4 b0 = bb[g / 4], b1 = bb[g / 4 + 1];
           __half2* oh = reinterpret_cast<__half2*>(&ovv[hh]);
-          oh[0] = __floats2half2_rn(__uint_as_float(v1[g + 0]) + b0.x, __uint_as_float(v1[g + 1]) + b0.y);
-          oh[1] = __floats2half2_rn(__uint_as_float(v1[g + 2]) + b0.z, __uint_as_float(v1[g + 3]) + b0.w);
-          oh[2] = __floats2half2_rn(__uint_as_float(v1[g + 4]) + b1.x, __uint_as_float(v1[g + 5]) + b1.y);
-          oh[3] = __floats2half2_rn(__uint_as_float(v1[g + 6]) + b1.z, __uint_as_float(v1[g + 7]) + b1.w);
-          if (has_res) {
-            const __half2* rh = reinterpret_cast<const __half2*>(&rcur[(g16 >> 3) + hh]);
+          uint32_t* ow = reinterpret_cast<uint32_t*>(&ovv[hh]);
+          const float f0 = __uint_as_float(v1[g + 0]) + b0.x, f1 = __uint_as_float(v1[g + 1]) + b0.y;
+          const float f2 = __uint_as_float(v1[g + 2]) + b0.z, f3 = __uint_as_float(v1[g + 3]) + b0.w;
+          const float f4 = __uint_as_float(v1[g + 4]) + b1.x, f5 = __uint_as_float(v1[g + 5]) + b1.y;
+          const float f6 = __uint_as_float(v1[g + 6]) + b1.z, f7 = __uint_as_float(v1[g + 7]) + b1.w;
+          if (!has_res && p.relu) {
+            ow[0] = f32x2_to_f16x2_sat_relu(f0, f1);
+            ow[1] = f32x2_to_f16x2_sat_relu(f2, f3);
+            ow[2] = f32x2_to_f16x2_sat_relu(f4, f5);
+            ow[3] = f32x2_to_f16x2_sat_relu(f6, f7);
+          } else {
+            ow[0] = f32x2_to_f16x2_sat(f0, f1);
+            ow[1] = f32x2_to_f16x2_sat(f2, f3);
+            ow[2] = f32x2_to_f16x2_sat(f4, f5);
+            ow[3] = f32x2_to_f16x2_sat(f6, f7);
+            if (has_res) {
+              const __half2* rh = reinterpret_cast<const __half2*>(&rcur[(g16 >> 3) + hh]);
+              const __half2 hmax = __floats2half2_rn(65504.f, 65504.f);
+              const __half2 lo = p.relu ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(-65504.f, -65504.f);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) oh[u] = __hadd2(oh[u], rh[u]);
+              for (int u = 0; u < 4; ++u) oh[u] = __hmin2(__hmax2(__hadd2(oh[u], rh[u]), lo), hmax);
+            }
           }
-          const __half2 hmax = __floats2half2_rn(65504.f, 65504.f);
-          const __half2 lo = p.relu ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(-65504.f, -65504.f);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) oh[u] = __hmin2(__hmax2(oh[u], lo), hmax);
           if (kHeadOk && head) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {

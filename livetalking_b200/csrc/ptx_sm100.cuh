@@ -247,6 +247,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// fp32 pair -> packed fp16x2 with saturation to +-65504 (and ReLU) in ONE instruction (F2FP.SATFINITE[.RELU].F16.F32.PACK_AB):
+// replaces convert + max(0) + min(65504) of the epilogue (3 instructions per channel pair).  Result: {lo, hi} = half2(lo, hi).
+__device__ __forceinline__ uint32_t f32x2_to_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t f32x2_to_f16x2_sat_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // 256-bit global accesses (sm_100+): one full 32-byte sector per thread
 __device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
   // plain (coherent) load, not .nc: with programmatic dependent launch the predecessor may still be writing this tensor

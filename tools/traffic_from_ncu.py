@@ -32,7 +32,7 @@ def main(src, dst):
     step = None
     for a, b in zip(marks, marks[1:]):
         names = [launches[i]["name"] for i in ids if a <= i < b]
-        if any("mel_stft" in n for n in names) and any("paste" in n for n in names):
+        if any(("mel_fused" in n or "mel_stft" in n) for n in names) and any("paste" in n for n in names):
             step = (a, b)                                  # keep the last complete step
     if step is None:
         raise SystemExit("no complete step (set_int .. mel .. paste) in the launch list")
@@ -44,7 +44,7 @@ def main(src, dst):
         L = launches[i]
         by = L.get("dram__bytes_read.sum", 0.0) + L.get("dram__bytes_write.sum", 0.0)
         us = L.get("gpu__time_duration.sum", 0.0)
-        is_conv = any(k in L["name"] for k in ("conv_halo_umma", "conv_gather_umma", "stem_umma", "splitk_finalize"))
+        is_conv = any(k in L["name"] for k in ("conv_halo_umma", "conv_ystack_umma", "conv_gather_umma", "stem_umma", "splitk_finalize"))
         short = L["name"].split("(")[0].replace("void ", "").replace("ltb::", "")
         pk = per_kernel.setdefault(short, [0, 0.0, 0.0])
         pk[0] += 1
