@@ -18,7 +18,7 @@ Extra keys on the same JSON line (all measured in this run):
   sessions32        BASELINE configs[3]: 32 concurrent sessions on this GPU, each batch 16 (per-session fps, arena bytes)
   cross_session     the batching scheduler's engine call: 16 slots from 8 different sessions in one forward + paste launch
   musetalk          BASELINE configs[2] (MuseTalk 256x256 batch 8, fp16): value / e2e / roofline of its own
-  musetalk512       BASELINE configs[4] (64x64 latents), with --musetalk512
+  musetalk512       BASELINE configs[4] (512x512 = 64x64 latents, batch 8) + 8 CONCURRENT sessions per GPU; every rank at N > 1
   torch_eager_b200  the reference network in stock PyTorch on THIS GPU (fp32 = TF32 cuDNN as the reference runs it, and fp16
                     channels_last): the existing Blackwell path to beat
   cpu_baseline      the oracle port on the host cores (N = 1 only)
@@ -350,7 +350,7 @@ def plugin_e2e(engine, model, av_lists, audio, steps, warmup):
             "d2h_bytes_per_step": BATCH * FRAME_H * FRAME_W * 3}
 
 
-def sessions_leg(torch, engine, model, av, audio, n_sessions, steps):
+def sessions_leg(torch, engine, model, av, audio, n_sessions, steps, dist=None, world=1):
     """BASELINE configs[3]: n concurrent sessions on one GPU, each batch 16 on its own stream / arena."""
     free0 = torch.cuda.mem_get_info()[0]
     ss = [engine.W2LSession(model, av, BATCH, SL, SR, FPS) for _ in range(n_sessions)]
@@ -370,10 +370,15 @@ def sessions_leg(torch, engine, model, av, audio, n_sessions, steps):
         step_all(k)
     torch.cuda.synchronize()
     ms = timed_steps(torch, streams[0], g, step_all, steps, streams[1:])
-    fps = n_sessions * BATCH * steps / (ms / 1000.0)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    fps = world * n_sessions * BATCH * steps / (ms / 1000.0)
     for s_ in ss:
         s_.close()
-    return {"sessions_per_gpu": n_sessions, "value": round(fps, 1), "unit": "frames/s", "per_session_fps": round(fps / n_sessions, 1),
+    return {"sessions_per_gpu": n_sessions, "n_gpus": world, "total_sessions": world * n_sessions, "value": round(fps, 1), "unit": "frames/s",
+            "per_session_fps": round(fps / (world * n_sessions), 1),
             "realtime_sessions_at_25fps": int(fps // 25), "arena_bytes_per_session": int(arena), "ms_per_round": round(ms / steps, 3),
             "what": "BASELINE configs[3] on one GPU: every session has its own stream, activation arena and CUDA graph; weights / avatar shared"}
 
@@ -410,76 +415,169 @@ def cross_session_leg(engine, model, steps):
             "how": "ltb_w2l_infer_slots: 16 slots from 8 avatars per call, host mel windows in, 16 composited 720p frames out (pinned), synchronous"}
 
 
-def musetalk_leg(torch, engine, args, peaks, hw: int, B: int = 8):
-    """BASELINE configs[2] (hw = 32: 256x256) / configs[4] (hw = 64: 512x512): the online path the reference runs per step
-    (avatars/musetalk_avatar.py:130-164): Whisper features -> PE -> UNet -> VAE decode -> blend paste-back."""
-    from livetalking_b200 import configs, synth
-    from livetalking_b200.musetalk import MuseTalkAvatar, MuseTalkModel, MuseTalkSession
-    from livetalking_b200.ops import Ctx
-    from livetalking_b200.whisper import WhisperEncoder, WhisperFeatures
-    ucfg, vcfg = configs.UNetConfig(), configs.VAEConfig()
-    t0 = time.time()
-    ctx = Ctx()
-    net = MuseTalkModel(ctx, synth.random_unet_state_dict(ucfg), synth.random_vae_state_dict(vcfg), ucfg, vcfg, with_encoder=False)
-    wenc = WhisperEncoder(ctx, synth.random_whisper_state_dict())
-    frames, masks, coords, crops, latents = synth.synthetic_musetalk_avatar(n=16, hw=hw)
-    av = MuseTalkAvatar(ctx, frames, masks, coords, crops, latents)
-    sess = MuseTalkSession(net, av, B, ctx=ctx)            # device-resident leg: one stream for the whole timed chain
-    wf = WhisperFeatures(wenc, B, SL, SR, out=sess.audio_in, out_rows=64, ctx=ctx)
-    load_s = time.time() - t0
-    audio = synth.sine_audio(10.0)
-    wf.run_async(step_pcm(audio, 0, B))
-    ctx.sync()
-    stream = torch.cuda.ExternalStream(ctx.cuda_stream)
-    gate = Gate(torch, stream)
-    steps, warm = max(5, min(args.steps, 20)), max(3, min(args.warmup, 5))
+class MuseTalkBench:
+    """MuseTalk legs.  The model is built ONCE per rank; with N > 1 ranks the synthetic state dicts are generated on rank 0 and
+    shipped with one NCCL broadcast (BASELINE configs[4]: "NCCL weight-broadcast init"), exactly like the wav2lip blob."""
 
-    def online(k):
-        wf.run_async(None)
-        sess.step_async(k * B)
+    def __init__(self, torch, dist, world, rank):
+        from livetalking_b200 import configs, synth
+        from livetalking_b200.musetalk import MuseTalkModel
+        from livetalking_b200.ops import Ctx
+        from livetalking_b200.whisper import WhisperEncoder
+        self.torch, self.dist, self.world, self.rank = torch, dist, world, rank
+        self.ucfg, self.vcfg = configs.UNetConfig(), configs.VAEConfig()
+        t0 = time.time()
+        sds = None
+        if rank == 0:
+            sds = [synth.random_unet_state_dict(self.ucfg), synth.random_vae_state_dict(self.vcfg), synth.random_whisper_state_dict()]
+        bcast_s = 0.0
+        if world > 1:
+            tb = time.time()
+            sds = self._broadcast_state_dicts(sds)
+            bcast_s = time.time() - tb
+        self.ctx = Ctx()
+        self.net = MuseTalkModel(self.ctx, sds[0], sds[1], self.ucfg, self.vcfg, with_encoder=False)
+        self.wenc = WhisperEncoder(self.ctx, sds[2])
+        self.load_s, self.bcast_s = time.time() - t0, bcast_s
+        self.audio = synth.sine_audio(10.0)
 
-    for k in range(warm):
-        online(k)
-    ctx.sync()
-    l0 = ctx.launch_count
-    ms = timed_steps(torch, stream, gate, online, steps) / steps
-    launches = (ctx.launch_count - l0) // steps
-    ms_net = timed_steps(torch, stream, gate, lambda k: sess.infer_async(k * B, None), steps) / steps
-    # e2e: host PCM in, host frames out, through the session objects the plugin drives (own ctx per role, as deployed)
-    sess2 = MuseTalkSession(net, av, B)
-    wf2 = WhisperFeatures(wenc, B, SL, SR)
-    S = hw * 8
+    def _broadcast_state_dicts(self, sds):
+        """rank 0: [dict name -> float32 ndarray] x 3  ->  every rank, through ONE flat NCCL broadcast (+ a small metadata object)."""
+        torch, dist = self.torch, self.dist
+        meta = [None]
+        if self.rank == 0:
+            meta = [[[(k, tuple(np.asarray(v).shape)) for k, v in sd.items()] for sd in sds]]
+        dist.broadcast_object_list(meta, src=0)
+        total = sum(int(np.prod(shape)) if len(shape) else 1 for part in meta[0] for _k, shape in part)
+        flat = torch.empty(total, dtype=torch.float32, device="cuda")
+        if self.rank == 0:
+            host = np.concatenate([np.asarray(v, np.float32).reshape(-1) for sd in sds for v in sd.values()])
+            flat.copy_(torch.from_numpy(host))
+        dist.broadcast(flat, 0)                    # ~3.7 GB over NVLink / NVSwitch
+        if self.rank == 0:
+            return sds
+        host = flat.cpu().numpy()
+        out, o = [], 0
+        for part in meta[0]:
+            d = {}
+            for k, shape in part:
+                n = int(np.prod(shape)) if len(shape) else 1
+                d[k] = host[o:o + n].reshape(shape)
+                o += n
+            out.append(d)
+        return out
 
-    def e2e_one(k):
-        feats = wf2.run(step_pcm(audio, k, B))                      # WhisperASR.run_step features (H2D PCM, D2H features)
-        sess2.infer(k * B, feats, want_pred=False)                  # inference_batch (H2D features)
-        return sess2.paste_batch(k * B)                             # B composited frames to the host
+    def _reduce_max(self, ms):
+        if self.world == 1:
+            return ms
+        t = self.torch.tensor([ms], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
 
-    for k in range(warm):
-        e2e_one(k)
-    t1 = time.perf_counter()
-    for k in range(steps):
-        e2e_one(k)
-    e2e_ms = (time.perf_counter() - t1) * 1000.0 / steps
-    gf = MT_GFLOP_ONLINE[hw] * B + MT_GFLOP_WHISPER_STEP
-    tf = gf / ms
-    res = {
-        "metric": "lip-sync frames/sec (MuseTalk %dx%d, batch %d, fp16: whisper + PE + UNet + VAE decode + blend paste-back)" % (S, S, B),
-        "value": round(1000.0 * B / ms, 2), "unit": "frames/s", "ms_per_step": round(ms, 3), "steps": steps, "warmup": warm,
-        "config": {"workload": "MuseTalk %dx%d batch %d, 1xB200, fp16 (BASELINE.json configs[%d]); online path of "
-                               "avatars/musetalk_avatar.py:130-164, latents pre-encoded" % (S, S, B, 2 if hw == 32 else 4)},
-        "e2e": {"value": round(1000.0 * B / e2e_ms, 2), "unit": "frames/s", "h2d_bytes_per_step": int(wf2.n * 4 + B * 50 * 384 * 2),
-                "d2h_bytes_per_step": int(B * 50 * 384 * 2 + B * av.H * av.W * 3),
-                "how": "WhisperFeatures.run(host PCM) + MuseTalkSession.infer(host features) + paste_batch -> host frames, wall clock"},
-        "roofline": {"bound": "tensor", "achieved": round(tf, 1), "peak": peaks["burst"], "unit": "TFLOP/s", "frac": round(tf / peaks["burst"], 4),
-                     "frac_sustained_peak": round(tf / peaks["sustained"], 4), "algorithmic_gflop_per_step": round(gf, 1),
-                     "unet_vae_only_ms": round(ms_net, 3), "traffic": None},
-        "gpu_launches_per_step": int(launches), "sessions_at_25fps": int((1000.0 * B / ms) // 25), "model_load_s": round(load_s, 1),
-    }
-    sess2.close()
-    wf2.close()
-    ctx.close()
-    return res
+    def leg(self, args, peaks, hw: int, B: int = 8, n_sessions: int = 0, B_sess: int = 2):
+        """BASELINE configs[2] (hw = 32: 256x256) / configs[4] (hw = 64: 512x512): the online path the reference runs per step
+        (avatars/musetalk_avatar.py:130-164): Whisper features -> PE -> UNet -> VAE decode -> blend paste-back.
+        n_sessions > 0: additionally that many CONCURRENT sessions per GPU (own stream / graph / buffers each, batch B_sess)."""
+        from livetalking_b200 import synth
+        from livetalking_b200.musetalk import MuseTalkAvatar, MuseTalkSession
+        from livetalking_b200.whisper import WhisperFeatures
+        torch, ctx, net, wenc, audio, world = self.torch, self.ctx, self.net, self.wenc, self.audio, self.world
+        frames, masks, coords, crops, latents = synth.synthetic_musetalk_avatar(n=16, hw=hw, seed=self.rank)
+        av = MuseTalkAvatar(ctx, frames, masks, coords, crops, latents)
+        sess = MuseTalkSession(net, av, B, ctx=ctx)            # device-resident leg: one stream for the whole timed chain
+        wf = WhisperFeatures(wenc, B, SL, SR, out=sess.audio_in, out_rows=64, ctx=ctx)
+        wf.run_async(step_pcm(audio, 0, B))
+        ctx.sync()
+        stream = torch.cuda.ExternalStream(ctx.cuda_stream)
+        gate = Gate(torch, stream)
+        steps, warm = max(5, min(args.steps, 20)), max(3, min(args.warmup, 5))
+
+        def online(k):
+            wf.run_async(None)
+            sess.step_async(k * B)
+
+        for k in range(warm):
+            online(k)
+        ctx.sync()
+        l0 = ctx.launch_count
+        ms = self._reduce_max(timed_steps(torch, stream, gate, online, steps)) / steps
+        launches = (ctx.launch_count - l0) // steps
+        ms_net = timed_steps(torch, stream, gate, lambda k: sess.infer_async(k * B, None), steps) / steps
+        # e2e: host PCM in, host frames out, through the session objects the plugin drives (own ctx per role, as deployed)
+        sess2 = MuseTalkSession(net, av, B)
+        wf2 = WhisperFeatures(wenc, B, SL, SR)
+        S = hw * 8
+
+        def e2e_one(k):
+            feats = wf2.run(step_pcm(audio, k, B))                      # WhisperASR.run_step features (H2D PCM, D2H features)
+            sess2.infer(k * B, feats, want_pred=False)                  # inference_batch (H2D features)
+            return sess2.paste_batch(k * B)                             # B composited frames to the host
+
+        for k in range(warm):
+            e2e_one(k)
+        t1 = time.perf_counter()
+        for k in range(steps):
+            e2e_one(k)
+        e2e_ms = self._reduce_max((time.perf_counter() - t1) * 1000.0) / steps
+        sess2.close()
+        wf2.close()
+        gf = MT_GFLOP_ONLINE[hw] * B + MT_GFLOP_WHISPER_STEP
+        tf = gf / ms
+        res = {
+            "metric": "lip-sync frames/sec (MuseTalk %dx%d, batch %d, fp16: whisper + PE + UNet + VAE decode + blend paste-back)" % (S, S, B),
+            "value": round(world * 1000.0 * B / ms, 2), "unit": "frames/s", "n_gpus": world, "ms_per_step": round(ms, 3), "steps": steps, "warmup": warm,
+            "config": {"workload": "MuseTalk %dx%d batch %d, 1xB200 per rank, fp16 (BASELINE.json configs[%d]); online path of "
+                                   "avatars/musetalk_avatar.py:130-164, latents pre-encoded" % (S, S, B, 2 if hw == 32 else 4),
+                       "weights": "synthetic; rank 0 -> all ranks by one NCCL broadcast (%.1f s)" % self.bcast_s if world > 1 else "synthetic"},
+            "e2e": {"value": round(world * 1000.0 * B / e2e_ms, 2), "unit": "frames/s", "h2d_bytes_per_step": int(wf2.n * 4 + B * 50 * 384 * 2),
+                    "d2h_bytes_per_step": int(B * 50 * 384 * 2 + B * av.H * av.W * 3),
+                    "how": "WhisperFeatures.run(host PCM) + MuseTalkSession.infer(host features) + paste_batch -> host frames, wall clock"},
+            "roofline": {"bound": "tensor", "achieved": round(tf, 1), "peak": peaks["burst"], "unit": "TFLOP/s", "frac": round(tf / peaks["burst"], 4),
+                         "frac_sustained_peak": round(tf / peaks["sustained"], 4), "algorithmic_gflop_per_step": round(gf, 1),
+                         "unet_vae_only_ms": round(ms_net, 3), "traffic": None, "per_gpu": True},
+            "gpu_launches_per_step": int(launches), "sessions_at_25fps_per_gpu": int((1000.0 * B / ms) // 25), "model_load_s": round(self.load_s, 1),
+        }
+        if n_sessions > 0:
+            res["concurrent_sessions"] = self._sessions(args, av, hw, n_sessions, B_sess)
+        return res
+
+    def _sessions(self, args, av, hw, n_sessions, B):
+        """n concurrent MuseTalk sessions on this GPU (BASELINE configs[4]: 8 sessions per GPU): every session owns its stream,
+        CUDA graph and buffers (MuseTalkSession + WhisperFeatures with their own Ctx), weights and avatar are shared."""
+        from livetalking_b200.musetalk import MuseTalkSession
+        from livetalking_b200.whisper import WhisperFeatures
+        torch, world = self.torch, self.world
+        free0 = torch.cuda.mem_get_info()[0]
+        ss = [MuseTalkSession(self.net, av, B) for _ in range(n_sessions)]
+        wfs = [WhisperFeatures(self.wenc, B, SL, SR, out=s_.audio_in, out_rows=64, ctx=s_.ctx) for s_ in ss]
+        per_sess = (free0 - torch.cuda.mem_get_info()[0]) / n_sessions
+        for w_ in wfs:
+            w_.run_async(step_pcm(self.audio, 0, B))
+        torch.cuda.synchronize()
+        streams = [torch.cuda.ExternalStream(s_.ctx.cuda_stream) for s_ in ss]
+        gate = Gate(torch, streams[0])
+        steps = max(5, min(args.steps, 20))
+
+        def step_all(k):
+            for s_, w_ in zip(ss, wfs):
+                w_.run_async(None)
+                s_.step_async(k * B)
+
+        for k in range(3):
+            step_all(k)
+        torch.cuda.synchronize()
+        ms = self._reduce_max(timed_steps(torch, streams[0], gate, step_all, steps, streams[1:])) / steps
+        fps = n_sessions * B * 1000.0 / ms
+        for w_ in wfs:
+            w_.close()
+        for s_ in ss:
+            s_.close()
+        return {"sessions_per_gpu": n_sessions, "batch_per_session": B, "n_gpus": world, "value": round(world * fps, 2), "unit": "frames/s",
+                "per_session_fps": round(fps / n_sessions, 2), "ms_per_round": round(ms, 3), "bytes_per_session": int(per_sess),
+                "what": "%d concurrent %dx%d sessions per GPU, each batch %d on its own stream / graph" % (n_sessions, hw * 8, hw * 8, B)}
+
+    def close(self):
+        self.ctx.close()
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -660,10 +758,20 @@ def run_ours(args):
         guarded("sessions32", lambda: sessions_leg(torch, engine, model, av, audio, 32, max(5, min(args.steps, 20))))
         guarded("cross_session", lambda: cross_session_leg(engine, model, max(5, min(args.steps, 20))))
         guarded("torch_eager_b200", lambda: torch_eager_b200(torch))
-    if rank == 0 and not args.no_musetalk and not args.quick:
-        guarded("musetalk", lambda: musetalk_leg(torch, engine, args, peaks, 32))
-        if args.musetalk512:
-            guarded("musetalk512", lambda: musetalk_leg(torch, engine, args, peaks, 64))
+    if world > 1 and not args.quick:            # configs[3] at N > 1: 32 sessions on EVERY GPU (aggregate over ranks)
+        guarded("sessions32", lambda: sessions_leg(torch, engine, model, av, audio, 32, max(5, min(args.steps, 20)), dist, world))
+    if not args.no_musetalk and not args.quick:  # every rank runs the MuseTalk legs (collectives inside): same guard on all ranks
+        mt = None
+        try:
+            mt = MuseTalkBench(torch, dist, world, rank)
+            extras["musetalk"] = mt.leg(args, peaks, 32)
+            if not args.no_musetalk512:
+                extras["musetalk512"] = mt.leg(args, peaks, 64, n_sessions=8, B_sess=2)
+        except Exception as e:
+            extras.setdefault("musetalk", {"error": repr(e)[:300]})
+        finally:
+            if mt is not None:
+                mt.close()
     if world > 1:
         barrier()
 
@@ -714,7 +822,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-musetalk", action="store_true", help="skip the MuseTalk (configs[2]) leg")
-    ap.add_argument("--musetalk512", action="store_true", help="also run MuseTalk at 64x64 latents (configs[4])")
+    ap.add_argument("--no-musetalk512", action="store_true", help="skip MuseTalk at 64x64 latents (configs[4]: 512x512, 8 concurrent sessions)")
+    ap.add_argument("--musetalk512", action="store_true", help=argparse.SUPPRESS)   # accepted for compatibility: the leg is on by default
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--sustained-s", type=float, default=3.0)
     ap.add_argument("--quick", action="store_true", help="contract line only (value / e2e / roofline), no extra legs")
