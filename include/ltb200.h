@@ -200,6 +200,10 @@ typedef struct ltb_conv_op {
    * output tensor into gn_stats[N][gn_groups][2] — fused into the conv epilogue when the kernel supports it */
   void* gn_stats;
   int gn_groups, gn_hw;
+  /* 1: nearest-2x upsample fused with this 3x3 p1 s1 conv (diffusers Upsample2D: F.interpolate(scale 2, nearest) + conv): the
+   * input is the LOW-resolution map (N, IH, IW), OH = 2*IH, OW = 2*IW; `w` / `w_tap` hold the 16 pre-summed sub-pixel slices
+   * ([Cout][16][Cin] phase-major / [16][Cout][Cin] view-major, built by livetalking_b200.ops.ConvWeight.upconv()), Ktot = 16*Cin */
+  int upsample2x;
 } ltb_conv_op;
 int ltb_op_conv2d(ltb_ctx* c, const ltb_conv_op* d);
 int ltb_op_w_tap_major(ltb_ctx* c, const void* w, void* wt, int cout, int cin);

@@ -26,7 +26,7 @@ class ConvOp(C.Structure):
                                         "rc_off", "KH", "KW", "sy", "sx", "pad_t", "pad_l", "Ktot", "w_koff", "relu", "no_halo",
                                         "zbatch", "zdiv")] +
                 [(n, C.c_longlong) for n in ("in_zo", "in_zi", "w_zo", "w_zi", "out_zo", "out_zi")] +
-                [("gn_stats", C.c_void_p), ("gn_groups", C.c_int), ("gn_hw", C.c_int)])
+                [("gn_stats", C.c_void_p), ("gn_groups", C.c_int), ("gn_hw", C.c_int), ("upsample2x", C.c_int)])
 
 
 class MtPasteOp(C.Structure):

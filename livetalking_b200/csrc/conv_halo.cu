@@ -40,9 +40,10 @@ constexpr int kHaloP = 10;  // halo row pitch in pixels (8 + 2)
 // re-streamed weights were 60 % of all L2->SM traffic).  Requires Cout == BN (every tile uses the same weights).
 template <int BN, int NSUB, int NACC, int TAPS, int RC = 0>
 struct HaloCfg {
-  static constexpr int P = (TAPS == 9) ? kHaloP : 8;                        // halo row pitch (pixels)
-  static constexpr int HR = (TAPS == 9) ? 16 * NSUB + 2 : 16 * NSUB;        // halo rows
-  static constexpr int TG = (TAPS == 9) ? 3 : 1;                            // B stages per K chunk / taps per B stage
+  static constexpr bool HALO = (TAPS != 1);                                 // 9: 3x3 conv / ConvT, 16: nearest-2x upsample + 3x3 conv
+  static constexpr int P = HALO ? kHaloP : 8;                               // halo row pitch (pixels)
+  static constexpr int HR = HALO ? 16 * NSUB + 2 : 16 * NSUB;               // halo rows
+  static constexpr int TG = (TAPS == 9) ? 3 : (TAPS == 16 ? 4 : 1);         // B stages per K chunk / weight slices per B stage
   static constexpr int A_BYTES_RAW = HR * P * 128;                          // TMA transaction bytes per A stage
   static constexpr int A_BYTES = (A_BYTES_RAW + 1023) & ~1023;
   static constexpr int B_BYTES = TG * BN * 128;                             // TG taps x BN rows x 64 k
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr bool kHeadOk = (BN == 32 && NACC == 1 && TAPS == 9);
+  constexpr bool kHaloMode = C::HALO;
   if (kHeadOk && p.head_out && tid >= 64 && tid < 64 + 99) head_sw[tid - 64] = (tid - 64 < 96) ? p.head_w[tid - 64] : p.head_b[tid - 64 - 96];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = smem0;
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  const int tiles_m = (TAPS == 9) ? p.tiles_x * p.tiles_y * p.N : p.tiles_x;
+  const int tiles_m = kHaloMode ? p.tiles_x * p.tiles_y * p.N : p.tiles_x;
 
   // PDL: the next kernel of the stream may start its own prologue now; resident weights (constants) are fetched before
   // this kernel waits for its predecessor, everything that touches activations comes after pdl_wait()
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
     mbar_arrive_expect_tx(smem_u32(&b_full[0]), RC * C::TG * C::B_BYTES);
     for (int c = 0; c < RC; ++c)
       for (int j = 0; j < C::TG; ++j)
-        tma_load_3d(b_smem + (c * C::TG + j) * C::B_BYTES, &p.tm_w, smem_u32(&b_full[0]), c * 64, 0, j * 3);
+        tma_load_3d(b_smem + (c * C::TG + j) * C::B_BYTES, &p.tm_w, smem_u32(&b_full[0]), c * 64, 0, j * C::TG);
   }
   pdl_wait();
 
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
         const int nt = t / tiles_m;
         int mt = t - nt * tiles_m;
         int img = 0, y0 = 0, x0 = 0;
-        if (TAPS == 9) {
+        if (kHaloMode) {
           img = mt / (p.tiles_x * p.tiles_y);
           mt -= img * (p.tiles_x * p.tiles_y);
           const int ty = mt / p.tiles_x, tx = mt - ty * p.tiles_x;
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
             mbar_arrive(smem_u32(&a_full[as]));
           } else {
             mbar_arrive_expect_tx(smem_u32(&a_full[as]), C::A_BYTES_RAW);
-            if (TAPS == 9) tma_load_4d(a_smem + as * C::A_BYTES, &p.tm_in, smem_u32(&a_full[as]), c * 64, x0, y0, img);
+            if (kHaloMode) tma_load_4d(a_smem + as * C::A_BYTES, &p.tm_in, smem_u32(&a_full[as]), c * 64, x0, y0, img);
             else tma_load_2d(a_smem + as * C::A_BYTES, &p.tm_in, smem_u32(&a_full[as]), c * 64, mt * (128 * NSUB));
           }
           ++ai;
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
               continue;
             }
             mbar_arrive_expect_tx(smem_u32(&b_full[bs]), C::B_BYTES);
-            if (TAPS == 9) tma_load_3d(b_smem + bs * C::B_BYTES, &p.tm_w, smem_u32(&b_full[bs]), c * 64, nt * BN, j * 3);
+            if (kHaloMode) tma_load_3d(b_smem + bs * C::B_BYTES, &p.tm_w, smem_u32(&b_full[bs]), c * 64, nt * BN, j * C::TG);
             else tma_load_2d(b_smem + bs * C::B_BYTES, &p.tm_w, smem_u32(&b_full[bs]), c * 64, nt * BN);
             ++bi;
           }
@@ -178,12 +180,13 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
       uint32_t ai = 0, bi = 0, it = 0;
       // ConvT (NACC == 4): per-stage "fat" MMA list in registers (see HaloParams::fat): one instruction feeds every
       // sub-pixel accumulator that reads the same halo view, N = 64..256 instead of nine N = BN instructions
-      uint32_t fat_n[3], fat_aoff[3][3], fat_doff[3][3], fat_boff[3][3], fat_idesc[3][3], fat_acc0[3][3];
+      constexpr int FS = (NACC == 4) ? C::TG : 1, FQ = (NACC == 4) ? (TAPS == 16 ? 4 : 3) : 1;   // stages x instructions per stage
+      uint32_t fat_n[FS], fat_aoff[FS][FQ], fat_doff[FS][FQ], fat_boff[FS][FQ], fat_idesc[FS][FQ], fat_acc0[FS][FQ];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
+      for (int j = 0; j < FS; ++j) {
         fat_n[j] = (NACC == 4) ? (uint32_t)p.fat_n[j] : 0u;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int q = 0; q < FQ; ++q) {
           fat_aoff[j][q] = (uint32_t)p.fat[j][q].view * 8u;
           fat_doff[j][q] = (uint32_t)p.fat[j][q].dcol;
           fat_boff[j][q] = (uint32_t)p.fat[j][q].brow * 8u;
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
             if constexpr (NACC == 1) {
 #pragma unroll
               for (int tt = 0; tt < C::TG; ++tt) {
-                const uint32_t aoff = (TAPS == 9) ? (uint32_t)(j * C::P + tt) * 8u : 0u;
+                const uint32_t aoff = kHaloMode ? (uint32_t)(j * C::P + tt) * 8u : 0u;
                 const uint32_t acc0 = later | ((j | tt) ? 1u : 0u);
 #pragma unroll
                 for (int sub = 0; sub < NSUB; ++sub) {
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
               }
             } else {
 #pragma unroll
-              for (int q = 0; q < 3; ++q) {
+              for (int q = 0; q < FQ; ++q) {
                 if (q < (int)fat_n[j]) {   // warp-uniform
                   const uint32_t d = dbase + fat_doff[j][q];
                   const uint32_t a_lo = a_lo0 + fat_aoff[j][q];
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
       const int nt = t / tiles_m;
       int mt = t - nt * tiles_m;
       int img = 0, ty = 0, tx = 0;
-      if (TAPS == 9) {
+      if (kHaloMode) {
         img = mt / (p.tiles_x * p.tiles_y);
         mt -= img * (p.tiles_x * p.tiles_y);
         ty = mt / p.tiles_x;
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
         sub = ((ci * 32) / BN) % NSUB;
         c0 = (ci * 32) % BN;
         row_ok = true;
-        if (TAPS == 9) {
+        if (kHaloMode) {
           const int gy = ty * (16 * NSUB) + sub * 16 + ry, gx = tx * 8 + rx;
           opix = ((size_t)img * p.OH + gy * p.osy + p.acc_oy[acc]) * p.OW + gx * p.osx + p.acc_ox[acc];
           row_ok = gy < p.GH && gx < p.GW;   // tiles may overhang small / odd-sized maps
@@ -457,7 +460,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
             if (p.gn_stats) {
               const int ng = p.gn_cpg >= 32 ? 1 : 32 / p.gn_cpg;
               int gimg = img;
-              if (TAPS != 9) gimg = (int)(((size_t)mt * (128 * NSUB) + sub * 128 + q * 32) / (size_t)p.gn_hw);
+              if (!kHaloMode) gimg = (int)(((size_t)mt * (128 * NSUB) + sub * 128 + q * 32) / (size_t)p.gn_hw);
               float* sbase = p.gn_stats + ((size_t)gimg * p.gn_groups + (n0 + c0) / p.gn_cpg) * 2;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -535,6 +538,11 @@ static bool is_convT(const ConvParams& p) {
   return p.IH == p.GH && p.IW == p.GW && p.OH == 2 * p.GH && p.OW == 2 * p.GW;
 }
 
+static bool is_upconv(const ConvParams& p) {
+  return p.upconv == 1 && p.nphases == 4 && p.osy == 2 && p.osx == 2 && p.sy == 1 && p.sx == 1 && p.IH == p.GH && p.IW == p.GW &&
+         p.OH == 2 * p.GH && p.OW == 2 * p.GW && p.zbatch <= 1;
+}
+
 static bool is_gemm(const ConvParams& p) {
   return p.nphases == 1 && p.ph[0].ntaps == 1 && p.ph[0].dy[0] == 0 && p.ph[0].dx[0] == 0 && p.sy == 1 && p.sx == 1 && p.osy == 1 &&
          p.osx == 1 && p.IH == p.GH && p.IW == p.GW && p.OH == p.GH && p.OW == p.GW && p.zbatch <= 1;
@@ -548,6 +556,8 @@ bool conv_halo_supported(const ConvParams& p) {
     return p.Cout % 32 == 0 && p.Cin % 8 == 0 && p.Cin >= 32 && (p.ICtot % 8) == 0 && (p.ic_off % 8) == 0 && (p.Ktot % 8) == 0 &&
            (p.ph[0].koff % 8) == 0 && p.M >= 512 && get_encode() != nullptr;
   }
+  if (is_upconv(p))
+    return p.Cout % 64 == 0 && p.Cin >= 16 && (p.ICtot % 8) == 0 && (p.ic_off % 8) == 0 && p.Ktot == 16 * p.Cin && get_encode() != nullptr;
   if (!(is_conv3x3(p) || is_convT(p))) return false;
   // tiles of 16*NSUB x 8 pixels may overhang the map (TMA zero-fills the halo, the epilogue masks the stores): small maps
   // (8x8, 4x4 ...) waste MMA rows but still beat the latency-bound gather kernel
@@ -601,6 +611,12 @@ static bool pick_cfg(const ConvParams& p, int* BN, int* NSUB, int* NACC) {
     while (*BN > 32 && tiles(*BN, *NSUB) < 120) *BN >>= 1;
     return true;
   }
+  if (is_upconv(p)) {
+    *NACC = 4;
+    *NSUB = 1;
+    *BN = 64;
+    return true;
+  }
   const bool tr = is_convT(p);
   *NACC = tr ? 4 : 1;
   if (tr) {
@@ -650,9 +666,10 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
   out->BN = BN;
   out->NSUB = NSUB;
   out->NACC = NACC;
-  const bool tr = NACC == 4;
+  const bool up = is_upconv(p);
+  const bool tr = NACC == 4 && !up;
   const bool gemm = is_gemm(p);
-  out->TAPS = gemm ? 1 : 9;
+  out->TAPS = gemm ? 1 : (up ? 16 : 9);
   if (gemm) {
     // A: 2-D (K, rows) ; B: 2-D (K, Cout) over the layer's own K-major weight rows
     cuuint64_t dims[2] = {(cuuint64_t)p.Cin, (cuuint64_t)p.M};
@@ -678,6 +695,12 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
     cuuint64_t strides[3] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Cout * p.Cin * 2, (cuuint64_t)3 * p.Cout * p.Cin * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)BN, 1, 3};
     if (!encode(&h.tm_w, 4, w_tap_major, dims, strides, box)) return 2;
+  } else if (up) {
+    // 16 view-major slices [16][Cout][Cin], four per weight stage
+    cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, 16};
+    cuuint64_t strides[2] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Cout * p.Cin * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)BN, 4};
+    if (!encode(&h.tm_w, 3, w_tap_major, dims, strides, box)) return 2;
   } else if (!gemm) {
     cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, 9};
     cuuint64_t strides[2] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Cout * p.Cin * 2};
@@ -713,7 +736,35 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
   h.relu = p.relu;
   h.halo_y0 = tr ? 0 : -1;
   h.halo_x0 = tr ? 0 : -1;
-  if (tr) {
+  if (up) {
+    // Upsample(nearest 2x) + conv3x3: output phase (a, b) = 2x2 conv over the low-res halo.  Phase a reads halo rows {-1, 0}
+    // (a = 0) or {0, +1} (a = 1); 16 (phase, view) slices, stored view-major so that one instruction per halo view feeds every
+    // phase that reads it (accumulator slots p00, p01, p11, p10 as for ConvT):
+    //   stage 0: view( 0, 0) -> all four slots                                   (N = 4*BN)
+    //   stage 1: view(-1, 0) -> p00,p01 ; view( 0,+1) -> p01,p11                 (N = 2*BN each)
+    //   stage 2: view(+1, 0) -> p11,p10 ; view( 0,-1) -> p00 ; view( 0,-1) -> p10
+    //   stage 3: the four corner views, one slot each
+    // 10 instructions per K step instead of 4 pixels x 9 taps = 36 on the upsampled map (and no upsampled tensor in HBM).
+    const int slot_phase[4] = {0, 1, 3, 2};
+    for (int sl = 0; sl < 4; ++sl) {
+      h.acc_oy[sl] = p.ph[slot_phase[sl]].ooy;
+      h.acc_ox[sl] = p.ph[slot_phase[sl]].oox;
+    }
+    auto view = [](int vy, int vx) { return (vy + 1) * kHaloP + (vx + 1); };
+    struct G { int stage, view, slot0, brow, nslots, first; };
+    const G groups[10] = {{0, view(0, 0), 0, 0, 4, 1},
+                          {1, view(-1, 0), 0, 0, 2, 0}, {1, view(0, 1), 1, 2, 2, 0},
+                          {2, view(1, 0), 2, 0, 2, 0},  {2, view(0, -1), 0, 2, 1, 0}, {2, view(0, -1), 3, 3, 1, 0},
+                          {3, view(-1, -1), 0, 0, 1, 0}, {3, view(-1, 1), 1, 1, 1, 0}, {3, view(1, 1), 2, 2, 1, 0}, {3, view(1, -1), 3, 3, 1, 0}};
+    for (const G& g : groups) {
+      HaloParams::FatMma& f = h.fat[g.stage][h.fat_n[g.stage]++];
+      f.view = g.view;
+      f.dcol = g.slot0 * BN;
+      f.brow = g.brow * BN;
+      f.n = g.nslots * BN;     // BN = 64: at most 256
+      f.first = g.first;
+    }
+  } else if (tr) {
     // accumulator slots p0, p1, p3, p2 (phase index = oy*2 + ox): slots that share a halo view are adjacent
     const int slot_phase[4] = {0, 1, 3, 2};
     for (int sl = 0; sl < 4; ++sl) {
@@ -775,6 +826,7 @@ cudaError_t launch_conv_halo(const HaloPlan& pl, cudaStream_t st) {
     sms_cached.store(sms);
   }
   if (pl.YS) return launch_conv_ystack(pl, sms, st);
+  if (pl.TAPS == 16) return (pl.BN == 64 && pl.NSUB == 1 && pl.NACC == 4) ? launch_cfg<64, 1, 4, 16>(pl, sms, st) : cudaErrorInvalidValue;
   const int key = pl.BN * 100 + pl.NSUB * 10 + pl.NACC;
   if (pl.TAPS == 1) {
     switch (key) {

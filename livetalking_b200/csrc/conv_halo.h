@@ -34,8 +34,8 @@ struct alignas(64) HaloParams {
     int n;      // MMA N (multiple of 16, <= 256)
     int first;  // 1 = overwrite on the first K chunk (first instruction that touches these columns)
   };
-  int fat_n[3];
-  FatMma fat[3][3];
+  int fat_n[4];
+  FatMma fat[4][4];   // ConvT: 3 stages x <= 3; upsample+conv (TAPS = 16): 4 stages x <= 4
   int acc_oy[4], acc_ox[4];
   int tiles_x, tiles_y, tiles_n, total_tiles;
   int tile_rows;         // output rows per tile: 16*NSUB, or 16*NSUB - 2 for the y-stacked kernel (tiles overlap by two MMA rows)

@@ -51,6 +51,10 @@ struct ConvParams {
   // their fp32 partial tile to ws[split][M][Cout]; splitk_finalize sums the slices and applies bias/residual/activation.
   int ksplit;
   float* ws;
+  // 1: nearest-neighbour 2x upsample fused with the 3x3 p1 conv that follows it (diffusers Upsample2D): 4 output phases, each a
+  // 2x2 conv over the LOW-resolution input with pre-summed taps (16 weight slices [Cout][16][Cin], see ops.py
+  // ConvWeight.upconv).  Halo kernel only (no gather fallback).
+  int upconv;
 };
 
 }  // namespace ltb

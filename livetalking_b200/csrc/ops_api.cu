@@ -230,6 +230,32 @@ int ltb_op_conv2d(ltb_ctx* c, const ltb_conv_op* d) {
       p.ph[0].dy[kh * d->KW + kw] = (signed char)(kh - d->pad_t);
       p.ph[0].dx[kh * d->KW + kw] = (signed char)(kw - d->pad_l);
     }
+  if (d->upsample2x) {
+    if (d->KH != 3 || d->KW != 3 || d->sy != 1 || d->sx != 1 || d->pad_t != 1 || d->pad_l != 1 || d->OH != 2 * d->IH || d->OW != 2 * d->IW ||
+        d->Ktot != 16 * d->Cin || !d->w_tap || d->zbatch > 1)
+      return LTB_FAIL("conv2d: upsample2x needs a 3x3 s1 p1 conv, OH = 2*IH, OW = 2*IW and the 16-slice weights");
+    // four sub-pixel phases over the low-resolution grid: phase (a, b) reads rows {-1, 0} (a = 0) or {0, +1} (a = 1)
+    p.GH = d->IH;
+    p.GW = d->IW;
+    p.M = d->N * d->IH * d->IW;
+    p.osy = p.osx = 2;
+    p.nphases = 4;
+    p.upconv = 1;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        ConvPhase& ph = p.ph[a * 2 + b];
+        ph.ntaps = 4;
+        ph.koff = (a * 2 + b) * 4 * d->Cin;
+        ph.ooy = a;
+        ph.oox = b;
+        for (int ry = 0; ry < 2; ++ry)
+          for (int rx = 0; rx < 2; ++rx) {
+            ph.dy[ry * 2 + rx] = (signed char)(ry - 1 + a);
+            ph.dx[ry * 2 + rx] = (signed char)(rx - 1 + b);
+          }
+      }
+    if (!conv_halo_supported(p)) return LTB_FAIL("conv2d: upsample2x: geometry not supported by the halo kernel (Cout % 64, Cin % 8)");
+  }
   p.zbatch = d->zbatch;
   p.zdiv = d->zdiv > 0 ? d->zdiv : 1;
   p.in_zo = d->in_zo;

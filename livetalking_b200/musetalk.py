@@ -241,8 +241,15 @@ class Builder:
         tok = self.linear(gg, t.ff2, res=tok)
         return self.linear(tok, t.proj_out, res=x)
 
+    # Upsample2D (nearest 2x + conv3x3) as ONE kernel: four 2x2 sub-pixel convs over the low-res map (ops.ConvWeight.upconv).
+    FUSE_UPSAMPLE = os.environ.get("LTB_FUSE_UPSAMPLE", "1") == "1"
+
     def upsample(self, x: DevTensor, w: ConvWeight):
         N, H, W, C = x.shape
+        if self.FUSE_UPSAMPLE and w.upconv_supported() and x.pitch % 8 == 0 and x.c_off % 8 == 0:
+            out = self.new(N, 2 * H, 2 * W, w.cout)
+            self.ctx.conv(x, w, out, N=N, IH=H, IW=W, OH=2 * H, OW=2 * W, pad=(1, 1), upsample2x=True)
+            return out
         up = self.new(N, 2 * H, 2 * W, C)
         self.ctx.upsample2x(x, N, H, W, up)
         return self.conv3(up, w, stats=True)

@@ -205,3 +205,32 @@ def test_fused_groupnorm_statistics_path(small_nets):
     assert psnr_u8(outs[0], outs[1]) >= 48.0
     want = M.decode_latents_u8(vs, vcfg, M.unet_forward(us, ucfg, lat, M.positional_encoding(aud)))
     assert psnr_u8(outs[1], want) >= 40.0
+
+
+@pytest.mark.parametrize("shape", [(2, 12, 10, 64, 64), (1, 32, 32, 128, 128), (3, 8, 8, 320, 192)], ids=["ragged", "2tiles_n", "5chunks"])
+def test_fused_upsample_conv_matches_interpolate_plus_conv(shape):
+    """Upsample2D (F.interpolate nearest 2x + conv3x3 p1) as four sub-pixel 2x2 convs over the low-res map (ops.ConvWeight.upconv,
+    conv_halo.cu TAPS = 16) against plain PyTorch fp32 of the same op.  Tolerance: fp16 in/out, fp32 accumulate, and the pre-summed
+    taps are rounded to fp16 once (|err| <= 3e-2 + 1.5e-2 |ref|)."""
+    import torch.nn.functional as F
+    from livetalking_b200 import engine
+    from livetalking_b200.ops import ConvWeight, Ctx
+    engine.set_device(0)
+    N, H, W, cin, cout = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = (torch.randn(N, cin, H, W, generator=g) * 0.7).half()
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.2
+    ref = F.conv2d(F.interpolate(x.float(), scale_factor=2.0, mode="nearest"), w.half().float(), b, padding=1)
+    ref = ref.permute(0, 2, 3, 1).contiguous().numpy()
+    ctx = Ctx()
+    cw = ConvWeight(ctx, w.numpy(), b.numpy())
+    assert cw.upconv_supported()
+    dx = ctx.upload(x.permute(0, 2, 3, 1).contiguous().numpy())
+    out = ctx.alloc((N, 2 * H, 2 * W, cout), np.float16, zero=True)
+    ctx.conv(dx, cw, out, N=N, IH=H, IW=W, OH=2 * H, OW=2 * W, pad=(1, 1), upsample2x=True)
+    got = ctx.download(out).astype(np.float32)
+    err = np.abs(got - ref)
+    assert (err <= 3e-2 + 1.5e-2 * np.abs(ref)).all(), f"max err {err.max():.4f} at {np.unravel_index(err.argmax(), err.shape)}"
+    assert err.mean() < 3e-3
+    ctx.close()
