@@ -76,9 +76,17 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float head_sw[100];   // fused head: 3 x 32 weights + 3 biases
+  // fused GroupNorm statistics: (sum, sum of squares) per (image, group) accumulated in SHARED memory across all tiles of this
+  // persistent CTA and flushed with one global atomic per entry at the end.  (Round 1 issued global float atomics from every
+  // epilogue warp and item on the same few addresses and measured slower than a separate statistics pass.)
+  constexpr int kGnSmem = (NACC == 1) ? 2048 : 1;
+  __shared__ float gn_acc[kGnSmem];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr bool kHeadOk = (BN == 32 && NACC == 1 && TAPS == 9);
+  const bool gn_smem = NACC == 1 && p.gn_stats != nullptr && p.gn_images * p.gn_groups * 2 <= kGnSmem;
+  if (gn_smem)
+    for (int i = tid; i < p.gn_images * p.gn_groups * 2; i += 320) gn_acc[i] = 0.f;
   constexpr bool kHaloMode = C::HALO;
   if (kHeadOk && p.head_out && tid >= 64 && tid < 64 + 99) head_sw[tid - 64] = (tid - 64 < 96) ? p.head_w[tid - 64] : p.head_b[tid - 64 - 96];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -461,7 +469,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
               const int ng = p.gn_cpg >= 32 ? 1 : 32 / p.gn_cpg;
               int gimg = img;
               if (!kHaloMode) gimg = (int)(((size_t)mt * (128 * NSUB) + sub * 128 + q * 32) / (size_t)p.gn_hw);
-              float* sbase = p.gn_stats + ((size_t)gimg * p.gn_groups + (n0 + c0) / p.gn_cpg) * 2;
+              float* sbase = (gn_smem ? gn_acc : p.gn_stats) + ((size_t)gimg * p.gn_groups + (n0 + c0) / p.gn_cpg) * 2;
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 if (i < ng) {
@@ -490,6 +498,12 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (gn_smem) {
+    for (int i = tid; i < p.gn_images * p.gn_groups * 2; i += 320) {
+      const float v = gn_acc[i];
+      if (v != 0.f) atomicAdd(p.gn_stats + i, v);
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem, C::TCOLS);

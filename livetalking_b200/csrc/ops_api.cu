@@ -278,6 +278,7 @@ int ltb_op_conv2d(ltb_ctx* c, const ltb_conv_op* d) {
       pl.hp.gn_groups = d->gn_groups;
       pl.hp.gn_cpg = d->Cout / d->gn_groups;
       pl.hp.gn_hw = d->gn_hw;
+      pl.hp.gn_images = p.M / d->gn_hw;
       stats_fused = true;
     }
     e = launch_conv_halo(pl, c->st);
