@@ -15,6 +15,7 @@ Extra keys on the same JSON line (all measured in this run):
   sustained         the same step loop run for >= 3 s with the clock / power trace
   e2e_plugin        fps through the reference-facing hooks exactly as avatars/base_avatar.py calls them:
                     MelASR features -> LipReal.inference_batch -> 16 x paste_back_frame (host arrays in and out)
+  e2e_plugin_threads the same hooks under the reference's three-thread driving (one session, un-paced)
   sessions32        BASELINE configs[3]: 32 concurrent sessions on this GPU, each batch 16 (per-session fps, arena bytes)
   cross_session     the batching scheduler's engine call: 16 slots from 8 different sessions in one forward + paste launch
   musetalk          BASELINE configs[2] (MuseTalk 256x256 batch 8, fp16): value / e2e / roofline of its own
@@ -348,6 +349,59 @@ def plugin_e2e(engine, model, av_lists, audio, steps, warmup):
     return {"value": round(BATCH * steps / dt, 1), "unit": "frames/s", "ms_per_step": round(1000.0 * dt / steps, 3),
             "how": "MelASR features + LipReal.inference_batch + 16 x paste_back_frame, host numpy in/out, one thread, wall clock",
             "d2h_bytes_per_step": BATCH * FRAME_H * FRAME_W * 3}
+
+
+def plugin_threads(engine, model, av_lists, n_frames=480):
+    """The same hooks driven the way the reference drives them: three threads (asr.run_step | inference_batch | paste_back_frame,
+    avatars/base_avatar.py:469-501) with the reference's bounded queues, speech fed as fast as the session drains it, frames
+    pushed to a counting sink.  Un-paced throughput of ONE session through the full host pipeline."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import stubs
+    stubs.install()
+    from livetalking_b200.plugin import wav2lip_avatar as P
+    frames, faces, coords = av_lists
+    lip = P.LipReal(stubs.Opt(batch_size=BATCH, fps=FPS, l=SL, r=SR), model, P.make_avatar(frames, faces, coords))
+
+    class Sink:
+        n, t_first, t_last = 0, None, None
+
+        def push_video_frame(self, f):
+            now = time.perf_counter()
+            if self.t_first is None:
+                self.t_first = now
+            self.t_last = now
+            self.n += 1
+
+        def push_audio_frame(self, a, u):
+            pass
+
+    sink, quit_event = Sink(), threading.Event()
+    rng = np.random.default_rng(0)
+    chunk = (0.2 * rng.standard_normal(320)).astype(np.float32)
+
+    def feeder():
+        while not quit_event.is_set():
+            if lip.asr.queue.qsize() < 4 * BATCH:
+                for _ in range(2 * BATCH):
+                    lip.asr.put_audio_frame(chunk, {})
+            else:
+                time.sleep(0.0005)
+
+    th = threading.Thread(target=stubs.run_three_threads, args=(lip, sink, quit_event))
+    fd = threading.Thread(target=feeder)
+    fd.start()
+    th.start()
+    t0 = time.time()
+    while sink.n < n_frames + 4 * BATCH and time.time() - t0 < 60:
+        time.sleep(0.005)
+    quit_event.set()
+    th.join(timeout=30)
+    fd.join(timeout=5)
+    n, dt = sink.n, (sink.t_last - sink.t_first) if sink.n > 1 else 1.0
+    lip.engine_session.close()
+    return {"value": round((n - 1) / dt, 1), "unit": "frames/s", "frames": n,
+            "how": "one session, three threads + bounded queues as avatars/base_avatar.py:469-501 (run_step | inference_batch | paste_back_frame), "
+                   "speech fed on demand, counting sink, wall clock between first and last frame"}
 
 
 def sessions_leg(torch, engine, model, av, audio, n_sessions, steps, dist=None, world=1):
@@ -755,6 +809,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.quick:
         guarded("e2e_plugin", lambda: plugin_e2e(engine, model, (list(frames), list(faces), [tuple(c) for c in coords]), audio,
                                                   max(5, min(args.steps, 20)), 3))
+        guarded("e2e_plugin_threads", lambda: plugin_threads(engine, model, (list(frames), list(faces), [tuple(c) for c in coords])))
         guarded("sessions32", lambda: sessions_leg(torch, engine, model, av, audio, 32, max(5, min(args.steps, 20))))
         guarded("cross_session", lambda: cross_session_leg(engine, model, max(5, min(args.steps, 20))))
         guarded("torch_eager_b200", lambda: torch_eager_b200(torch))
