@@ -41,15 +41,19 @@ constexpr int kHaloP = 10;  // halo row pitch in pixels (8 + 2)
 template <int BN, int NSUB, int NACC, int TAPS, int RC = 0>
 struct HaloCfg {
   static constexpr bool HALO = (TAPS != 1);                                 // 9: 3x3 conv / ConvT, 16: nearest-2x upsample + 3x3 conv
-  static constexpr int P = HALO ? kHaloP : 8;                               // halo row pitch (pixels)
-  static constexpr int HR = HALO ? 16 * NSUB + 2 : 16 * NSUB;               // halo rows
-  static constexpr int TG = (TAPS == 9) ? 3 : (TAPS == 16 ? 4 : 1);         // B stages per K chunk / weight slices per B stage
-  static constexpr int A_BYTES_RAW = HR * P * 128;                          // TMA transaction bytes per A stage
-  static constexpr int A_BYTES = (A_BYTES_RAW + 1023) & ~1023;
+  static constexpr bool S2 = (TAPS == 10);                                  // 10: 3x3 stride-2 pad-1 conv over four parity planes
+  static constexpr int P = S2 ? 9 : (HALO ? kHaloP : 8);                    // halo row pitch (pixels)
+  static constexpr int HR = S2 ? 16 * NSUB + 1 : (HALO ? 16 * NSUB + 2 : 16 * NSUB);   // halo rows
+  static constexpr int TG = (TAPS == 9 || TAPS == 10) ? 3 : (TAPS == 16 ? 4 : 1);      // B stages per K chunk / weight slices per B stage
+  // stride 2: input pixel (2y+dy-1, 2x+dx-1) lies in parity plane (row even/odd, col even/odd); each plane is TMA-loaded with
+  // traversal stride 2 into its own (HR x P) sub-tile, the nine taps are views into the four planes
+  static constexpr int PLANE_BYTES = (HR * P * 128 + 1023) & ~1023;
+  static constexpr int A_BYTES_RAW = (S2 ? 4 : 1) * HR * P * 128;           // TMA transaction bytes per A stage
+  static constexpr int A_BYTES = S2 ? 4 * PLANE_BYTES : ((A_BYTES_RAW + 1023) & ~1023);
   static constexpr int B_BYTES = TG * BN * 128;                             // TG taps x BN rows x 64 k
   // stage counts: fill the 227 KB of shared memory
   static constexpr int BUDGET = 223 * 1024;   // 227 KB per CTA minus ~3.5 KB of static shared memory (barriers, head weights, GN table)
-  static constexpr int A_STAGES_STREAM = (BN <= 32) ? 4 : (BN <= 64 ? 3 : (NSUB == 1 ? 3 : 2));
+  static constexpr int A_STAGES_STREAM = S2 ? 2 : ((BN <= 32) ? 4 : (BN <= 64 ? 3 : (NSUB == 1 ? 3 : 2)));
   static constexpr int A_STAGES_RES = ((BUDGET - RC * TG * B_BYTES) / A_BYTES) > 4 ? 4 : ((BUDGET - RC * TG * B_BYTES) / A_BYTES);
   static constexpr int A_STAGES = RC ? A_STAGES_RES : A_STAGES_STREAM;
   static constexpr int B_STAGES_MAX = (BUDGET - A_STAGES * A_BYTES) / B_BYTES;
@@ -156,7 +160,13 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
             mbar_arrive(smem_u32(&a_full[as]));
           } else {
             mbar_arrive_expect_tx(smem_u32(&a_full[as]), C::A_BYTES_RAW);
-            if (kHaloMode) tma_load_4d(a_smem + as * C::A_BYTES, &p.tm_in, smem_u32(&a_full[as]), c * 64, x0, y0, img);
+            if (C::S2) {
+              // plane (rp, cp): rows of parity rp, columns of parity cp.  Odd planes start one plane-pixel early (input index 2*x0 - 1)
+#pragma unroll
+              for (int pl = 0; pl < 4; ++pl)
+                tma_load_4d(a_smem + as * C::A_BYTES + pl * C::PLANE_BYTES, &p.tm_in, smem_u32(&a_full[as]), c * 64,
+                            2 * (x0 + 1) - (pl & 1), 2 * (y0 + 1) - (pl >> 1), img);
+            } else if (kHaloMode) tma_load_4d(a_smem + as * C::A_BYTES, &p.tm_in, smem_u32(&a_full[as]), c * 64, x0, y0, img);
             else tma_load_2d(a_smem + as * C::A_BYTES, &p.tm_in, smem_u32(&a_full[as]), c * 64, mt * (128 * NSUB));
           }
           ++ai;
@@ -227,7 +237,9 @@ __global__ void __launch_bounds__(320, 1) conv_halo_umma_kernel(const __grid_con
             if constexpr (NACC == 1) {
 #pragma unroll
               for (int tt = 0; tt < C::TG; ++tt) {
-                const uint32_t aoff = kHaloMode ? (uint32_t)(j * C::P + tt) * 8u : 0u;
+                // stride 2: tap (dy = j, dx = tt) reads plane (dy != 1, dx != 1) at view (dy == 2, dx == 2)
+                const uint32_t aoff = C::S2 ? (uint32_t)(((j != 1) * 2 + (tt != 1)) * (C::PLANE_BYTES / 16) + ((j == 2) * C::P + (tt == 2)) * 8)
+                                            : (kHaloMode ? (uint32_t)(j * C::P + tt) * 8u : 0u);
                 const uint32_t acc0 = later | ((j | tt) ? 1u : 0u);
 #pragma unroll
                 for (int sub = 0; sub < NSUB; ++sub) {
@@ -529,10 +541,10 @@ static EncodeTiledFn get_encode() {
 }
 
 static bool encode(CUtensorMap* tm, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                   const cuuint32_t* box) {
+                   const cuuint32_t* box, int spatial_stride = 1) {
   EncodeTiledFn fn = get_encode();
   if (!fn) return false;
-  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  cuuint32_t es[5] = {1, (cuuint32_t)spatial_stride, (cuuint32_t)spatial_stride, 1, 1};   // traversal stride of the W and H dimensions
   return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -552,6 +564,13 @@ static bool is_convT(const ConvParams& p) {
   return p.IH == p.GH && p.IW == p.GW && p.OH == 2 * p.GH && p.OW == 2 * p.GW;
 }
 
+static bool is_conv3x3_s2(const ConvParams& p) {
+  if (p.nphases != 1 || p.ph[0].ntaps != 9 || p.sy != 2 || p.sx != 2 || p.osy != 1 || p.osx != 1 || p.zbatch > 1) return false;
+  for (int t = 0; t < 9; ++t)
+    if (p.ph[0].dy[t] != t / 3 - 1 || p.ph[0].dx[t] != t % 3 - 1) return false;
+  return p.IH == 2 * p.GH && p.IW == 2 * p.GW && p.OH == p.GH && p.OW == p.GW;
+}
+
 static bool is_upconv(const ConvParams& p) {
   return p.upconv == 1 && p.nphases == 4 && p.osy == 2 && p.osx == 2 && p.sy == 1 && p.sx == 1 && p.IH == p.GH && p.IW == p.GW &&
          p.OH == 2 * p.GH && p.OW == 2 * p.GW && p.zbatch <= 1;
@@ -569,6 +588,15 @@ bool conv_halo_supported(const ConvParams& p) {
     // TMA GEMM: K-major rows with 16-byte aligned pitch; worth it from a few M tiles upwards
     return p.Cout % 32 == 0 && p.Cin % 8 == 0 && p.Cin >= 32 && (p.ICtot % 8) == 0 && (p.ic_off % 8) == 0 && (p.Ktot % 8) == 0 &&
            (p.ph[0].koff % 8) == 0 && p.M >= 512 && get_encode() != nullptr;
+  }
+  if (is_conv3x3_s2(p)) {
+    // parity-plane TMA path: worth it while the 16-row tiles are mostly full (the 8x8 / 4x4 output maps stay on the split-K gather kernel)
+    static const bool off = [] {
+      const char* e = std::getenv("LTB_NO_S2_TMA");
+      return e && e[0] && e[0] != '0';
+    }();
+    return !off && p.Cout % 32 == 0 && p.Cin >= 16 && (p.ICtot % 8) == 0 && (p.ic_off % 8) == 0 && p.Ktot == 9 * p.Cin && p.GH >= 16 &&
+           p.GW >= 8 && get_encode() != nullptr;
   }
   if (is_upconv(p))
     return p.Cout % 64 == 0 && p.Cin >= 16 && (p.ICtot % 8) == 0 && (p.ic_off % 8) == 0 && p.Ktot == 16 * p.Cin && get_encode() != nullptr;
@@ -631,6 +659,12 @@ static bool pick_cfg(const ConvParams& p, int* BN, int* NSUB, int* NACC) {
     *BN = 64;
     return true;
   }
+  if (is_conv3x3_s2(p)) {
+    *NACC = 1;
+    *NSUB = 1;
+    *BN = (p.Cout % 64 == 0) ? 64 : 32;
+    return true;
+  }
   const bool tr = is_convT(p);
   *NACC = tr ? 4 : 1;
   if (tr) {
@@ -681,9 +715,10 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
   out->NSUB = NSUB;
   out->NACC = NACC;
   const bool up = is_upconv(p);
+  const bool s2 = is_conv3x3_s2(p);
   const bool tr = NACC == 4 && !up;
   const bool gemm = is_gemm(p);
-  out->TAPS = gemm ? 1 : (up ? 16 : 9);
+  out->TAPS = gemm ? 1 : (up ? 16 : (s2 ? 10 : 9));
   if (gemm) {
     // A: 2-D (K, rows) ; B: 2-D (K, Cout) over the layer's own K-major weight rows
     cuuint64_t dims[2] = {(cuuint64_t)p.Cin, (cuuint64_t)p.M};
@@ -700,7 +735,11 @@ int conv_halo_make_plan(const ConvParams& p, const __half* w_tap_major, HaloPlan
     cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.IW, (cuuint64_t)p.IH, (cuuint64_t)p.N};
     cuuint64_t strides[3] = {(cuuint64_t)p.ICtot * 2, (cuuint64_t)p.IW * p.ICtot * 2, (cuuint64_t)p.IH * p.IW * p.ICtot * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)kHaloP, (cuuint32_t)(ys ? 16 * NSUB : 16 * NSUB + 2), 1};
-    if (!encode(&h.tm_in, 4, p.in + p.ic_off, dims, strides, box)) return 2;
+    if (s2) {   // one parity plane per load: 9 x (16*NSUB + 1) pixels picked with traversal stride 2 (box extent 2n - 1)
+      box[1] = 2 * 9 - 1;
+      box[2] = 2 * (16 * NSUB + 1) - 1;
+    }
+    if (!encode(&h.tm_in, 4, p.in + p.ic_off, dims, strides, box, s2 ? 2 : 1)) return 2;
   }
   // weights: 3-D (k = Cin, n = Cout, tap = 9) view of the tap-major copy [9][Cout][Cin]
   if (ys) {
@@ -840,6 +879,10 @@ cudaError_t launch_conv_halo(const HaloPlan& pl, cudaStream_t st) {
     sms_cached.store(sms);
   }
   if (pl.YS) return launch_conv_ystack(pl, sms, st);
+  if (pl.TAPS == 10) {
+    if (pl.NSUB != 1 || pl.NACC != 1) return cudaErrorInvalidValue;
+    return pl.BN == 64 ? launch_cfg<64, 1, 1, 10>(pl, sms, st) : (pl.BN == 32 ? launch_cfg<32, 1, 1, 10>(pl, sms, st) : cudaErrorInvalidValue);
+  }
   if (pl.TAPS == 16) return (pl.BN == 64 && pl.NSUB == 1 && pl.NACC == 4) ? launch_cfg<64, 1, 4, 16>(pl, sms, st) : cudaErrorInvalidValue;
   const int key = pl.BN * 100 + pl.NSUB * 10 + pl.NACC;
   if (pl.TAPS == 1) {

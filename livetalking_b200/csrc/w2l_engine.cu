@@ -211,8 +211,9 @@ struct Tensor {
 };
 struct Op {
   int type;  // 0 = conv (gather kernel), 1 = prep, 2 = audio conv0, 3 = head, 4 = conv (halo kernel), 5 = stem (tensor-core),
-             // 6 = mel of the resident PCM chunk (skipped when the host supplies mel windows)
+             // 6 = mel of the resident PCM chunk (skipped when the host supplies mel windows), 7 = 1x1-map conv (fc_rows)
   ConvParams cp;
+  FcParams fc;
   int halo = -1;    // index into the session's halo plans (type 4)
   int branch = 0;   // 1 = audio-encoder branch: runs on the side stream, concurrently with the face encoder
   bool join = false;  // first op that consumes the audio branch's result
@@ -226,6 +227,7 @@ struct LayerOut {
 struct ltb_w2l_session {
   ltb_w2l_model* m = nullptr;
   ltb_w2l_avatar* a = nullptr;
+  int device = 0;   // copied from the model: entry points and the destructor must not dereference a model that may be gone
   int B = 0, l = 10, r = 10, fps = 25, flags = 0;
   cudaStream_t st = nullptr;
   cudaStream_t st2 = nullptr;  // audio-encoder branch (forked/joined with events; becomes a parallel branch of the graph)
@@ -291,7 +293,7 @@ static int dev_alloc(ltb_w2l_session* s, size_t bytes, void** out, bool zero) {
 // fresh render / inference / process threads, which default to device 0).
 static inline int enter(const ltb_w2l_session* s) {
   int cur = -1;
-  if (cudaGetDevice(&cur) != cudaSuccess || cur != s->m->device) LTB_CUDA(cudaSetDevice(s->m->device));
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != s->device) LTB_CUDA(cudaSetDevice(s->device));
   return 0;
 }
 
@@ -445,7 +447,10 @@ static int build_plan(ltb_w2l_session* s) {
     o.type = 0;
     o.cp = p;
     const bool gemm1x1 = (p.nphases == 1 && p.ph[0].ntaps == 1);
-    if (!(s->flags & LTB_SESSION_NO_HALO) && (m->wt[li] || gemm1x1) && conv_halo_supported(p)) {
+    if (!(s->flags & LTB_SESSION_NO_HALO) && fc_rows_supported(p)) {
+      o.type = 7;
+      fc_rows_make(p, &o.fc);
+    } else if (!(s->flags & LTB_SESSION_NO_HALO) && (m->wt[li] || gemm1x1) && conv_halo_supported(p)) {
       HaloPlan pl;
       if (conv_halo_make_plan(p, m->wt[li], &pl) == 0) {
         o.type = 4;
@@ -641,6 +646,7 @@ static const char* op_name(const Op& o) {
     case 4: return "conv_halo";
     case 5: return "stem_umma";
     case 6: return "mel";
+    case 7: return "fc_rows";
   }
   return "?";
 }
@@ -676,6 +682,7 @@ static int run_ops(ltb_w2l_session* s, bool with_mel, cudaEvent_t* events = null
       case 3: e = launch_w2l_head(o.cp.in, s->m->head_w, s->m->head_b, s->pred, s->B * 65536, st); break;
       case 4: e = launch_conv_halo(s->halo_plans[o.halo], st); break;
       case 5: e = launch_stem(s->stem, st); break;
+      case 7: e = launch_fc_rows(o.fc, st); break;
       case 6:
         if (with_mel) e = launch_mel_step(s->pcm, s->pcm_cap, s->B, s->l, s->fps, s->mel_spec, s->mel_mel, s->mel, st);
         break;
@@ -729,10 +736,10 @@ static int model_from(ltb_w2l_model* m, const uint8_t* header_host, size_t nbyte
     model_free(m);
     return 1;
   }
-  // tap-major weight copies for the halo kernel: every 3x3 s1 p1 conv and every k3 s2 ConvT
+  // tap-major weight copies for the halo kernel: every 3x3 p1 conv (stride 1, and stride 2 for the parity-plane path) and every k3 s2 ConvT
   for (int i = 1; i < kNumLayers; ++i) {
     const LDef& L = kLayers[i];
-    const bool conv3 = L.kind == 'c' && L.k == 3 && L.sy == 1 && L.sx == 1 && L.pad == 1 && L.cin >= 16;
+    const bool conv3 = L.kind == 'c' && L.k == 3 && L.pad == 1 && L.cin >= 16 && ((L.sy == 1 && L.sx == 1) || (L.sy == 2 && L.sx == 2));
     const bool convt = L.kind == 't' && L.k == 3;
     if (!conv3 && !convt) continue;
     const size_t bytes = (size_t)L.cout * 9 * L.cin * 2;
@@ -839,7 +846,7 @@ int ltb_w2l_avatar_destroy(ltb_w2l_avatar* a) {
 
 int ltb_w2l_session_destroy(ltb_w2l_session* s) {
   if (!s) return 0;
-  if (s->m) cudaSetDevice(s->m->device);
+  cudaSetDevice(s->device);
   if (s->st) cudaStreamSynchronize(s->st);
   if (s->st_asr) {
     cudaStreamSynchronize(s->st_asr);
@@ -874,6 +881,7 @@ int ltb_w2l_session_create(ltb_w2l_model* m, ltb_w2l_avatar* a, int batch, int s
   auto* s = new ltb_w2l_session();
   s->m = m;
   s->a = a;
+  s->device = m->device;
   s->B = batch;
   s->l = stride_left;
   s->r = stride_right;
@@ -1129,7 +1137,7 @@ int ltb_w2l_infer_slots(ltb_w2l_session* s, const ltb_w2l_slot* slots, int nslot
   for (int i = 0; i < nslots; ++i) {
     const ltb_w2l_avatar* a = slots[i].avatar;
     if (!a || !slots[i].mel) return LTB_FAIL("infer_slots: slot " + std::to_string(i) + " has a null avatar / mel");
-    if (a->device != s->m->device) return LTB_FAIL("infer_slots: avatar lives on another device");
+    if (a->device != s->device) return LTB_FAIL("infer_slots: avatar lives on another device");
     if (a->H != H || a->W != W) return LTB_FAIL("infer_slots: all avatars of a batch must share the frame size of the session's avatar");
     if (slots[i].idx < 0 || slots[i].idx >= a->n) return LTB_FAIL("infer_slots: frame index out of range");
   }
@@ -1198,7 +1206,7 @@ int ltb_w2l_profile_ops(ltb_w2l_session* s, int index, int max_ops, int* n_ops, 
     if (kinds) kinds[i] = o.type;
     if (flops) {
       double f = 0;
-      if (o.type == 0 || o.type == 4 || o.type == 5) {
+      if (o.type == 0 || o.type == 4 || o.type == 5 || o.type == 7) {
         for (int p = 0; p < o.cp.nphases; ++p) f += 2.0 * o.cp.M * o.cp.Cout * (double)o.cp.ph[p].ntaps * o.cp.Cin;
       }
       flops[i] = f;

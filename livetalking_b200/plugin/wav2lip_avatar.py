@@ -137,6 +137,22 @@ class LipReal(BaseAvatar):
                 logger.warning("pinned output ring unavailable (%r): using pageable buffers", e)
                 self._ring = []
 
+    def close(self):
+        """Release this session's engine objects (arena, graphs, streams, pinned ring).  The shared cross-session scheduler
+        and the avatar assets belong to the model / payload and stay."""
+        sess, self.engine_session = getattr(self, "engine_session", None), None
+        if sess is not None:
+            sess.close()
+        for b in getattr(self, "_ring", []):
+            b.close()
+        self._ring = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def _next_out(self):
         if not self._ring:
             return None
