@@ -771,7 +771,7 @@ def run_ours(args):
         ms_ops, flops, kinds = sess.profile_ops(idx[0])
         passes = [sess.profile_ops(idx[0])[0] for _ in range(3)]
         med = np.median(np.stack(passes + [ms_ops]), axis=0)
-        conv = (kinds == 0) | (kinds == 4) | (kinds == 5) | (kinds == 7)
+        conv = (kinds == 0) | (kinds == 4) | (kinds == 5)
         algo_flops = GFLOP_PER_FRAME * 1e9 * BATCH
         K = max(20, args.steps)
         for _ in range(3):
@@ -802,7 +802,7 @@ def run_ours(args):
         if args.dump_ops:
             os.makedirs(os.path.dirname(os.path.abspath(args.dump_ops)), exist_ok=True)
             json.dump({"ops": [(int(k), round(float(m), 4), float(f)) for k, m, f in zip(kinds, med, flops)],
-                       "note": "kind(0 conv gather,1 prep,2 audio_conv0,3 head,4 conv halo/ystack,5 stem,6 mel,7 fc_rows), median ms, algorithmic flops"},
+                       "note": "kind(0 conv gather,1 prep,2 audio_conv0,3 head,4 conv halo/ystack,5 stem,6 mel), median ms, algorithmic flops"},
                       open(args.dump_ops, "w"))
 
     extras = {}

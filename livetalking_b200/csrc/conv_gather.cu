@@ -99,7 +99,11 @@ __global__ void __launch_bounds__(160) conv_gather_umma_kernel(const __grid_cons
     // ------------------------------------------------------------------ producers
     const int j = tid % C::CH;
     const int r0 = tid / C::CH;
-    int rb[C::CH], riy[C::CH], rix[C::CH];
+    // per producer row: input coordinates of tap (0,0) and the element offset of that pixel (+ this thread's 16-byte K chunk);
+    // per K iteration only one uniform tap offset is added — the address arithmetic used to be three 64-bit multiplies per
+    // cp.async and made the small-channel layers issue bound (ncu r02f: 60 % issue slots busy at 4.7 % tensor pipe)
+    int riy[C::CH], rix[C::CH];
+    long long rbase[C::CH];
     const int gsz = p.GH * p.GW;
 #pragma unroll
     for (int i = 0; i < C::CH; ++i) {
@@ -109,13 +113,13 @@ __global__ void __launch_bounds__(160) conv_gather_umma_kernel(const __grid_cons
         const int rem = m - b * gsz;
         const int gy = rem / p.GW;
         const int gx = rem - gy * p.GW;
-        rb[i] = b;
         riy[i] = gy * p.sy;
         rix[i] = gx * p.sx;
+        rbase[i] = ((long long)(b * p.IH + riy[i]) * p.IW + rix[i]) * p.ICtot + p.ic_off + j * 8;
       } else {
-        rb[i] = 0;
         riy[i] = -(1 << 20);  // forces the bounds test to fail -> zero rows
         rix[i] = 0;
+        rbase[i] = 0;
       }
     }
     int tap = it_begin / cpt, cc = it_begin % cpt;
@@ -125,13 +129,13 @@ __global__ void __launch_bounds__(160) conv_gather_umma_kernel(const __grid_cons
       const uint32_t a_base = tiles + stage * C::STAGE_BYTES;
       const uint32_t b_base = a_base + C::A_BYTES;
       const int dy = ph.dy[tap], dx = ph.dx[tap];
+      const long long toff = (long long)(dy * p.IW + dx) * p.ICtot + cc * KB;   // uniform over the CTA
 #pragma unroll
       for (int i = 0; i < C::CH; ++i) {
         const int row = r0 + i * C::RSTEP;
         const int iy = riy[i] + dy, ix = rix[i] + dx;
         const bool inb = ((unsigned)iy < (unsigned)p.IH) && ((unsigned)ix < (unsigned)p.IW);
-        const size_t off = ((size_t)(rb[i] * p.IH + iy) * p.IW + ix) * p.ICtot + p.ic_off + cc * KB + j * 8;
-        const __half* src = inb ? (in_base + off) : in_base;
+        const __half* src = inb ? (in_base + rbase[i] + toff) : in_base;
         cp_async16(a_base + row * C::ROWB + swz_chunk<KB>(row, j) * 16, src, inb ? 16u : 0u);
       }
       const size_t wk = (size_t)ph.koff + (size_t)tap * p.Cin + cc * KB + j * 8;

@@ -590,12 +590,15 @@ bool conv_halo_supported(const ConvParams& p) {
            (p.ph[0].koff % 8) == 0 && p.M >= 512 && get_encode() != nullptr;
   }
   if (is_conv3x3_s2(p)) {
-    // parity-plane TMA path: worth it while the 16-row tiles are mostly full (the 8x8 / 4x4 output maps stay on the split-K gather kernel)
+    // parity-plane TMA path: worth it while the 16-row tiles are mostly full (the 8x8 / 4x4 output maps stay on the split-K gather
+    // kernel) and a tile carries enough MMAs to hide the four plane loads behind two A stages.  Measured (profiles/r02l_per_op):
+    // 64->128 @64->32: 18.5 -> 14.4 us, 128->256 @32->16: 22.5 -> 14.3 us, but 16->32 @256->128: 38.9 -> 64.1 us (nine K=16
+    // instructions per 78 KB of zero-padded plane loads: latency bound) -> Cin >= 64 only.
     static const bool off = [] {
       const char* e = std::getenv("LTB_NO_S2_TMA");
       return e && e[0] && e[0] != '0';
     }();
-    return !off && p.Cout % 32 == 0 && p.Cin >= 16 && (p.ICtot % 8) == 0 && (p.ic_off % 8) == 0 && p.Ktot == 9 * p.Cin && p.GH >= 16 &&
+    return !off && p.Cout % 32 == 0 && p.Cin >= 64 && (p.ICtot % 8) == 0 && (p.ic_off % 8) == 0 && p.Ktot == 9 * p.Cin && p.GH >= 16 &&
            p.GW >= 8 && get_encode() != nullptr;
   }
   if (is_upconv(p))

@@ -77,19 +77,6 @@ struct SlotDesc {
 cudaError_t launch_conv_gather(const ConvParams& p, cudaStream_t st, float* splitk_ws = nullptr, size_t splitk_ws_floats = 0);
 int conv_gather_pick_bn(const ConvParams& p);
 
-// fc_rows.cu: convs whose output map is 1x1 at batch <= 16 (weight-streaming, one warp per output channel)
-struct FcParams {
-  const __half* in;      // row m at in + m * in_row ; K index k = tap * Cin + c  ->  element tap * tap_pitch + c
-  const __half* w;       // [Cout][K] K-major
-  const float* bias;
-  __half* out;           // row m at out + m * out_row
-  int M, K, Cin, Cout, relu, tap_pitch;
-  long long in_row, out_row;
-};
-bool fc_rows_supported(const ConvParams& c);
-void fc_rows_make(const ConvParams& c, FcParams* f);
-cudaError_t launch_fc_rows(const FcParams& f, cudaStream_t st);
-
 // wav2lip-specific small kernels (w2l_small.cu)
 // faces u8 [nf,256,256,3] BGR -> padded fp16 [B,262,264,8]: ch0-2 = face/255 with rows >= 128 zeroed, ch3-5 = face/255
 // the first avatar index of the step is read from device memory (*d_index) so that a captured CUDA graph can be replayed

@@ -211,9 +211,8 @@ struct Tensor {
 };
 struct Op {
   int type;  // 0 = conv (gather kernel), 1 = prep, 2 = audio conv0, 3 = head, 4 = conv (halo kernel), 5 = stem (tensor-core),
-             // 6 = mel of the resident PCM chunk (skipped when the host supplies mel windows), 7 = 1x1-map conv (fc_rows)
+             // 6 = mel of the resident PCM chunk (skipped when the host supplies mel windows)
   ConvParams cp;
-  FcParams fc;
   int halo = -1;    // index into the session's halo plans (type 4)
   int branch = 0;   // 1 = audio-encoder branch: runs on the side stream, concurrently with the face encoder
   bool join = false;  // first op that consumes the audio branch's result
@@ -447,10 +446,7 @@ static int build_plan(ltb_w2l_session* s) {
     o.type = 0;
     o.cp = p;
     const bool gemm1x1 = (p.nphases == 1 && p.ph[0].ntaps == 1);
-    if (!(s->flags & LTB_SESSION_NO_HALO) && fc_rows_supported(p)) {
-      o.type = 7;
-      fc_rows_make(p, &o.fc);
-    } else if (!(s->flags & LTB_SESSION_NO_HALO) && (m->wt[li] || gemm1x1) && conv_halo_supported(p)) {
+    if (!(s->flags & LTB_SESSION_NO_HALO) && (m->wt[li] || gemm1x1) && conv_halo_supported(p)) {
       HaloPlan pl;
       if (conv_halo_make_plan(p, m->wt[li], &pl) == 0) {
         o.type = 4;
@@ -646,7 +642,6 @@ static const char* op_name(const Op& o) {
     case 4: return "conv_halo";
     case 5: return "stem_umma";
     case 6: return "mel";
-    case 7: return "fc_rows";
   }
   return "?";
 }
@@ -682,7 +677,6 @@ static int run_ops(ltb_w2l_session* s, bool with_mel, cudaEvent_t* events = null
       case 3: e = launch_w2l_head(o.cp.in, s->m->head_w, s->m->head_b, s->pred, s->B * 65536, st); break;
       case 4: e = launch_conv_halo(s->halo_plans[o.halo], st); break;
       case 5: e = launch_stem(s->stem, st); break;
-      case 7: e = launch_fc_rows(o.fc, st); break;
       case 6:
         if (with_mel) e = launch_mel_step(s->pcm, s->pcm_cap, s->B, s->l, s->fps, s->mel_spec, s->mel_mel, s->mel, st);
         break;
@@ -1206,7 +1200,7 @@ int ltb_w2l_profile_ops(ltb_w2l_session* s, int index, int max_ops, int* n_ops, 
     if (kinds) kinds[i] = o.type;
     if (flops) {
       double f = 0;
-      if (o.type == 0 || o.type == 4 || o.type == 5 || o.type == 7) {
+      if (o.type == 0 || o.type == 4 || o.type == 5) {
         for (int p = 0; p < o.cp.nphases; ++p) f += 2.0 * o.cp.M * o.cp.Cout * (double)o.cp.ph[p].ntaps * o.cp.Cin;
       }
       flops[i] = f;

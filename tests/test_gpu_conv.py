@@ -32,10 +32,10 @@ CASES = [
     (16, 16, 16, 768, 384, 3, (2, 2), 1, True, False),   # ConvT with 128-wide N tiles: fat-N issue splits N = 384 into 256 + 128
     (16, 32, 32, 384, 384, 3, (1, 1), 1, False, True),   # 384 channels @32x32, batch 16: the cost model picks BN=128, NSUB=1 (3 waves)
     # stride-2 parity-plane TMA path (conv_halo.cu TAPS = 10): four planes loaded with traversal stride 2, nine taps as views
-    (2, 64, 64, 16, 32, 3, (2, 2), 1, False, False),     # L14 geometry (Cin = 16: one K step per tap), BN = 32
+    (2, 64, 64, 80, 32, 3, (2, 2), 1, False, False),     # BN = 32, ragged second K chunk (80 channels)
     (2, 32, 48, 64, 128, 3, (2, 2), 1, False, False),    # 2 N tiles of 64, non-square, output 16 x 24
     (1, 64, 32, 128, 256, 3, (2, 2), 1, False, False),   # 2 K chunks, 4 N tiles
-    (3, 40, 36, 32, 64, 3, (2, 2), 1, False, False),     # ragged output 20 x 18: overhanging tile rows / columns
+    (3, 40, 36, 64, 64, 3, (2, 2), 1, False, False),     # ragged output 20 x 18: overhanging tile rows / columns
     # y-stacked narrow-layer kernel (conv_ystack.cu): N = 3*BN per instruction, rows combined in the epilogue.  By default only the
     # 80->32 geometry takes it (see pick_ystack); test_ystack_all_variants runs every case below with LTB_YSTACK=all in a subprocess
     (2, 64, 64, 64, 64, 3, (1, 1), 1, False, True),      # BN=64 NSUB=1: 5 overlapping row tiles, residual, streamed weights
