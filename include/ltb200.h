@@ -224,6 +224,13 @@ int ltb_op_eltwise(ltb_ctx* c, const void* x, const void* y, long long n, long l
 int ltb_op_upsample2x(ltb_ctx* c, const void* x, int N, int H, int W, int C, void* out);
 int ltb_op_copy_channels(ltb_ctx* c, const void* src, long long rows, int C, int SCtot, int sc_off, void* dst, int DCtot, int dc_off);
 int ltb_op_transpose_heads(ltb_ctx* c, const void* v, int B, int n_keys, int Ctot, int c_off, int heads, int d, int n_pad, void* vt);
+/* Fused multi-head attention out = softmax(scale * Q K^T) V on tcgen05 (scores stay in TMEM / shared memory): the diffusers Attention
+ * blocks of the UNet (avatars/musetalk/models/unet.py:29-48) and the Whisper encoder layers (whisper/audio2feature.py:106-117).
+ * q [B][nq] rows of q_pitch halves, k [B][kv_rows] rows of kv_pitch halves, head h at columns [h*d, (h+1)*d); vt = the
+ * ltb_op_transpose_heads output [B*heads][d][n_pad]; keys >= valid get probability 0; out [B*nq][out_pitch], head h at columns
+ * h*d.  d % 16 == 0, d <= 160; pitches and n_pad multiples of 8. */
+int ltb_op_attention(ltb_ctx* c, const void* q, int q_pitch, const void* k, int kv_pitch, int kv_rows, const void* vt, int n_pad, int B, int heads,
+                     int nq, int valid, int d, float scale, void* out, int out_pitch);
 /* VAE.decode_latents post-processing, avatars/musetalk/models/vae.py:104-107 -> uint8 BGR NHWC */
 int ltb_op_vae_post(ltb_ctx* c, const void* x, long long npix, int Ctot, void* out_u8);
 /* Encoder hand-off: composited uint8 BGR frames [N,H,W,3] -> planar I420 [N, H*3/2, W] on the device,

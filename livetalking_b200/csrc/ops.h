@@ -22,6 +22,10 @@ cudaError_t launch_copy_channels(const __half* src, size_t rows, int C, int SCto
                                  cudaStream_t st);
 cudaError_t launch_transpose_heads(const __half* v, int B, int n_keys, int Ctot, int c_off, int heads, int d, int n_pad, __half* vt,
                                    cudaStream_t st);
+// softmax(scale * Q K^T) V in one kernel (attn_fused.cu); head dim d % 16 == 0, d <= 160
+bool attn_fused_supported(int d, int q_pitch, int kv_pitch, int n_pad);
+cudaError_t launch_attn_fused(const __half* q, int q_pitch, const __half* k, int kv_pitch, int kv_rows, const __half* vt, int n_pad, int B, int H,
+                              int nq, int valid, int d, float scale, __half* out, int out_pitch, cudaStream_t st);
 cudaError_t launch_vae_post(const __half* x, size_t npix, int Ctot, uint8_t* out, cudaStream_t st);
 // uint8 BGR [N,H,W,3] -> planar I420 [N, H*3/2, W] (OpenCV COLOR_BGR2YUV_I420 arithmetic); H even, W % 4 == 0
 cudaError_t launch_bgr_to_i420(const uint8_t* bgr, int N, int H, int W, uint8_t* out, cudaStream_t st);

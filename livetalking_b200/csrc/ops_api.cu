@@ -385,6 +385,17 @@ int ltb_op_transpose_heads(ltb_ctx* c, const void* v, int B, int n_keys, int Cto
   c->launches += 1;
   return 0;
 }
+int ltb_op_attention(ltb_ctx* c, const void* q, int q_pitch, const void* k, int kv_pitch, int kv_rows, const void* vt, int n_pad, int B, int heads,
+                     int nq, int valid, int d, float scale, void* out, int out_pitch) {
+  if (!c || !q || !k || !vt || !out) return LTB_FAIL("attention: null argument");
+  if (!attn_fused_supported(d, q_pitch, kv_pitch, n_pad)) return LTB_FAIL("attention: unsupported head dim / pitch (d % 16 == 0, d <= 160, pitches % 8 == 0)");
+  LTB_CTX_ENTER(c);
+  cudaError_t e = launch_attn_fused(static_cast<const __half*>(q), q_pitch, static_cast<const __half*>(k), kv_pitch, kv_rows,
+                                    static_cast<const __half*>(vt), n_pad, B, heads, nq, valid, d, scale, static_cast<__half*>(out), out_pitch, c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("attention: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
 int ltb_op_vae_post(ltb_ctx* c, const void* x, long long npix, int Ctot, void* out_u8) {
   if (!c || !x || !out_u8) return LTB_FAIL("vae_post: null argument");
   LTB_CTX_ENTER(c);

@@ -194,6 +194,9 @@ class Builder:
         skip = self.linear(x, r.shortcut) if r.shortcut is not None else x
         return self.conv3(h, r.conv2, res=skip, stats=True)
 
+    # softmax(QK^T)V as one tcgen05 kernel (scores never reach HBM); LTB_FUSE_ATTENTION=0 restores GEMM + softmax + GEMM
+    FUSE_ATTENTION = os.environ.get("LTB_FUSE_ATTENTION", "1") == "1"
+
     def attention(self, a, xq: DevTensor, B: int, nq: int, res: DevTensor, kv_src: Optional[DevTensor] = None, n_keys: Optional[int] = None,
                   n_valid: Optional[int] = None, stats_imgs: int = 0):
         """xq: (B*nq, C) normalised tokens.  Self-attention when kv_src is None, else keys/values from kv_src (B*n_keys, kv_dim).
@@ -216,6 +219,12 @@ class Builder:
             q_ptr, q_pitch = q.ptr, Hdp
             k_ptr, v_ptr, kv_pitch = kv.ptr, kv.offset(Hdp), 2 * Hdp
             nk, valid, kv_rows = n_keys, n_valid, n_keys
+        if self.FUSE_ATTENTION and dp % 16 == 0 and dp <= 160:
+            VT = self.new(B * H, dp, nk)
+            ctx.transpose_heads(v_ptr, B, kv_rows, kv_pitch, H, dp, nk, VT)
+            O = self.new(B * nq, Hdp)
+            ctx.attention(q_ptr, q_pitch, k_ptr, kv_pitch, kv_rows, VT, nk, B, H, nq, valid, dp, float(d) ** -0.5, O)
+            return self.linear(O, a.out, res=res, stats_imgs=stats_imgs)
         S = self.new(B * H, nq, nk)
         qv = DevTensor(q_ptr, (nq, dp), pitch=q_pitch)
         sv = DevTensor(S.ptr, (nq, nk), pitch=nk)

@@ -214,6 +214,12 @@ class Ctx:
     def transpose_heads(self, v_ptr: int, B: int, n_keys: int, Ctot: int, heads: int, d: int, n_pad: int, vt: DevTensor):
         check(lib().ltb_op_transpose_heads(self._h, C.c_void_p(v_ptr), B, n_keys, Ctot, 0, heads, d, n_pad, C.c_void_p(vt.ptr)))
 
+    def attention(self, q_ptr: int, q_pitch: int, k_ptr: int, kv_pitch: int, kv_rows: int, vt: DevTensor, n_pad: int, B: int, heads: int, nq: int,
+                  valid: int, d: int, scale: float, out: DevTensor):
+        """out = softmax(scale * Q K^T) V, one kernel (csrc/attn_fused.cu)."""
+        check(lib().ltb_op_attention(self._h, C.c_void_p(q_ptr), q_pitch, C.c_void_p(k_ptr), kv_pitch, kv_rows, C.c_void_p(vt.ptr), n_pad, B,
+                                     heads, nq, valid, d, scale, C.c_void_p(out.ptr), out.pitch))
+
     def bgr_to_i420(self, frames_u8: DevTensor, N: int, H: int, W: int, out_u8: DevTensor):
         """uint8 BGR [N,H,W,3] -> planar I420 [N, H*3/2, W] (encoder hand-off; cv2.COLOR_BGR2YUV_I420 arithmetic)."""
         check(lib().ltb_op_bgr_to_i420(self._h, C.c_void_p(frames_u8.ptr), N, H, W, C.c_void_p(out_u8.ptr)))

@@ -234,3 +234,55 @@ def test_fused_upsample_conv_matches_interpolate_plus_conv(shape):
     assert (err <= 3e-2 + 1.5e-2 * np.abs(ref)).all(), f"max err {err.max():.4f} at {np.unravel_index(err.argmax(), err.shape)}"
     assert err.mean() < 3e-3
     ctx.close()
+
+
+@pytest.mark.parametrize("shape", [
+    # B, H, d, nq, kv_rows, valid, self-attention layout (fused qkv buffer) or separate q / kv buffers
+    (2, 8, 48, 1024, 1024, 1024, True),     # UNet 32x32 self-attention (d 40 padded to 48): 8 key tiles, 2 passes
+    (1, 6, 64, 1500, 1500, 1500, True),     # Whisper-tiny encoder: ragged last query tile and key tile (1500 = 11*128 + 92)
+    (3, 8, 80, 256, 64, 50, False),         # UNet cross-attention: 50 valid audio tokens of 64 rows, two K chunks
+    (2, 8, 160, 64, 64, 64, True),          # 8x8 level: three K chunks, single-stage K ring, 512 TMEM columns
+    (1, 8, 160, 16, 16, 16, True),          # mid block at 4x4: 16 queries, 16 keys
+    (1, 2, 16, 130, 200, 137, False),       # smallest head dim; nothing aligned
+], ids=["self1024_d48", "whisper1500_d64", "cross50_d80", "self64_d160", "mid16_d160", "ragged_d16"])
+def test_fused_attention_matches_torch(shape):
+    """softmax(scale QK^T)V as ONE tcgen05 kernel (csrc/attn_fused.cu) against plain PyTorch fp32 on the same fp16 inputs.
+    Tolerance: probabilities are rounded to fp16 before the PV product (like the unfused path stored them), fp32 accumulate, fp16 out:
+    |err| <= 4e-3 + 1e-2 |ref|."""
+    from livetalking_b200 import engine
+    from livetalking_b200.ops import Ctx, DevTensor
+    engine.set_device(0)
+    B, H, d, nq, kv_rows, valid, fused_qkv = shape
+    g = torch.Generator().manual_seed(sum(shape[:6]))
+    Hd = H * d
+    scale = float(d) ** -0.5
+    if fused_qkv:
+        assert kv_rows == nq
+        qkv = (torch.randn(B, nq, 3 * Hd, generator=g) * 1.5).half()
+        q, k, v = qkv[..., :Hd], qkv[..., Hd:2 * Hd], qkv[..., 2 * Hd:]
+    else:
+        q = (torch.randn(B, nq, Hd, generator=g) * 1.5).half()
+        kv = (torch.randn(B, kv_rows, 2 * Hd, generator=g) * 1.5).half()
+        k, v = kv[..., :Hd], kv[..., Hd:]
+    qh = q.float().view(B, nq, H, d).permute(0, 2, 1, 3)
+    kh = k.float().view(B, kv_rows, H, d).permute(0, 2, 1, 3)[:, :, :valid]
+    vh = v.float().view(B, kv_rows, H, d).permute(0, 2, 1, 3)[:, :, :valid]
+    ref = torch.softmax(qh @ kh.transpose(-1, -2) * scale, -1) @ vh                     # B,H,nq,d
+    ref = ref.permute(0, 2, 1, 3).reshape(B * nq, Hd).numpy()
+    ctx = Ctx()
+    n_pad = (kv_rows + 15) // 16 * 16
+    if fused_qkv:
+        dq = ctx.upload(qkv.contiguous().numpy())
+        q_ptr, q_pitch, k_ptr, v_ptr, kv_pitch = dq.ptr, 3 * Hd, dq.ptr + 2 * Hd, dq.ptr + 4 * Hd, 3 * Hd
+    else:
+        dq, dkv = ctx.upload(q.contiguous().numpy()), ctx.upload(kv.contiguous().numpy())
+        q_ptr, q_pitch, k_ptr, v_ptr, kv_pitch = dq.ptr, Hd, dkv.ptr, dkv.ptr + 2 * Hd, 2 * Hd
+    vt = ctx.alloc((B * H, d, n_pad), np.float16, zero=True)
+    ctx.transpose_heads(v_ptr, B, kv_rows, kv_pitch, H, d, n_pad, vt)
+    out = ctx.alloc((B * nq, Hd), np.float16, zero=True)
+    ctx.attention(q_ptr, q_pitch, k_ptr, kv_pitch, kv_rows, vt, n_pad, B, H, nq, valid, d, scale, out)
+    got = ctx.download(out).astype(np.float32)
+    err = np.abs(got - ref)
+    assert np.isfinite(got).all()
+    assert (err <= 4e-3 + 1e-2 * np.abs(ref)).all(), f"max err {err.max():.5f} at {np.unravel_index(err.argmax(), err.shape)}"
+    ctx.close()

@@ -155,3 +155,64 @@ def test_load_avatar_prefers_packed_assets(tmp_path, monkeypatch):
     assert np.array_equal(ea.faces, eb.faces) and np.array_equal(ea.frames, eb.frames) and np.array_equal(ea.coords, eb.coords)
     ea.close()
     eb.close()
+
+
+def test_lipreal_cross_session_mode(w2l_state_dict):
+    """opt.ltb_cross_session: two sessions with different avatars and small batch sizes submit their frames
+    to the shared scheduler from two threads; each gets its own frames back, equal (PSNR >= 40 dB after the u8 conversion) to
+    the CPU oracle's frames for its own audio and avatar, and the scheduler packed requests of both sessions into common launches."""
+    import threading
+    stubs.install()
+    from livetalking_b200 import engine
+    from livetalking_b200.plugin import wav2lip_avatar as W
+    from oracle import wav2lip_ref as R
+    import registry
+    engine.set_device(0)
+    B, H, Wd = 2, 240, 320
+    rng = np.random.default_rng(8)
+    model = engine.W2LModel.from_state_dict(w2l_state_dict)
+    sessions = []
+    for s in range(2):
+        _, img = R.synth_inputs(3, seed=30 + s)
+        faces = list((img[:, 3:6].permute(0, 2, 3, 1).numpy() * 255.0).round().astype(np.uint8))
+        frames = list(rng.integers(0, 256, (3, H, Wd, 3), dtype=np.uint8))
+        coords = [(10 + s, 170 + s, 40, 210), (20, 148, 60 + s, 188 + s), (0, 240, 0, 320)]
+        av = registry.create("avatar", "wav2lip", opt=stubs.Opt(batch_size=B, ltb_cross_session=True, sessionid=s), model=model,
+                             avatar=W.make_avatar(frames, faces, coords))
+        t = np.arange((20 + 2 * B) * 320) / 16000.0
+        audio = (0.3 * np.sin(2 * np.pi * (250 + 90 * s) * t) + 0.05 * rng.standard_normal(t.size)).astype(np.float32)
+        sessions.append((av, faces, frames, coords, audio))
+    batcher = sessions[0][0]._batcher
+    assert batcher is not None and sessions[1][0]._batcher is batcher
+    results = [None, None]
+
+    def run(s):
+        av, faces, frames, coords, audio = sessions[s]
+        for c in range(2 * B):
+            av.asr.put_audio_frame(audio[c * 320:(c + 1) * 320], {})
+        av.asr.run_step()
+        feats = av.asr.feat_queue.get(timeout=5)
+        index = 1 + s
+        outs = []
+        for _rep in range(6):                                        # several steps so that requests of both sessions meet in a batch
+            pred = av.inference_batch(index, feats)
+            outs = [av.paste_back_frame(p, W.mirror_index(3, index + i)) for i, p in enumerate(pred)]
+        results[s] = (index, outs)
+
+    ths = [threading.Thread(target=run, args=(s,)) for s in range(2)]
+    for t_ in ths:
+        t_.start()
+    for t_ in ths:
+        t_.join(timeout=120)
+    for s in range(2):
+        av, faces, frames, coords, audio = sessions[s]
+        index, outs = results[s]
+        pcm = np.concatenate([np.zeros(20 * 320, np.float32), audio[:2 * B * 320]])
+        _, _, res_o = _pipeline_oracle(w2l_state_dict, faces, frames, coords, pcm, B, index)
+        for i in range(B):
+            assert outs[i].shape == (H, Wd, 3) and outs[i].flags.writeable
+            assert R.psnr_u8(outs[i], res_o[i]) >= 40.0, (s, i)
+    assert batcher.slots == 2 * 6 * B and batcher.batches <= 2 * 6         # (packing itself is asserted deterministically in tests/test_batcher.py)
+    batcher.close()
+    for av, *_ in sessions:
+        av.close()
