@@ -528,7 +528,7 @@ class MuseTalkBench:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def leg(self, args, peaks, hw: int, B: int = 8, n_sessions: int = 0, B_sess: int = 2):
+    def leg(self, args, peaks, hw: int, B: int = 8, n_sessions: int = 0, B_sess: int = 2, batch_sessions: int = 0):
         """BASELINE configs[2] (hw = 32: 256x256) / configs[4] (hw = 64: 512x512): the online path the reference runs per step
         (avatars/musetalk_avatar.py:130-164): Whisper features -> PE -> UNet -> VAE decode -> blend paste-back.
         n_sessions > 0: additionally that many CONCURRENT sessions per GPU (own stream / graph / buffers each, batch B_sess)."""
@@ -593,6 +593,45 @@ class MuseTalkBench:
         }
         if n_sessions > 0:
             res["concurrent_sessions"] = self._sessions(args, av, hw, n_sessions, B_sess)
+        if batch_sessions > 0:
+            res["cross_session"] = self._cross_session(args, hw, batch_sessions, B)
+        return res
+
+    def _cross_session(self, args, hw, G, Bs):
+        """SURVEY 8(f) rank 1 for MuseTalk: G sessions x Bs frames as ONE graph of batch G*Bs (MuseTalkBatchSession): every group has
+        its own avatar, frame index and Whisper feature window; aggregate frames/s of one GPU serving G sessions per launch."""
+        from livetalking_b200 import synth
+        from livetalking_b200.musetalk import MuseTalkAvatar, MuseTalkBatchSession
+        from livetalking_b200.whisper import WhisperFeatures
+        torch, ctx, world = self.torch, self.ctx, self.world
+        avs = [MuseTalkAvatar(ctx, *synth.synthetic_musetalk_avatar(n=16, hw=hw, seed=100 + 8 * self.rank + g)) for g in range(G)]
+        bs = MuseTalkBatchSession(self.net, avs, Bs, ctx=ctx)
+        wfs = [WhisperFeatures(self.wenc, Bs, SL, SR, out=bs.audio_in_of[g], out_rows=64, ctx=ctx) for g in range(G)]
+        for g, w_ in enumerate(wfs):
+            w_.run_async(step_pcm(self.audio, g, Bs))
+        ctx.sync()
+        stream = torch.cuda.ExternalStream(ctx.cuda_stream)
+        gate = Gate(torch, stream)
+        steps = max(5, min(args.steps, 20))
+
+        def one(k):
+            for w_ in wfs:
+                w_.run_async(None)                    # every session's own Whisper window, every round
+            bs.step_async([k * Bs + 3 * g for g in range(G)])
+
+        for k in range(3):
+            one(k)
+        ctx.sync()
+        ms = self._reduce_max(timed_steps(torch, stream, gate, one, steps)) / steps
+        fps = 1000.0 * G * Bs / ms
+        gf = MT_GFLOP_ONLINE[hw] * G * Bs + MT_GFLOP_WHISPER_STEP * G
+        res = {"value": round(world * fps, 2), "unit": "frames/s", "n_gpus": world, "sessions_per_launch": G, "frames_per_session": Bs,
+               "ms_per_round": round(ms, 3), "tflops": round(gf / ms, 1), "sessions_at_25fps_per_gpu": int(fps // 25),
+               "what": "%d sessions x %d frames in ONE UNet + VAE graph (batch %d), per-session avatar / index / Whisper window, "
+                       "blend paste-back per session; device-timed, inputs resident" % (G, Bs, G * Bs)}
+        for w_ in wfs:
+            w_.close()
+        bs.close()
         return res
 
     def _sessions(self, args, av, hw, n_sessions, B):
@@ -813,7 +852,7 @@ def run_ours(args):
         except Exception as e:                                  # an extra leg must never take the contract line down
             extras[name] = {"error": repr(e)[:300]}
 
-    if rank == 0 and world == 1 and not args.quick:
+    if rank == 0 and world == 1 and not args.quick and not args.only_musetalk:
         guarded("e2e_plugin", lambda: plugin_e2e(engine, model, (list(frames), list(faces), [tuple(c) for c in coords]), audio,
                                                   max(5, min(args.steps, 20)), 3))
         guarded("e2e_plugin_threads", lambda: plugin_threads(engine, model, (list(frames), list(faces), [tuple(c) for c in coords])))
@@ -826,7 +865,7 @@ def run_ours(args):
         mt = None
         try:
             mt = MuseTalkBench(torch, dist, world, rank)
-            extras["musetalk"] = mt.leg(args, peaks, 32)
+            extras["musetalk"] = mt.leg(args, peaks, 32, batch_sessions=4)
             if not args.no_musetalk512:
                 extras["musetalk512"] = mt.leg(args, peaks, 64, n_sessions=8, B_sess=2)
         except Exception as e:
@@ -840,7 +879,7 @@ def run_ours(args):
     if rank == 0:
         cores = os.cpu_count() or 1
         cpu = None
-        if world == 1 and not args.no_cpu_baseline and not args.quick:
+        if world == 1 and not args.no_cpu_baseline and not args.quick and not args.only_musetalk:
             c = CpuPath(cores)
             c.frames_of(0, 2)
             t0 = time.perf_counter()
@@ -889,6 +928,7 @@ def main():
     ap.add_argument("--musetalk512", action="store_true", help=argparse.SUPPRESS)   # accepted for compatibility: the leg is on by default
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--sustained-s", type=float, default=3.0)
+    ap.add_argument("--only-musetalk", action="store_true", help="development: contract line + the MuseTalk legs only")
     ap.add_argument("--quick", action="store_true", help="contract line only (value / e2e / roofline), no extra legs")
     ap.add_argument("--sessions", type=int, default=1, help="concurrent avatar sessions per GPU in the `value` leg (each batch 16, own stream)")
     ap.add_argument("--dump-ops", default=None, help="write per-op timings (json)")

@@ -20,7 +20,7 @@ from __future__ import annotations
 import os
 
 import math
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
@@ -628,6 +628,108 @@ class MuseTalkSession:
         """Everything resident (audio features already on the device): UNet + VAE decode + blend paste-back."""
         self.infer_async(index, None)
         self.paste_batch_async(index)
+
+
+class MuseTalkBatchSession:
+    """Cross-session batching for MuseTalk (the MuseTalk twin of ltb_w2l_infer_slots): G sessions x Bs frames
+    run as ONE captured UNet + VAE-decode graph of batch G*Bs.  Group g carries its own avatar (latent table, frames, masks, boxes)
+    and its own frame index; its audio features occupy rows [g*Bs, (g+1)*Bs) of audio_in.  The reference serves every session with
+    its own B-frame forward (avatars/musetalk_avatar.py:130-152 under app.py:76-100's max_session connections); at batch 8 the UNet
+    is launch-latency bound on a B200 (64 M-tiles per layer), so four sessions per launch cost far less than four launches."""
+
+    def __init__(self, model: MuseTalkModel, avatars: Sequence[MuseTalkAvatar], frames_per_session: int, ctx: Optional[Ctx] = None):
+        if not avatars:
+            raise ValueError("MuseTalkBatchSession: at least one avatar")
+        hw = avatars[0].lat_hw
+        if any(a.lat_hw != hw for a in avatars):
+            raise ValueError("MuseTalkBatchSession: all avatars of a batch must share the latent size")
+        self.model, self.avatars, self.Bs, self.G = model, list(avatars), int(frames_per_session), len(avatars)
+        self.B = B = self.G * self.Bs
+        self._own_ctx = ctx is None
+        ctx = self.ctx = Ctx() if ctx is None else ctx
+        Bs, cad = self.Bs, model.ucfg.cross_attention_dim
+        self.builder = Builder(ctx)
+        self._d_index = ctx.alloc((4 * self.G,), np.int32, zero=True)
+        self.d_index = [DevTensor(self._d_index.ptr + 16 * g, (4,), np.int32) for g in range(self.G)]
+        self.audio_in = ctx.alloc((B, KEY_PAD, cad), np.float16, zero=True)
+        self.audio_in_of = [DevTensor(self.audio_in.ptr + g * Bs * KEY_PAD * cad * 2, (Bs, KEY_PAD, cad)) for g in range(self.G)]
+        self.audio_pe = ctx.alloc((B * KEY_PAD, cad), np.float16, zero=True)
+        self.latents16 = ctx.alloc((B, hw, hw, 16), np.float16, zero=True)
+        self.image_u8 = ctx.alloc((B, hw * 8, hw * 8, 3), np.uint8, zero=True)
+        self.frames_out = [ctx.alloc((Bs, a.H, a.W, 3), np.uint8, zero=True) for a in self.avatars]
+        self._audio_host = np.zeros((B, KEY_PAD, cad), np.float16)
+        row = hw * hw * 16
+
+        def emit():
+            for g, a in enumerate(self.avatars):
+                ctx.gather_rows(a.latents, a.latents.shape[0], self.d_index[g], Bs, row,
+                                DevTensor(self.latents16.ptr + g * Bs * row * 2, (Bs, hw, hw, 16)))
+            ctx.eltwise(self.audio_in, model.pe, self.audio_in.rows * self.audio_in.C, KEY_PAD * self.audio_in.C, 0, self.audio_pe)
+            self.pred16 = model.emit_unet(self.builder, self.latents16, self.audio_pe, None)
+            self.image16 = model.emit_vae_decode(self.builder, self.pred16, self.image_u8, None)
+
+        emit()
+        ctx.sync()
+        temps, self.builder.temps = self.builder.temps, []
+        self.builder.new = _Replay(temps)
+        with ctx.capture() as cap:
+            emit()
+        self.graph = cap.graph
+
+    def _check(self, indices):
+        if len(indices) != self.G:
+            raise ValueError(f"expected {self.G} frame indices (one per session of the batch), got {len(indices)}")
+
+    def infer_async(self, indices: Sequence[int], audio_feats: Optional[np.ndarray] = None):
+        """indices[g]: first avatar frame index of session g's Bs frames; audio_feats (G*Bs, 50, 384) or None (already resident)."""
+        self._check(indices)
+        if audio_feats is not None:
+            a = np.asarray(audio_feats)
+            if a.shape != (self.B, 50, self._audio_host.shape[2]):
+                raise ValueError(f"audio features must be ({self.B},50,{self._audio_host.shape[2]}), got {a.shape}")
+            self._audio_host[:, :50] = a.astype(np.float16)
+            self.ctx.h2d(self.audio_in, self._audio_host, sync=False)
+        for g, i in enumerate(indices):
+            self.ctx.set_i32(self.d_index[g], int(i))
+        self.graph.launch()
+
+    def paste_async(self, indices: Sequence[int]):
+        self._check(indices)
+        for g, (a, i) in enumerate(zip(self.avatars, indices)):
+            op = _capi.MtPasteOp()
+            op.frames, op.coords, op.crop, op.masks, op.mask_off = a.frames.ptr, a.coords.ptr, a.crop.ptr, a.masks.ptr, a.mask_off.ptr
+            op.pred, op.out = self.image_u8.ptr, self.frames_out[g].ptr
+            op.nf, op.H, op.W = a.n, a.H, a.W
+            op.index, op.explicit_idx, op.slot0, op.count = int(i), -1, g * self.Bs, self.Bs
+            op.pred_hw = a.lat_hw * 8
+            self.ctx.mt_paste(op)
+
+    def step_async(self, indices: Sequence[int]):
+        self.infer_async(indices, None)
+        self.paste_async(indices)
+
+    def step(self, indices: Sequence[int], audio_feats: Optional[np.ndarray] = None) -> List[np.ndarray]:
+        """One batched round: returns, per session, its Bs composited frames (Bs, H, W, 3) uint8."""
+        with self.ctx.lock:
+            self.infer_async(indices, audio_feats)
+            self.paste_async(indices)
+            outs = [self.ctx.download(t, sync=False) for t in self.frames_out]
+            self.ctx.sync()
+            return outs
+
+    def close(self):
+        if getattr(self, "graph", None) is not None:
+            self.graph.close()
+            self.graph = None
+        if self._own_ctx and self.ctx is not None:
+            self.ctx.close()
+        self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class _Replay:

@@ -286,3 +286,50 @@ def test_fused_attention_matches_torch(shape):
     assert np.isfinite(got).all()
     assert (err <= 4e-3 + 1e-2 * np.abs(ref)).all(), f"max err {err.max():.5f} at {np.unravel_index(err.argmax(), err.shape)}"
     ctx.close()
+
+
+def test_cross_session_batch_matches_per_session(small_nets):
+    """MuseTalkBatchSession (G sessions x Bs frames in ONE graph of batch G*Bs, per-group avatar + frame index) against the same
+    sessions run one by one through MuseTalkSession: network output within the tile-configuration jitter (the batched launch may
+    pick other tile shapes: fp32 accumulation order differs; <= 2 u8 steps, PSNR >= 50 dB) and each group's paste-back BIT-EXACT
+    against the blend oracle applied to the batch's own prediction with that group's avatar assets."""
+    from livetalking_b200 import engine
+    from livetalking_b200.musetalk import MuseTalkBatchSession, MuseTalkModel, MuseTalkSession
+    from livetalking_b200.ops import Ctx
+    from oracle import musetalk_ref as M
+    from oracle import paste_ref as P
+    from oracle.wav2lip_ref import psnr_u8
+    ucfg, vcfg, us, vs = small_nets
+    engine.set_device(0)
+    G, Bs, n = 3, 2, 5
+    ctx = Ctx()
+    model = MuseTalkModel(ctx, us, vs, ucfg, vcfg)
+    avs, assets = [], []
+    for g in range(G):
+        lat, _ = M.synth_latents_and_audio(n, seed=10 + g)
+        av, frames, coords, crops, masks = _avatar(ctx, lat.numpy(), n, H=300 + 20 * g, W=400 - 16 * g, seed=g)
+        avs.append(av)
+        assets.append((frames, coords, crops, masks))
+    _, aud = M.synth_latents_and_audio(G * Bs, seed=77)
+    aud = aud.numpy()
+    indices = [3, 0, 7]                                     # 7 > n: mirror-indexed like the reference (basereal mirror_index)
+    bs = MuseTalkBatchSession(model, avs, Bs)
+    outs = bs.step(indices, aud)
+    pred_b = bs.ctx.download(bs.image_u8)
+    for g in range(G):
+        s = MuseTalkSession(model, avs[g], Bs)
+        pred_s = s.infer(indices[g], aud[g * Bs:(g + 1) * Bs])
+        got = pred_b[g * Bs:(g + 1) * Bs]
+        assert np.abs(got.astype(int) - pred_s.astype(int)).max() <= 2 and psnr_u8(got, pred_s) >= 50.0, (g, psnr_u8(got, pred_s))
+        frames, coords, crops, masks = assets[g]
+        assert outs[g].shape == (Bs, frames.shape[1], frames.shape[2], 3)
+        for i in range(Bs):
+            idx = P.mirror_index(n, indices[g] + i)
+            want = P.mt_paste_back(got[i], frames[idx], coords[idx], masks[idx], crops[idx])
+            assert np.array_equal(outs[g][i], want), (g, i)
+        s.close()
+    again = bs.step(indices, None)                           # features resident: replay
+    for g in range(G):
+        assert np.abs(again[g].astype(int) - outs[g].astype(int)).max() <= 2
+    bs.close()
+    ctx.close()
