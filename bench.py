@@ -605,7 +605,7 @@ class MuseTalkBench:
         from livetalking_b200.whisper import WhisperFeatures
         torch, ctx, world = self.torch, self.ctx, self.world
         avs = [MuseTalkAvatar(ctx, *synth.synthetic_musetalk_avatar(n=16, hw=hw, seed=100 + 8 * self.rank + g)) for g in range(G)]
-        bs = MuseTalkBatchSession(self.net, avs, Bs, ctx=ctx)
+        bs = MuseTalkBatchSession(self.net, hw, G, Bs, ctx=ctx)
         wfs = [WhisperFeatures(self.wenc, Bs, SL, SR, out=bs.audio_in_of[g], out_rows=64, ctx=ctx) for g in range(G)]
         for g, w_ in enumerate(wfs):
             w_.run_async(step_pcm(self.audio, g, Bs))
@@ -617,7 +617,7 @@ class MuseTalkBench:
         def one(k):
             for w_ in wfs:
                 w_.run_async(None)                    # every session's own Whisper window, every round
-            bs.step_async([k * Bs + 3 * g for g in range(G)])
+            bs.step_async([(avs[g], k * Bs + 3 * g, None) for g in range(G)])
 
         for k in range(3):
             one(k)

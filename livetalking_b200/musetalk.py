@@ -504,12 +504,20 @@ class MuseTalkAvatar:
 class MuseTalkSession:
     """One avatar stream at a fixed batch size: the captured UNet + VAE-decode graph and the paste-back buffers."""
 
-    def __init__(self, model: MuseTalkModel, avatar: MuseTalkAvatar, batch: int, keep_taps: bool = False, ctx: Optional[Ctx] = None):
+    def __init__(self, model: MuseTalkModel, avatar: MuseTalkAvatar, batch: int, keep_taps: bool = False, ctx: Optional[Ctx] = None,
+                 paste_only: bool = False):
         """ctx: the session's own stream + scratch (created here unless given).  Sessions never share a ctx: the reference
         opens up to max_session of them concurrently (app.py:76-100), each driven by its own three threads, and capturing /
-        synchronising a stream another session is using would corrupt both."""
+        synchronising a stream another session is using would corrupt both.
+        paste_only: no network graph and no activation arena — only paste_pred() works (cross-session mode: the UNet / VAE pass of
+        this session's frames runs in a shared MuseTalkBatchSession)."""
         self.model, self.avatar, self.B = model, avatar, int(batch)
         self._own_ctx = ctx is None
+        self._paste_ctx = None
+        self.graph = None
+        if paste_only:
+            self.ctx, self._own_ctx = None, False
+            return
         ctx = self.ctx = Ctx() if ctx is None else ctx
         B, hw = self.B, avatar.lat_hw
         self.builder = Builder(ctx)
@@ -540,6 +548,8 @@ class MuseTalkSession:
 
     # ---- MuseReal.inference_batch (musetalk_avatar.py:130-152)
     def infer_async(self, index: int, audio_feats: Optional[np.ndarray] = None):
+        if self.graph is None:
+            raise RuntimeError("MuseTalkSession: paste-only (or closed) session has no network graph")
         if audio_feats is not None:
             a = np.asarray(audio_feats)
             if a.shape != (self.B, 50, self._audio_host.shape[2]):
@@ -631,23 +641,21 @@ class MuseTalkSession:
 
 
 class MuseTalkBatchSession:
-    """Cross-session batching for MuseTalk (the MuseTalk twin of ltb_w2l_infer_slots): G sessions x Bs frames
-    run as ONE captured UNet + VAE-decode graph of batch G*Bs.  Group g carries its own avatar (latent table, frames, masks, boxes)
-    and its own frame index; its audio features occupy rows [g*Bs, (g+1)*Bs) of audio_in.  The reference serves every session with
-    its own B-frame forward (avatars/musetalk_avatar.py:130-152 under app.py:76-100's max_session connections); at batch 8 the UNet
-    is launch-latency bound on a B200 (64 M-tiles per layer), so four sessions per launch cost far less than four launches."""
+    """Cross-session batching for MuseTalk (the MuseTalk twin of ltb_w2l_infer_slots): up to G sessions x Bs
+    frames run as ONE captured PE + UNet + VAE-decode graph of batch G*Bs.  A *group request* is (avatar, first frame index,
+    Whisper features (Bs, 50, 384) or None): group g's latents are gathered from ITS avatar's table (mirror-indexed, outside the
+    graph, so any session may occupy any group of any round), its features occupy rows [g*Bs, (g+1)*Bs) of audio_in.
+    The reference serves every session with its own B-frame forward (avatars/musetalk_avatar.py:130-152 under app.py:76-100's
+    max_session connections); at batch 8 the UNet is launch-latency bound on a B200 (64 M-tiles per layer), so four sessions per
+    launch cost far less than four launches.  `batch` / `infer_slots` make it a mux for plugin.batcher.CrossSessionBatcher."""
 
-    def __init__(self, model: MuseTalkModel, avatars: Sequence[MuseTalkAvatar], frames_per_session: int, ctx: Optional[Ctx] = None):
-        if not avatars:
-            raise ValueError("MuseTalkBatchSession: at least one avatar")
-        hw = avatars[0].lat_hw
-        if any(a.lat_hw != hw for a in avatars):
-            raise ValueError("MuseTalkBatchSession: all avatars of a batch must share the latent size")
-        self.model, self.avatars, self.Bs, self.G = model, list(avatars), int(frames_per_session), len(avatars)
+    def __init__(self, model: MuseTalkModel, lat_hw: int, groups: int, frames_per_session: int, ctx: Optional[Ctx] = None):
+        self.model, self.lat_hw, self.Bs, self.G = model, int(lat_hw), int(frames_per_session), int(groups)
+        self.batch = self.G                                  # CrossSessionBatcher: requests per engine call
         self.B = B = self.G * self.Bs
         self._own_ctx = ctx is None
         ctx = self.ctx = Ctx() if ctx is None else ctx
-        Bs, cad = self.Bs, model.ucfg.cross_attention_dim
+        Bs, hw, cad = self.Bs, self.lat_hw, model.ucfg.cross_attention_dim
         self.builder = Builder(ctx)
         self._d_index = ctx.alloc((4 * self.G,), np.int32, zero=True)
         self.d_index = [DevTensor(self._d_index.ptr + 16 * g, (4,), np.int32) for g in range(self.G)]
@@ -655,15 +663,12 @@ class MuseTalkBatchSession:
         self.audio_in_of = [DevTensor(self.audio_in.ptr + g * Bs * KEY_PAD * cad * 2, (Bs, KEY_PAD, cad)) for g in range(self.G)]
         self.audio_pe = ctx.alloc((B * KEY_PAD, cad), np.float16, zero=True)
         self.latents16 = ctx.alloc((B, hw, hw, 16), np.float16, zero=True)
+        self.latents16_of = [DevTensor(self.latents16.ptr + g * Bs * hw * hw * 16 * 2, (Bs, hw, hw, 16)) for g in range(self.G)]
         self.image_u8 = ctx.alloc((B, hw * 8, hw * 8, 3), np.uint8, zero=True)
-        self.frames_out = [ctx.alloc((Bs, a.H, a.W, 3), np.uint8, zero=True) for a in self.avatars]
+        self._frames_out: Dict[tuple, DevTensor] = {}
         self._audio_host = np.zeros((B, KEY_PAD, cad), np.float16)
-        row = hw * hw * 16
 
         def emit():
-            for g, a in enumerate(self.avatars):
-                ctx.gather_rows(a.latents, a.latents.shape[0], self.d_index[g], Bs, row,
-                                DevTensor(self.latents16.ptr + g * Bs * row * 2, (Bs, hw, hw, 16)))
             ctx.eltwise(self.audio_in, model.pe, self.audio_in.rows * self.audio_in.C, KEY_PAD * self.audio_in.C, 0, self.audio_pe)
             self.pred16 = model.emit_unet(self.builder, self.latents16, self.audio_pe, None)
             self.image16 = model.emit_vae_decode(self.builder, self.pred16, self.image_u8, None)
@@ -676,44 +681,74 @@ class MuseTalkBatchSession:
             emit()
         self.graph = cap.graph
 
-    def _check(self, indices):
-        if len(indices) != self.G:
-            raise ValueError(f"expected {self.G} frame indices (one per session of the batch), got {len(indices)}")
+    def _check(self, requests):
+        if not 1 <= len(requests) <= self.G:
+            raise ValueError(f"1..{self.G} group requests per call, got {len(requests)}")
+        for r in requests:
+            if r[0].lat_hw != self.lat_hw:
+                raise ValueError("avatar latent size does not match the batch session")
 
-    def infer_async(self, indices: Sequence[int], audio_feats: Optional[np.ndarray] = None):
-        """indices[g]: first avatar frame index of session g's Bs frames; audio_feats (G*Bs, 50, 384) or None (already resident)."""
-        self._check(indices)
-        if audio_feats is not None:
-            a = np.asarray(audio_feats)
-            if a.shape != (self.B, 50, self._audio_host.shape[2]):
-                raise ValueError(f"audio features must be ({self.B},50,{self._audio_host.shape[2]}), got {a.shape}")
-            self._audio_host[:, :50] = a.astype(np.float16)
-            self.ctx.h2d(self.audio_in, self._audio_host, sync=False)
-        for g, i in enumerate(indices):
-            self.ctx.set_i32(self.d_index[g], int(i))
+    def infer_async(self, requests: Sequence[tuple]):
+        """requests[g] = (MuseTalkAvatar, first frame index, features (Bs,50,384) | None = resident in audio_in_of[g])."""
+        self._check(requests)
+        ctx, Bs, row = self.ctx, self.Bs, self.lat_hw * self.lat_hw * 16
+        stage = False
+        for g, (av, index, feats) in enumerate(requests):
+            if feats is not None:
+                a = np.asarray(feats)
+                if a.shape != (Bs, 50, self._audio_host.shape[2]):
+                    raise ValueError(f"group features must be ({Bs},50,{self._audio_host.shape[2]}), got {a.shape}")
+                self._audio_host[g * Bs:(g + 1) * Bs, :50] = a.astype(np.float16)
+                stage = True
+            ctx.set_i32(self.d_index[g], int(index))
+            ctx.gather_rows(av.latents, av.latents.shape[0], self.d_index[g], Bs, row, self.latents16_of[g])
+        if stage:
+            n = len(requests) * Bs
+            ctx.h2d(DevTensor(self.audio_in.ptr, (n,) + self.audio_in.shape[1:]), self._audio_host[:n], sync=False)
         self.graph.launch()
 
-    def paste_async(self, indices: Sequence[int]):
-        self._check(indices)
-        for g, (a, i) in enumerate(zip(self.avatars, indices)):
+    def infer_groups(self, requests: Sequence[tuple]) -> List[np.ndarray]:
+        """-> per request its (Bs, S, S, 3) uint8 BGR predictions (what MuseReal.inference_batch returns for that session)."""
+        with self.ctx.lock:
+            self.infer_async(requests)
+            n = len(requests) * self.Bs
+            S = self.lat_hw * 8
+            pred = self.ctx.download(DevTensor(self.image_u8.ptr, (n, S, S, 3), np.uint8))
+        return [pred[g * self.Bs:(g + 1) * self.Bs] for g in range(len(requests))]
+
+    infer_slots = infer_groups
+
+    def _out(self, g: int, av: MuseTalkAvatar) -> DevTensor:
+        key = (g, av.H, av.W)
+        if key not in self._frames_out:
+            self._frames_out[key] = self.ctx.alloc((self.Bs, av.H, av.W, 3), np.uint8, zero=True)
+        return self._frames_out[key]
+
+    def paste_async(self, requests: Sequence[tuple]) -> List[DevTensor]:
+        """Blend paste-back of every group's predictions into its own avatar frames (device resident; MuseReal.paste_back_frame x Bs)."""
+        self._check(requests)
+        outs = []
+        for g, (a, index, _f) in enumerate(requests):
             op = _capi.MtPasteOp()
             op.frames, op.coords, op.crop, op.masks, op.mask_off = a.frames.ptr, a.coords.ptr, a.crop.ptr, a.masks.ptr, a.mask_off.ptr
-            op.pred, op.out = self.image_u8.ptr, self.frames_out[g].ptr
+            out = self._out(g, a)
+            op.pred, op.out = self.image_u8.ptr, out.ptr
             op.nf, op.H, op.W = a.n, a.H, a.W
-            op.index, op.explicit_idx, op.slot0, op.count = int(i), -1, g * self.Bs, self.Bs
+            op.index, op.explicit_idx, op.slot0, op.count = int(index), -1, g * self.Bs, self.Bs
             op.pred_hw = a.lat_hw * 8
             self.ctx.mt_paste(op)
+            outs.append(out)
+        return outs
 
-    def step_async(self, indices: Sequence[int]):
-        self.infer_async(indices, None)
-        self.paste_async(indices)
+    def step_async(self, requests: Sequence[tuple]):
+        self.infer_async(requests)
+        self.paste_async(requests)
 
-    def step(self, indices: Sequence[int], audio_feats: Optional[np.ndarray] = None) -> List[np.ndarray]:
+    def step(self, requests: Sequence[tuple]) -> List[np.ndarray]:
         """One batched round: returns, per session, its Bs composited frames (Bs, H, W, 3) uint8."""
         with self.ctx.lock:
-            self.infer_async(indices, audio_feats)
-            self.paste_async(indices)
-            outs = [self.ctx.download(t, sync=False) for t in self.frames_out]
+            self.infer_async(requests)
+            outs = [self.ctx.download(t, sync=False) for t in self.paste_async(requests)]
             self.ctx.sync()
             return outs
 

@@ -16,9 +16,10 @@ import pickle
 import numpy as np
 
 from .. import engine
-from ..musetalk import MuseTalkAvatar, MuseTalkModel, MuseTalkSession
+from ..musetalk import MuseTalkAvatar, MuseTalkBatchSession, MuseTalkModel, MuseTalkSession
 from ..ops import Ctx
 from ..whisper import WhisperEncoder, WhisperFeatures
+from .batcher import CrossSessionBatcher
 from .whisper_asr import WhisperASR
 
 try:
@@ -104,6 +105,23 @@ def warm_up(batch_size, model):
     logger.info("warmup model... (engine sessions warm up at creation)")
 
 
+_BATCHER_LOCK = __import__("threading").Lock()
+
+
+def shared_batcher(model: EngineModel, lat_hw: int, frames_per_session: int) -> CrossSessionBatcher:
+    """Cross-session mode: one scheduler per (model, latent size, session batch size), created by the first
+    session that asks.  Its mux is a MuseTalkBatchSession: up to LTB_MT_GROUPS sessions' B frames run as ONE UNet + VAE graph."""
+    with _BATCHER_LOCK:
+        table = getattr(model, "_ltb_batchers", None)
+        if table is None:
+            table = model._ltb_batchers = {}
+        key = (int(lat_hw), int(frames_per_session))
+        if key not in table:
+            mux = MuseTalkBatchSession(model.net, lat_hw, int(os.environ.get("LTB_MT_GROUPS", "4")), frames_per_session)
+            table[key] = CrossSessionBatcher(mux, float(os.environ.get("LTB_MUX_WAIT_MS", "4")))
+        return table[key]
+
+
 @register("avatar", "musetalk")
 class MuseReal(BaseAvatar):
     def __init__(self, opt, model, avatar):
@@ -118,8 +136,12 @@ class MuseReal(BaseAvatar):
                                         self.mask_coords_list_cycle, self.input_latent_list_cycle)
             if isinstance(avatar, AvatarPayload):
                 avatar.engine_avatar = eng_avatar
-        # every session owns its stream + scratch (two: UNet/VAE graph, Whisper graph); weights / avatar assets are shared
-        self.engine_session = MuseTalkSession(model.net, eng_avatar, self.batch_size)
+        self._engine_avatar = eng_avatar
+        cross = bool(getattr(opt, "ltb_cross_session", False)) or os.environ.get("LTB_CROSS_SESSION", "0") == "1"
+        self._batcher = shared_batcher(model, eng_avatar.lat_hw, self.batch_size) if cross else None
+        # every session owns its stream + scratch (two: UNet/VAE graph, Whisper graph); weights / avatar assets are shared.
+        # Cross-session mode: the session keeps only a paste-back context, its UNet/VAE pass runs in the shared batch.
+        self.engine_session = MuseTalkSession(model.net, eng_avatar, self.batch_size, paste_only=cross)
         self.audio_processor = WhisperFeatures(model.whisper, self.batch_size, opt.l, opt.r)
         self.asr = WhisperASR(opt, self, self.audio_processor)
         self.asr.warm_up()
@@ -139,6 +161,8 @@ class MuseReal(BaseAvatar):
 
     def inference_batch(self, index, audiofeat_batch):
         whisper_batch = np.stack(audiofeat_batch)                                   # (B, 50, 384)
+        if self._batcher is not None:                                               # one group request of the shared cross-session batch
+            return self._batcher.submit([(self._engine_avatar, index, whisper_batch)])[0]
         return self.engine_session.infer(index, whisper_batch)                      # uint8 (B,256,256,3) BGR, as decode_latents
 
     def paste_back_frame(self, pred_frame, idx: int):

@@ -313,8 +313,9 @@ def test_cross_session_batch_matches_per_session(small_nets):
     _, aud = M.synth_latents_and_audio(G * Bs, seed=77)
     aud = aud.numpy()
     indices = [3, 0, 7]                                     # 7 > n: mirror-indexed like the reference (basereal mirror_index)
-    bs = MuseTalkBatchSession(model, avs, Bs)
-    outs = bs.step(indices, aud)
+    bs = MuseTalkBatchSession(model, 32, G, Bs)
+    reqs = [(avs[g], indices[g], aud[g * Bs:(g + 1) * Bs]) for g in range(G)]
+    outs = bs.step(reqs)
     pred_b = bs.ctx.download(bs.image_u8)
     for g in range(G):
         s = MuseTalkSession(model, avs[g], Bs)
@@ -328,8 +329,13 @@ def test_cross_session_batch_matches_per_session(small_nets):
             want = P.mt_paste_back(got[i], frames[idx], coords[idx], masks[idx], crops[idx])
             assert np.array_equal(outs[g][i], want), (g, i)
         s.close()
-    again = bs.step(indices, None)                           # features resident: replay
+    again = bs.step([(avs[g], indices[g], None) for g in range(G)])           # features resident: replay
     for g in range(G):
         assert np.abs(again[g].astype(int) - outs[g].astype(int)).max() <= 2
+    # a partial round with the sessions in other groups: any session may occupy any group
+    preds = bs.infer_groups([reqs[2], reqs[0]])
+    assert len(preds) == 2 and preds[0].shape == (Bs, 256, 256, 3)
+    assert np.abs(preds[0].astype(int) - pred_b[2 * Bs:3 * Bs].astype(int)).max() <= 2
+    assert np.abs(preds[1].astype(int) - pred_b[0:Bs].astype(int)).max() <= 2
     bs.close()
     ctx.close()

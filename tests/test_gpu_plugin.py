@@ -216,3 +216,66 @@ def test_lipreal_cross_session_mode(w2l_state_dict):
     batcher.close()
     for av, *_ in sessions:
         av.close()
+
+
+def test_musereal_cross_session_mode():
+    """opt.ltb_cross_session for MuseTalk: three sessions with their own avatars call inference_batch from three
+    threads; the shared scheduler packs their group requests into common UNet + VAE launches (MuseTalkBatchSession) and every session
+    gets ITS predictions back — equal (PSNR >= 40 dB) to the CPU oracle chain on its own latents / features — and pastes them with
+    its own assets, bit-exact against the blend oracle."""
+    import threading
+    stubs.install()
+    from transformers import WhisperConfig, WhisperModel
+    from livetalking_b200.plugin import musetalk_avatar as MT
+    from oracle import musetalk_ref as M
+    from oracle import paste_ref as P
+    from oracle.wav2lip_ref import psnr_u8
+    import registry
+    torch.manual_seed(1)
+    wm = WhisperModel(WhisperConfig(d_model=384, encoder_layers=4, encoder_attention_heads=6, encoder_ffn_dim=1536, decoder_layers=1,
+                                    decoder_attention_heads=6, decoder_ffn_dim=64)).eval()
+    us, vs = M.synth_unet_state_dict(M.UNET_SMALL), M.synth_vae_state_dict(M.VAE_SMALL)
+    model = MT.make_model(us, vs, wm.state_dict(), M.UNET_SMALL, M.VAE_SMALL)
+    B, n, S = 2, 3, 3
+    rng = np.random.default_rng(8)
+    coords = [(60, 30, 190, 170), (50, 20, 200, 180), (70, 40, 180, 160)]
+    crops = [(30, 10, 230, 195), (20, 5, 240, 198), (40, 20, 220, 190)]
+    masks = [np.repeat((np.linspace(0, 255, (c[3] - c[1]))[:, None] * np.ones((1, c[2] - c[0]))).astype(np.uint8)[..., None], 3, 2) for c in crops]
+    sessions = []
+    for s in range(S):
+        lat, aud = M.synth_latents_and_audio(n, seed=20 + s)
+        frames = list(rng.integers(0, 256, (n, 200, 260 + 4 * s, 3), dtype=np.uint8))
+        avatar = MT.make_avatar(frames, masks, coords, crops, [lat[i:i + 1] for i in range(n)], model)
+        av = registry.create("avatar", "musetalk", opt=stubs.Opt(batch_size=B, ltb_cross_session=True, sessionid=s), model=model, avatar=avatar)
+        sessions.append((av, lat, aud[:B], frames))
+    batcher = sessions[0][0]._batcher
+    assert batcher is not None and all(x[0]._batcher is batcher for x in sessions)
+    results = [None] * S
+
+    def run(s):
+        av, lat, aud, frames = sessions[s]
+        feats = [aud[i].numpy().astype(np.float32) for i in range(B)]
+        for _rep in range(4):
+            pred = av.inference_batch(s, feats)
+        results[s] = pred
+
+    ths = [threading.Thread(target=run, args=(s,)) for s in range(S)]
+    for t_ in ths:
+        t_.start()
+    for t_ in ths:
+        t_.join(timeout=180)
+    for s in range(S):
+        av, lat, aud, frames = sessions[s]
+        pred = results[s]
+        assert pred is not None and pred.shape == (B, 256, 256, 3) and pred.dtype == np.uint8
+        idxs = [P.mirror_index(n, s + i) for i in range(B)]
+        want = M.decode_latents_u8(vs, M.VAE_SMALL, M.unet_forward(us, M.UNET_SMALL, lat[idxs], M.positional_encoding(aud)))
+        assert psnr_u8(pred, want) >= 40.0, (s, psnr_u8(pred, want))
+        for i in range(B):
+            out = av.paste_back_frame(pred[i], idxs[i])
+            assert np.array_equal(out, P.mt_paste_back(pred[i], frames[idxs[i]], coords[idxs[i]], masks[idxs[i]], crops[idxs[i]]))
+    assert batcher.slots == S * 4 and batcher.batches <= S * 4
+    batcher.close()
+    batcher.mux.close()
+    for av, *_ in sessions:
+        av.close()
