@@ -14,6 +14,10 @@
 * mel_chain_golden.npz / mel_window_golden.npz — the reference's OWN audio.py + hparams.py and MelASR.run_step executed
                      here (only librosa.stft / filters.mel substituted): everything around the two librosa calls.
 * slice_golden.npz — Whisper window indices from the reference's own BaseASR._get_sliced_feature.
+* ultralight_golden.npz — the UNMODIFIED reference U-Net (avatars/ultralight/unet.py Model(6,'hubert'), imported by path) on
+                     oracle.ultralight_ref.synth_state_dict(0) / synth_inputs(2, seed=9); LightReal.inference_batch +
+                     paste_back_frame (avatars/ultralight_avatar.py:141-184) run from the reference module with that network; and
+                     the window rows of the reference's own BaseASR._feature2chunks as HubertASR.run_step calls it.
 * lipreal_golden.npz — LipReal.inference_batch + paste_back_frame run from the reference module (a4 + a5 + a6 glue).
 * pe_golden.npz, vae_glue_golden.npz, musereal_golden.npz — the reference's PositionalEncoding, VAE.preprocess_img /
                      decode_latents and MuseReal.inference_batch (third-party networks replaced by recorders / fakes).
@@ -422,6 +426,89 @@ def make_lipreal():
     print("lipreal golden ok", pred.shape, pred.dtype, float(pred.mean()))
 
 
+def make_ultralight():
+    """pins oracle/ultralight_ref.py to the reference's own code (see the module docstring)."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import stubs
+    stubs.install()
+    from oracle import ultralight_ref as U
+    sys.path.insert(0, REF)
+    sys.modules["avatars"].__path__ = [os.path.join(REF, "avatars")]
+    spec = importlib.util.spec_from_file_location("utils.image", os.path.join(REF, "utils/image.py"))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules["utils.image"] = m
+    spec.loader.exec_module(m)
+    dev = types.ModuleType("utils.device")
+    dev.initialize_device = lambda: "cpu"
+    sys.modules["utils.device"] = dev
+    av = types.ModuleType("av")
+    av.AudioFrame = av.VideoFrame = object
+    sys.modules["av"] = av
+    for name, attrs in (("avatars.audio_features", ()), ("avatars.audio_features.hubert", ("HubertASR",)),
+                        ("avatars.ultralight.audio2feature", ("Audio2Feature",))):
+        mod = types.ModuleType(name)
+        mod.__path__ = []
+        for a in attrs:
+            setattr(mod, a, object)
+        sys.modules[name] = mod
+    spec = importlib.util.spec_from_file_location("ref_ultralight_avatar", os.path.join(REF, "avatars/ultralight_avatar.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+
+    # (1) the network
+    sd = U.synth_state_dict(0)
+    img, audio, _faces = U.synth_inputs(2, seed=9)
+    net = ref.Model(6, "hubert")
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    with torch.no_grad():
+        out = net(img, audio).numpy()
+        aud = net.audio_model(audio).numpy()
+    # (2) the glue: batch 3 over a 2-frame avatar (mirror_index wraps and reverses)
+    B, n, index = 3, 2, 1
+    _i, audio3, faces = U.synth_inputs(3, seed=21)
+    faces = list(faces[:n])
+    rng = np.random.default_rng(21)
+    frames = [rng.integers(0, 256, (150, 200, 3), dtype=np.uint8) for _ in range(n)]
+    coords = [(20, 10, 140, 130), (30, 5, 114, 89)]                   # (x1, y1, x2, y2): 120x120 stretch-down, 84x84 = exact 2x decimation
+    feats = [audio3[i].numpy().reshape(16, 1024).copy() for i in range(B)]
+    lr = object.__new__(ref.LightReal)
+    lr.face_list_cycle, lr.frame_list_cycle, lr.coord_list_cycle = faces, frames, coords
+    lr.batch_size = B
+
+    class OnCpu(torch.nn.Module):                                      # LightReal calls .cuda() on its inputs: CPU box
+        def __init__(self, inner):
+            super().__init__()
+            self.inner = inner
+
+        def forward(self, a, b):
+            return self.inner(a, b)
+
+    lr.model = OnCpu(net)
+    torch.Tensor.cuda = lambda self, *a, **k: self                    # noqa: E731  (build container has no GPU)
+    pred = lr.inference_batch(index, feats)
+    pasted = [lr.paste_back_frame(pred[i], ref.mirror_index(n, index + i)) for i in range(B)]
+    crops = {}
+    for i in range(B):
+        x1, y1, x2, y2 = coords[ref.mirror_index(n, index + i)]
+        crops[f"crop{i}"] = pasted[i][y1:y2, x1:x2].copy()
+    # (3) window rows of HubertASR.run_step (hubert.py:42-45) from the reference's own BaseASR._get_sliced_feature
+    spec = importlib.util.spec_from_file_location("ref_base_asr", os.path.join(REF, "avatars/audio_features/base_asr.py"))
+    ba = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ba)
+    asr = object.__new__(ba.BaseASR)
+    rows = {}
+    for (T, Bsz, l) in ((51, 16, 10), (27, 4, 10), (19, 2, 6)):
+        table = np.arange(T, dtype=np.float32)[:, None] * np.ones((1, 4), np.float32)
+        chunks = asr._feature2chunks(feature_array=table, batch_size=Bsz, audio_feat_win=[4, 4], start=l / 2, feature_idx_multiplier=2)
+        rows[f"rows_{T}_{Bsz}_{l}"] = np.stack(chunks)[:, :, 0].astype(np.int64)
+    np.savez_compressed(os.path.join(HERE, "ultralight_golden.npz"), out_sub=out[:, :, ::4, ::4].astype(np.float32),
+                        out_u8=(out.transpose(0, 2, 3, 1) * 255.0).astype(np.uint8)[:, ::2, ::2], audio_emb=aud.reshape(2, -1)[:, ::16].astype(np.float32),
+                        pred_sub=pred[:, ::4, ::4, :].astype(np.float32), pred_shape=np.asarray(pred.shape), coords=np.asarray(coords, np.int32),
+                        index=np.int64(index), **crops, **rows)
+    print("ultralight golden ok", out.shape, float(out.mean()), float(out.std()), pred.dtype)
+
+
 if __name__ == "__main__":
     make_w2l()
     make_paste()
@@ -433,3 +520,4 @@ if __name__ == "__main__":
     make_mel_windows()
     make_mel_chain()
     make_musereal()
+    make_ultralight()
