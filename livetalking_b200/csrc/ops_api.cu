@@ -396,6 +396,77 @@ int ltb_op_attention(ltb_ctx* c, const void* q, int q_pitch, const void* k, int 
   c->launches += 1;
   return 0;
 }
+// ---- UltraLight / HuBERT ops
+int ltb_op_dwconv3x3(ltb_ctx* c, const void* x, int N, int IH, int IW, int ICtot, int ic_off, int C, const void* w_tap, const float* bias, int stride,
+                     int relu, void* out, int OCtot, int oc_off) {
+  if (!c || !x || !w_tap || !bias || !out) return LTB_FAIL("dwconv3x3: null argument");
+  LTB_CTX_ENTER(c);
+  cudaError_t e = launch_dwconv3x3(static_cast<const __half*>(x), N, IH, IW, ICtot, ic_off, C, static_cast<const __half*>(w_tap), bias, stride, relu,
+                                   static_cast<__half*>(out), OCtot, oc_off, c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("dwconv3x3 (C, pitches, offsets % 8 == 0; stride 1 | 2): ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
+int ltb_op_upsample_bilinear2x(ltb_ctx* c, const void* x, int N, int H, int W, int ICtot, int ic_off, int C, void* out, int OCtot, int oc_off) {
+  if (!c || !x || !out) return LTB_FAIL("upsample_bilinear2x: null argument");
+  LTB_CTX_ENTER(c);
+  cudaError_t e = launch_upsample_bilinear2x(static_cast<const __half*>(x), N, H, W, ICtot, ic_off, C, static_cast<__half*>(out), OCtot, oc_off, c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("upsample_bilinear2x: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
+int ltb_op_ul_prep(ltb_ctx* c, const void* faces_u8, int nf, const void* d_index, int B, void* out) {
+  if (!c || !faces_u8 || !d_index || !out || nf < 1 || B < 1) return LTB_FAIL("ul_prep: bad argument");
+  LTB_CTX_ENTER(c);
+  cudaError_t e = launch_ul_prep(static_cast<const uint8_t*>(faces_u8), nf, static_cast<const int*>(d_index), B, static_cast<__half*>(out), c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("ul_prep: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
+int ltb_op_head_sigmoid255(ltb_ctx* c, const void* x, const float* w3x32, const float* b3, long long npix, float* pred) {
+  if (!c || !x || !w3x32 || !b3 || !pred) return LTB_FAIL("head_sigmoid255: null argument");
+  LTB_CTX_ENTER(c);
+  cudaError_t e = launch_w2l_head(static_cast<const __half*>(x), w3x32, b3, pred, (int)npix, c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("head_sigmoid255: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
+int ltb_op_ul_paste(ltb_ctx* c, const void* frames, const void* faces, const void* coords, const float* pred, void* out, int nf, int H, int W,
+                    int index, int explicit_idx, int slot0, int count) {
+  if (!c || !frames || !faces || !coords || !pred || !out || nf < 1 || count < 1) return LTB_FAIL("ul_paste: bad argument");
+  if (explicit_idx >= nf) return LTB_FAIL("ul_paste: frame index out of range");
+  LTB_CTX_ENTER(c);
+  cudaError_t e = launch_ul_paste(static_cast<const uint8_t*>(frames), static_cast<const uint8_t*>(faces), static_cast<const int*>(coords), pred,
+                                  static_cast<uint8_t*>(out), nf, H, W, index, explicit_idx, slot0, count, c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("ul_paste: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
+int ltb_op_hubert_conv0(ltb_ctx* c, const float* pcm, int n, const float* w, const float* bias, int C, float* stats, void* out) {
+  if (!c || !pcm || !w || !stats || !out) return LTB_FAIL("hubert_conv0: null argument");
+  LTB_CTX_ENTER(c);
+  cudaError_t e = launch_hubert_conv0(pcm, n, w, bias, C, stats, static_cast<__half*>(out), c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("hubert_conv0: ") + cudaGetErrorString(e));
+  c->launches += 2;
+  return 0;
+}
+int ltb_op_hubert_pos_conv(ltb_ctx* c, const void* h, int T, int D, int groups, int K, const void* w, const float* bias, void* out) {
+  if (!c || !h || !w || !bias || !out) return LTB_FAIL("hubert_pos_conv: null argument");
+  LTB_CTX_ENTER(c);
+  cudaError_t e = launch_hubert_pos_conv(static_cast<const __half*>(h), T, D, groups, K, static_cast<const __half*>(w), bias, static_cast<__half*>(out), c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("hubert_pos_conv (K = 128, D / groups = 64, out != h): ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
+int ltb_op_hubert_slice(ltb_ctx* c, const void* hidden, int Tc, int T, int D, int B, int R, float start, float mult, int win_l, float* out_f32,
+                        void* out_nhwc) {
+  if (!c || !hidden || (!out_f32 && !out_nhwc)) return LTB_FAIL("hubert_slice: null argument");
+  LTB_CTX_ENTER(c);
+  cudaError_t e = launch_hubert_slice(static_cast<const __half*>(hidden), Tc, T, D, B, R, start, mult, win_l, out_f32, static_cast<__half*>(out_nhwc), c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("hubert_slice: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
 int ltb_op_vae_post(ltb_ctx* c, const void* x, long long npix, int Ctot, void* out_u8) {
   if (!c || !x || !out_u8) return LTB_FAIL("vae_post: null argument");
   LTB_CTX_ENTER(c);

@@ -220,6 +220,40 @@ class Ctx:
         check(lib().ltb_op_attention(self._h, C.c_void_p(q_ptr), q_pitch, C.c_void_p(k_ptr), kv_pitch, kv_rows, C.c_void_p(vt.ptr), n_pad, B,
                                      heads, nq, valid, d, scale, C.c_void_p(out.ptr), out.pitch))
 
+    # ---- UltraLight / HuBERT ops
+    def dwconv3x3(self, x: DevTensor, N: int, IH: int, IW: int, w_tap: DevTensor, bias: DevTensor, stride: int, relu: bool, out: DevTensor):
+        check(lib().ltb_op_dwconv3x3(self._h, C.c_void_p(x.ptr), N, IH, IW, x.pitch, x.c_off, x.C, C.c_void_p(w_tap.ptr), C.c_void_p(bias.ptr),
+                                     stride, int(relu), C.c_void_p(out.ptr), out.pitch, out.c_off))
+
+    def upsample_bilinear2x(self, x: DevTensor, N: int, H: int, W: int, out: DevTensor):
+        check(lib().ltb_op_upsample_bilinear2x(self._h, C.c_void_p(x.ptr), N, H, W, x.pitch, x.c_off, x.C, C.c_void_p(out.ptr), out.pitch,
+                                               out.c_off))
+
+    def ul_prep(self, faces_u8: DevTensor, nf: int, d_index: DevTensor, B: int, out: DevTensor):
+        check(lib().ltb_op_ul_prep(self._h, C.c_void_p(faces_u8.ptr), nf, C.c_void_p(d_index.ptr), B, C.c_void_p(out.ptr)))
+
+    def head_sigmoid255(self, x: DevTensor, w3x32: DevTensor, b3: DevTensor, npix: int, pred: DevTensor):
+        check(lib().ltb_op_head_sigmoid255(self._h, C.c_void_p(x.ptr), C.c_void_p(w3x32.ptr), C.c_void_p(b3.ptr), npix, C.c_void_p(pred.ptr)))
+
+    def ul_paste(self, frames: DevTensor, faces: DevTensor, coords: DevTensor, pred: DevTensor, out: DevTensor, nf: int, H: int, W: int,
+                 index: int, explicit_idx: int, slot0: int, count: int):
+        check(lib().ltb_op_ul_paste(self._h, C.c_void_p(frames.ptr), C.c_void_p(faces.ptr), C.c_void_p(coords.ptr), C.c_void_p(pred.ptr),
+                                    C.c_void_p(out.ptr), nf, H, W, index, explicit_idx, slot0, count))
+
+    def hubert_conv0(self, pcm: DevTensor, n: int, w: DevTensor, bias: Optional[DevTensor], Cc: int, stats: DevTensor, out: DevTensor):
+        check(lib().ltb_op_hubert_conv0(self._h, C.c_void_p(pcm.ptr), n, C.c_void_p(w.ptr), C.c_void_p(bias.ptr) if bias is not None else None,
+                                        Cc, C.c_void_p(stats.ptr), C.c_void_p(out.ptr)))
+
+    def hubert_pos_conv(self, h: DevTensor, T: int, D: int, groups: int, K: int, w: DevTensor, bias: DevTensor, out: DevTensor):
+        check(lib().ltb_op_hubert_pos_conv(self._h, C.c_void_p(h.ptr), T, D, groups, K, C.c_void_p(w.ptr), C.c_void_p(bias.ptr),
+                                           C.c_void_p(out.ptr)))
+
+    def hubert_slice(self, hidden: DevTensor, Tc: int, T: int, D: int, B: int, R: int, start: float, mult: float, win_l: int,
+                     out_f32: Optional[DevTensor], out_nhwc: Optional[DevTensor]):
+        check(lib().ltb_op_hubert_slice(self._h, C.c_void_p(hidden.ptr), Tc, T, D, B, R, float(start), float(mult), win_l,
+                                        C.c_void_p(out_f32.ptr) if out_f32 is not None else None,
+                                        C.c_void_p(out_nhwc.ptr) if out_nhwc is not None else None))
+
     def bgr_to_i420(self, frames_u8: DevTensor, N: int, H: int, W: int, out_u8: DevTensor):
         """uint8 BGR [N,H,W,3] -> planar I420 [N, H*3/2, W] (encoder hand-off; cv2.COLOR_BGR2YUV_I420 arithmetic)."""
         check(lib().ltb_op_bgr_to_i420(self._h, C.c_void_p(frames_u8.ptr), N, H, W, C.c_void_p(out_u8.ptr)))

@@ -16,7 +16,9 @@ def install_aliases():
     for ours, theirs in (("livetalking_b200.plugin.wav2lip_avatar", "avatars.wav2lip_avatar"),
                          ("livetalking_b200.plugin.mel_asr", "avatars.audio_features.mel"),
                          ("livetalking_b200.plugin.musetalk_avatar", "avatars.musetalk_avatar"),
-                         ("livetalking_b200.plugin.whisper_asr", "avatars.audio_features.whisper")):
+                         ("livetalking_b200.plugin.whisper_asr", "avatars.audio_features.whisper"),
+                         ("livetalking_b200.plugin.ultralight_avatar", "avatars.ultralight_avatar"),
+                         ("livetalking_b200.plugin.hubert_asr", "avatars.audio_features.hubert")):
         sys.modules[theirs] = importlib.import_module(ours)
 
 

@@ -176,3 +176,80 @@ def test_whisper_asr_run_step_bookkeeping_matches_reference():
         assert a.type == b.type and np.array_equal(a.data, b.data)
     for k in ("avatars.audio_features", "avatars.audio_features.base_asr", "avatars.musetalk.whisper.audio2feature"):
         sys.modules.pop(k, None)
+
+
+def test_hubert_asr_run_step_bookkeeping_matches_reference():
+    """HubertASR.run_step (avatars/audio_features/hubert.py:27-51): 2B chunks forwarded, silence tracking over TWO batches (features
+    are computed unless this batch and the previous one were all silence), the whole l+r+2B context handed to the extractor, one
+    list of B windows queued, l+r chunks kept.  In the build container the reference's own class runs the same event sequence
+    (speech, then two silent steps) with its Audio2Feature replaced by a recorder; every queue / buffer / flag must match."""
+    from livetalking_b200.plugin.hubert_asr import HubertASR
+
+    class FakeFeatures:                                   # stands in for livetalking_b200.hubert.HubertFeatures
+        def __init__(self, B):
+            self.B, self.calls = B, []
+
+        def run(self, pcm):
+            self.calls.append(pcm.copy())
+            return np.ones((self.B, 16, 1024), np.float32)
+
+    Bsz = 3
+    opt = stubs.Opt(batch_size=Bsz)
+
+    def drive(asr):
+        _feed(asr, 20 + 2 * Bsz, np.random.default_rng(4))
+        asr.warm_up()
+        shapes = []
+        for _step in range(3):                            # speech; silence (previous was speech -> still computed); silence (skipped)
+            asr.run_step()
+            shapes.append([np.asarray(f).shape for f in asr.feat_queue.get()])
+        return shapes
+
+    fake = FakeFeatures(Bsz)
+    ours = HubertASR(opt, None, fake, audio_feat_length=[4, 4])
+    shapes = drive(ours)
+    assert shapes == [[(16, 1024)] * Bsz, [(16, 1024)] * Bsz, [(10, 1024)] * Bsz]
+    assert len(fake.calls) == 2 and fake.calls[0].size == (20 + 2 * Bsz) * 320 and ours.last_is_silence
+    with pytest.raises(RuntimeError):
+        HubertASR(opt, None, None)                        # no engine object -> loud failure, never a CPU fallback
+
+    ref_path = "/root/reference/avatars/audio_features/hubert.py"
+    if not os.path.exists(ref_path):
+        return
+    import types
+    a2f = types.ModuleType("avatars.ultralight.audio2feature")
+    a2f.Audio2Feature = object
+    sys.modules.setdefault("avatars.ultralight", types.ModuleType("avatars.ultralight"))
+    sys.modules["avatars.ultralight.audio2feature"] = a2f
+    spec = importlib.util.spec_from_file_location("ref_base_asr3", "/root/reference/avatars/audio_features/base_asr.py")
+    ref_base = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_base)
+    af = types.ModuleType("avatars.audio_features")
+    af.__path__ = []
+    sys.modules["avatars.audio_features"] = af
+    sys.modules["avatars.audio_features.base_asr"] = ref_base
+    spec = importlib.util.spec_from_file_location("ref_hubert_asr", ref_path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+
+    class Recorder:                                        # the reference's audio_processor
+        def __init__(self):
+            self.calls = []
+
+        def get_hubert_from_16k_speech(self, pcm):
+            self.calls.append(np.asarray(pcm).copy())
+            return np.ones(((len(pcm) - 80) // 320, 1024), np.float32)
+
+    rec = Recorder()
+    theirs = ref.HubertASR(opt, None, rec, audio_feat_length=[4, 4])
+    tshapes = drive(theirs)
+    assert tshapes == shapes
+    assert len(rec.calls) == len(fake.calls) and all(np.array_equal(a, b) for a, b in zip(rec.calls, fake.calls))
+    assert theirs.last_is_silence == ours.last_is_silence
+    assert len(theirs.frames) == len(ours.frames) and all(np.array_equal(x, y) for x, y in zip(theirs.frames, ours.frames))
+    assert theirs.output_queue.qsize() == ours.output_queue.qsize()
+    for _ in range(theirs.output_queue.qsize()):
+        a, b = theirs.output_queue.get(), ours.output_queue.get()
+        assert a.type == b.type and np.array_equal(a.data, b.data)
+    for k in ("avatars.audio_features", "avatars.audio_features.base_asr", "avatars.ultralight.audio2feature", "avatars.ultralight"):
+        sys.modules.pop(k, None)
