@@ -673,6 +673,71 @@ class MuseTalkBench:
         self.ctx.close()
 
 
+def ultralight_leg(torch, args):
+    """the UltraLight avatar path at the reference's batch size — HuBERT-large features over the (l + r + 2B)-chunk
+    window (avatars/audio_features/hubert.py:27-51) + per-avatar U-Net at 160x160 (avatars/ultralight/unet.py) + paste-back into
+    720p frames (avatars/ultralight_avatar.py:141-184).  Random-init weights of the real architectures, synthetic avatar."""
+    from livetalking_b200 import synth
+    from livetalking_b200.hubert import HubertEncoder, HubertFeatures, gflop_per_window
+    from livetalking_b200.ops import Ctx
+    from livetalking_b200.ultralight import UltraLightAvatar, UltraLightModel, UltraLightSession, unet_gflop_per_frame
+    B = BATCH
+    t0 = time.time()
+    ctx = Ctx()
+    enc = HubertEncoder(ctx, synth.random_hubert_state_dict())
+    net = UltraLightModel(ctx, synth.random_ultralight_state_dict())
+    frames, faces, coords = synth.synthetic_ultralight_avatar(n=16)
+    av = UltraLightAvatar(ctx, net, frames, faces, coords)
+    sess = UltraLightSession(av, B, ctx=ctx)                         # device-resident leg: one stream for the whole timed chain
+    hf = HubertFeatures(enc, B, SL, SR, out_nhwc=sess.audio16, ctx=ctx)
+    load_s = time.time() - t0
+    audio = synth.sine_audio(10.0)
+    hf.run_async(step_pcm(audio, 0, B))
+    ctx.sync()
+    stream = torch.cuda.ExternalStream(ctx.cuda_stream)
+    gate = Gate(torch, stream)
+    steps, warm = max(5, min(args.steps, 20)), max(3, min(args.warmup, 5))
+
+    def online(k):
+        hf.run_async(None)
+        sess.step_async(k * B)
+
+    for k in range(warm):
+        online(k)
+    ctx.sync()
+    l0 = ctx.launch_count
+    ms = timed_steps(torch, stream, gate, online, steps) / steps
+    launches = (ctx.launch_count - l0) // steps
+    ms_net = timed_steps(torch, stream, gate, lambda k: sess.step_async(k * B), steps) / steps
+    sess2 = UltraLightSession(av, B)                                  # e2e: the objects the plugin drives (own ctx per role)
+    hf2 = HubertFeatures(enc, B, SL, SR)
+
+    def e2e_one(k):
+        feats = hf2.run(step_pcm(audio, k, B))                         # HubertASR.run_step features (H2D PCM, D2H windows)
+        return sess2.infer_paste(k * B, feats)                         # inference_batch + paste_back_frame x B -> host frames
+
+    for k in range(warm):
+        e2e_one(k)
+    t1 = time.perf_counter()
+    for k in range(steps):
+        e2e_one(k)
+    e2e_ms = (time.perf_counter() - t1) * 1000.0 / steps
+    gf = unet_gflop_per_frame() * B + gflop_per_window(hf.n)
+    res = {"metric": "lip-sync frames/sec (UltraLight 160x160, batch %d, fp16: HuBERT-large features + U-Net + paste-back)" % B,
+           "value": round(1000.0 * B / ms, 2), "unit": "frames/s", "ms_per_step": round(ms, 3), "steps": steps, "warmup": warm,
+           "unet_paste_only_ms": round(ms_net, 3), "algorithmic_gflop_per_step": round(gf, 1), "tflops": round(gf / ms, 1),
+           "e2e": {"value": round(1000.0 * B / e2e_ms, 2), "unit": "frames/s", "h2d_bytes_per_step": int(hf2.n * 4 + B * 16 * 1024 * 2),
+                   "d2h_bytes_per_step": int(B * 16 * 1024 * 4 + B * av.H * av.W * 3),
+                   "how": "HubertFeatures.run(host PCM) + UltraLightSession.infer_paste(host windows) -> host frames, wall clock"},
+           "gpu_launches_per_step": int(launches), "sessions_at_25fps_per_gpu": int((1000.0 * B / ms) // 25), "model_load_s": round(load_s, 1),
+           "config": {"workload": "UltraLight Model(6,'hubert') at 160x160 + hubert-large (24 layers) over %d samples per step, 720p frames" % hf.n,
+                      "weights": "synthetic"}}
+    for o in (hf2, sess2, hf, sess):
+        o.close()
+    ctx.close()
+    return res
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -859,6 +924,8 @@ def run_ours(args):
         guarded("sessions32", lambda: sessions_leg(torch, engine, model, av, audio, 32, max(5, min(args.steps, 20))))
         guarded("cross_session", lambda: cross_session_leg(engine, model, max(5, min(args.steps, 20))))
         guarded("torch_eager_b200", lambda: torch_eager_b200(torch))
+    if rank == 0 and world == 1 and not args.quick and not args.no_ultralight:
+        guarded("ultralight", lambda: ultralight_leg(torch, args))
     if world > 1 and not args.quick:            # configs[3] at N > 1: 32 sessions on EVERY GPU (aggregate over ranks)
         guarded("sessions32", lambda: sessions_leg(torch, engine, model, av, audio, 32, max(5, min(args.steps, 20)), dist, world))
     if not args.no_musetalk and not args.quick:  # every rank runs the MuseTalk legs (collectives inside): same guard on all ranks
@@ -928,6 +995,7 @@ def main():
     ap.add_argument("--musetalk512", action="store_true", help=argparse.SUPPRESS)   # accepted for compatibility: the leg is on by default
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--sustained-s", type=float, default=3.0)
+    ap.add_argument("--no-ultralight", action="store_true", help="skip the UltraLight + HuBERT leg")
     ap.add_argument("--only-musetalk", action="store_true", help="development: contract line + the MuseTalk legs only")
     ap.add_argument("--quick", action="store_true", help="contract line only (value / e2e / roofline), no extra legs")
     ap.add_argument("--sessions", type=int, default=1, help="concurrent avatar sessions per GPU in the `value` leg (each batch 16, own stream)")

@@ -187,3 +187,15 @@ class HubertFeatures:
             self.close()
         except Exception:
             pass
+
+
+def gflop_per_window(n_samples: int, layers: int = 24, d_model: int = 1024, ffn: int = 4096, conv_dim: int = 512) -> float:
+    """Algorithmic GFLOP (2 x MAC) of one HubertModel forward over n_samples of 16 kHz audio."""
+    fl, t, cin = 0.0, n_samples, 1
+    for k, s in zip(CONV_KERNEL, CONV_STRIDE):
+        t = (t - k) // s + 1
+        fl += 2.0 * t * conv_dim * cin * k
+        cin = conv_dim
+    fl += 2.0 * t * conv_dim * d_model + 2.0 * t * d_model * (d_model // POS_GROUPS) * POS_K
+    fl += layers * (2.0 * t * (4 * d_model * d_model + 2 * d_model * ffn) + 4.0 * t * t * d_model)
+    return fl / 1e9

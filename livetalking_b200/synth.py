@@ -55,6 +55,16 @@ def sine_audio(seconds: float = 60.0, freq: float = 440.0, amp: float = 0.5, sr:
 # ----------------------------------------------------------------------------------------------------------------------
 # random-init MuseTalk networks (diffusers / HF key schemes) for benchmarking — values from a rotating random pool
 # ----------------------------------------------------------------------------------------------------------------------
+class _Rng:
+    """Direct generator (same interface as _Pool) for the large HuBERT weights: 315 M values in a few seconds."""
+
+    def __init__(self, seed):
+        self.rng = np.random.default_rng(seed)
+
+    def randn(self, shape, std):
+        return self.rng.standard_normal(shape, dtype=np.float32) * np.float32(std)
+
+
 class _Pool:
     def __init__(self, seed):
         rng = np.random.default_rng(seed)
@@ -209,3 +219,85 @@ def synthetic_musetalk_avatar(n: int = 16, H: int = 720, W: int = 1280, bbox=(48
     mask = np.stack([m, m, m], -1)
     latents = [(rng.standard_normal((1, 8, hw, hw)) * 0.8).astype(np.float16) for _ in range(n)]
     return frames, [mask] * n, [bbox] * n, [crop] * n, latents
+
+
+def random_hubert_state_dict(layers: int = 24, d_model: int = 1024, ffn: int = 4096, seed: int = 3):
+    """HF ``HubertModel`` key scheme of hubert-large-ls960-ft (the checkpoint avatars/ultralight/audio2feature.py:9-10 loads):
+    7 conv layers (512 ch, per-layer LayerNorm, bias), projection 512 -> d_model, weight-normed 16-group positional conv (k 128),
+    `layers` stable-LayerNorm encoder layers."""
+    g = _Rng(seed)
+    ones, zeros = (lambda n: np.ones(n, np.float32)), (lambda n: np.zeros(n, np.float32))
+    sd = {}
+    for i, k in enumerate((10, 3, 3, 3, 3, 2, 2)):
+        cin = 1 if i == 0 else 512
+        p = f"feature_extractor.conv_layers.{i}"
+        sd[f"{p}.conv.weight"], sd[f"{p}.conv.bias"] = g.randn((512, cin, k), (2.0 / (cin * k)) ** 0.5), g.randn((512,), 0.02)
+        sd[f"{p}.layer_norm.weight"], sd[f"{p}.layer_norm.bias"] = ones(512), zeros(512)
+    sd["feature_projection.layer_norm.weight"], sd["feature_projection.layer_norm.bias"] = ones(512), zeros(512)
+    sd["feature_projection.projection.weight"], sd["feature_projection.projection.bias"] = g.randn((d_model, 512), 512 ** -0.5), zeros(d_model)
+    pc = "encoder.pos_conv_embed.conv"
+    v = g.randn((d_model, d_model // 16, 128), (1.0 / (128 * d_model // 16)) ** 0.5)
+    sd[f"{pc}.parametrizations.weight.original1"] = v
+    sd[f"{pc}.parametrizations.weight.original0"] = np.sqrt((v.astype(np.float64) ** 2).sum((0, 1), keepdims=True)).astype(np.float32)
+    sd[f"{pc}.bias"] = zeros(d_model)
+    sd["encoder.layer_norm.weight"], sd["encoder.layer_norm.bias"] = ones(d_model), zeros(d_model)
+    proto = {}                                   # one layer's worth of random values, reused by every layer (benchmark weights)
+    for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+        proto[n] = g.randn((d_model, d_model), d_model ** -0.5)
+    proto["fc1"], proto["fc2"] = g.randn((ffn, d_model), d_model ** -0.5), g.randn((d_model, ffn), ffn ** -0.5)
+    for i in range(layers):
+        p = f"encoder.layers.{i}"
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            sd[f"{p}.attention.{n}.weight"], sd[f"{p}.attention.{n}.bias"] = proto[n], zeros(d_model)
+        for n in ("layer_norm", "final_layer_norm"):
+            sd[f"{p}.{n}.weight"], sd[f"{p}.{n}.bias"] = ones(d_model), zeros(d_model)
+        sd[f"{p}.feed_forward.intermediate_dense.weight"], sd[f"{p}.feed_forward.intermediate_dense.bias"] = proto["fc1"], zeros(ffn)
+        sd[f"{p}.feed_forward.output_dense.weight"], sd[f"{p}.feed_forward.output_dense.bias"] = proto["fc2"], zeros(d_model)
+    return sd
+
+
+def random_ultralight_state_dict(seed: int = 4):
+    """``Model(6, 'hubert').state_dict()`` key scheme (avatars/ultralight/unet.py:184-206), He-normal convs, identity-ish BatchNorms."""
+    g = _Rng(seed)
+    sd = {}
+    ch = [32, 64, 128, 256, 512]
+
+    def bn(p, c):
+        sd[p + ".weight"], sd[p + ".bias"] = np.ones(c, np.float32), g.randn((c,), 0.05)
+        sd[p + ".running_mean"], sd[p + ".running_var"] = np.zeros(c, np.float32), np.ones(c, np.float32)
+
+    def ir(p, inp, oup):
+        hid = inp * 2
+        sd[p + ".conv.0.weight"] = g.randn((hid, inp, 1, 1), (2.0 / inp) ** 0.5)
+        bn(p + ".conv.1", hid)
+        sd[p + ".conv.3.weight"] = g.randn((hid, 1, 3, 3), (2.0 / 9) ** 0.5)
+        bn(p + ".conv.4", hid)
+        sd[p + ".conv.6.weight"] = g.randn((oup, hid, 1, 1), (0.5 / hid) ** 0.5)
+        bn(p + ".conv.7", oup)
+
+    def dc(p, i, o):
+        ir(p + ".double_conv.0", i, o)
+        ir(p + ".double_conv.1", o, o)
+
+    a = "audio_model"
+    ir(a + ".conv1", 16, ch[1]), ir(a + ".conv2", ch[1], ch[2]), ir(a + ".conv4", ch[3], ch[3]), ir(a + ".conv6", ch[4], ch[4]), ir(a + ".conv7", ch[4], ch[4])
+    for name, cin, cout in ((a + ".conv3", ch[2], ch[3]), (a + ".conv5", ch[3], ch[4])):
+        sd[name + ".weight"], sd[name + ".bias"] = g.randn((cout, cin, 3, 3), (2.0 / (9 * cin)) ** 0.5), g.randn((cout,), 0.05)
+    bn(a + ".bn3", ch[3]), bn(a + ".bn5", ch[4])
+    dc("fuse_conv.0", ch[4] * 2, ch[4]), dc("fuse_conv.1", ch[4], ch[3])
+    ir("inc.inconv.0", 6, ch[0])
+    for i in range(4):
+        dc(f"down{i + 1}.maxpool_conv.0", ch[i], ch[i + 1])
+    for i, (ci, co) in enumerate(((ch[4], ch[3] // 2), (ch[3], ch[2] // 2), (ch[2], ch[1] // 2), (ch[1], ch[0]))):
+        dc(f"up{i + 1}.conv", ci, co)
+    sd["outc.conv.weight"], sd["outc.conv.bias"] = g.randn((3, ch[0], 1, 1), (2.0 / ch[0]) ** 0.5), g.randn((3,), 0.1)
+    return sd
+
+
+def synthetic_ultralight_avatar(n: int = 16, H: int = 720, W: int = 1280, bbox=(500, 180, 780, 460), seed: int = 0):
+    """frames (n,H,W,3) uint8, 168x168 face crops, bbox (x1,y1,x2,y2) per frame (ultralight_avatar.py:63-82 on-disk content)."""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    frames = np.stack([np.roll(base, 3 * i, axis=1) for i in range(n)])
+    faces = rng.integers(0, 256, (n, 168, 168, 3), dtype=np.uint8)
+    return frames, faces, [tuple(bbox)] * n

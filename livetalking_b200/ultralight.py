@@ -250,3 +250,33 @@ class UltraLightSession:
             self.close()
         except Exception:
             pass
+
+
+def unet_gflop_per_frame() -> float:
+    """Algorithmic GFLOP (2 x MAC) of one Model(6,'hubert') forward at 160x160 (real channel counts, no padding)."""
+    fl = 0.0
+
+    def ir(inp, oup, H, s=1):
+        nonlocal fl
+        hid, O = 2 * inp, H // s
+        fl += 2.0 * H * H * inp * hid + 2.0 * O * O * 9 * hid + 2.0 * O * O * hid * oup
+        return O
+
+    def dc(inp, oup, H, s):
+        O = ir(inp, oup, H, s)
+        return ir(oup, oup, O)
+
+    ir(6, CH[0], 160)
+    H = 160
+    for i in range(4):
+        H = dc(CH[i], CH[i + 1], H, 2)
+    ir(16, CH[1], 32), ir(CH[1], CH[2], 32)
+    fl += 2.0 * 16 * 16 * 9 * CH[2] * CH[3]
+    ir(CH[3], CH[3], 16)
+    fl += 2.0 * 10 * 10 * 9 * CH[3] * CH[4]
+    ir(CH[4], CH[4], 10), ir(CH[4], CH[4], 10)
+    dc(2 * CH[4], CH[4], 10, 1), dc(CH[4], CH[3], 10, 1)
+    for i, (ci, co) in enumerate(((CH[4], CH[3] // 2), (CH[3], CH[2] // 2), (CH[2], CH[1] // 2), (CH[1], CH[0]))):
+        dc(ci, co, 20 << i, 1)
+    fl += 2.0 * 160 * 160 * CH[0] * 3
+    return fl / 1e9
