@@ -712,9 +712,12 @@ def ultralight_leg(torch, args):
     sess2 = UltraLightSession(av, B)                                  # e2e: the objects the plugin drives (own ctx per role)
     hf2 = HubertFeatures(enc, B, SL, SR)
 
+    from livetalking_b200 import engine
+    ring = [engine.PinnedBuffer((B, av.H, av.W, 3), np.uint8) for _ in range(4)]   # the plugin's pinned output ring
+
     def e2e_one(k):
         feats = hf2.run(step_pcm(audio, k, B))                         # HubertASR.run_step features (H2D PCM, D2H windows)
-        return sess2.infer_paste(k * B, feats)                         # inference_batch + paste_back_frame x B -> host frames
+        return sess2.infer_paste(k * B, feats, out=ring[k % 4].array)  # inference_batch + paste_back_frame x B -> host frames
 
     for k in range(warm):
         e2e_one(k)
@@ -732,7 +735,7 @@ def ultralight_leg(torch, args):
            "gpu_launches_per_step": int(launches), "sessions_at_25fps_per_gpu": int((1000.0 * B / ms) // 25), "model_load_s": round(load_s, 1),
            "config": {"workload": "UltraLight Model(6,'hubert') at 160x160 + hubert-large (24 layers) over %d samples per step, 720p frames" % hf.n,
                       "weights": "synthetic"}}
-    for o in (hf2, sess2, hf, sess):
+    for o in (hf2, sess2, hf, sess, *ring):
         o.close()
     ctx.close()
     return res

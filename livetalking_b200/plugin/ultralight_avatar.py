@@ -106,12 +106,32 @@ class LightReal(BaseAvatar):
         self.audio_processor = HubertFeatures(audio_processor.encoder, self.batch_size, opt.l, opt.r)
         self.asr = HubertASR(opt, self, self.audio_processor, audio_feat_length=[4, 4])
         self.asr.warm_up()
+        # page-locked output ring for the fused mode (a D2H into pageable memory runs at a few GB/s, pinned at PCIe speed); a buffer is
+        # reused after `ring` more batches: res_frame_queue holds at most 2 batches (base_avatar.py:86) + one produced + one pasted
+        self._ring, self._ring_pos = [], 0
+        if not self._return_pred:
+            try:
+                shape = (self.batch_size, eng_avatar.H, eng_avatar.W, 3)
+                self._ring = [engine.PinnedBuffer(shape, np.uint8) for _ in range(max(4, int(os.environ.get("LTB_PIN_RING", "4"))))]
+            except Exception as e:   # pinned memory exhausted: pageable output buffers
+                logger.warning("pinned output ring unavailable (%r): using pageable buffers", e)
+                self._ring = []
 
     def close(self):
         for o in (getattr(self, "engine_session", None), getattr(self, "audio_processor", None)):
             if o is not None:
                 o.close()
         self.engine_session = self.audio_processor = None
+        for b in getattr(self, "_ring", []):
+            b.close()
+        self._ring = []
+
+    def _next_out(self):
+        if not self._ring:
+            return None
+        buf = self._ring[self._ring_pos % len(self._ring)].array
+        self._ring_pos += 1
+        return buf
 
     def __del__(self):
         try:
@@ -135,7 +155,7 @@ class LightReal(BaseAvatar):
         feats = self._features(audiofeat_batch)
         if self._return_pred:
             return self.engine_session.infer(index, feats, want_pred=True)          # float32 (B,160,160,3), as the reference
-        frames = self.engine_session.infer_paste(index, feats)                       # (B,H,W,3) uint8: one engine round, one D2H
+        frames = self.engine_session.infer_paste(index, feats, out=self._next_out())   # (B,H,W,3) uint8: one engine round, one D2H
         length = len(self.face_list_cycle)
         return [EngineFrame(frames[i], mirror_index(length, index + i)) for i in range(self.batch_size)]
 
