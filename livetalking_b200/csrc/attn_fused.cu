@@ -13,7 +13,9 @@
 // box is 64 channels wide and the tensor's channel extent is the head dim, so the padding up to 64 is zero-filled); V^T tiles from
 // the [B*H][d][keys] buffer transpose_heads writes.  TMEM: 128 columns of S + d columns of O (<= 256 for d <= 128: two CTAs per SM
 // overlap each other's MMA / softmax phases, so the per-CTA pipeline is kept simple and serial).
-// Roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax + epilogue (TMEM lane quarter = warp % 4).
+// Roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 softmax + epilogue: TMEM lane quarter = warp % 4, and the two
+// warps of a quarter split the 128 key columns of a tile (ncu r02q: with four softmax warps the kernel sat at 32 % of the SFU pipe and
+// 37 % issue utilisation — latency bound on one warp per scheduler); their row statistics are merged once, after pass 1.
 #include <cuda.h>
 
 #include <mutex>
@@ -33,7 +35,7 @@ struct alignas(64) AttnParams {
   float scale_log2e;   // scale * log2(e): probabilities are exp2((s - m) * scale_log2e)
 };
 
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 320;
 constexpr int kTileBytes = 128 * 128;   // 128 rows x 64 fp16
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -46,6 +48,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fused_kernel(const __grid_c
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t q_full, k_full[2], k_empty[2], v_full, v_empty, s_full, s_empty, p_full, p_empty, o_full;
   __shared__ uint32_t tmem_slot;
+  __shared__ float2 row_stat[2][128];      // (max, sum) of each query row over one half of the key columns
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * 128, bh = blockIdx.y, b = bh / p.H, h = bh - b * p.H;
@@ -70,8 +73,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fused_kernel(const __grid_c
     mbar_init(smem_u32(&v_full), 1);
     mbar_init(smem_u32(&v_empty), 1);
     mbar_init(smem_u32(&s_full), 1);
-    mbar_init(smem_u32(&s_empty), 4);     // the four softmax warps
-    mbar_init(smem_u32(&p_full), 4);
+    mbar_init(smem_u32(&s_empty), 8);     // the eight softmax warps
+    mbar_init(smem_u32(&p_full), 8);
     mbar_init(smem_u32(&p_empty), 1);
     mbar_init(smem_u32(&o_full), 1);
     mbar_fence_init();
@@ -151,68 +154,82 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fused_kernel(const __grid_c
     umma_commit_if(leader, smem_u32(&o_full));
     __syncwarp();
   } else {
-    // =============================================================== softmax + epilogue: one query row per thread
+    // =============================================================== softmax + epilogue: one query row x 64 key columns per thread
     const int q = warp & 3;                        // TMEM lane quarter of this warp
+    const int half = (warp - 2) >> 2;              // which 64 key columns of every tile
     const int row = q * 32 + lane;                 // query row inside the tile
     const uint32_t trow = ((uint32_t)(q * 32) << 16);
+    const int cbase = half * 64;
     float m = -INFINITY, l = 0.f;
     uint32_t si = 0;
-    // ---- pass 1: running maximum and sum
+    // ---- pass 1: running maximum and sum over this thread's columns
     for (int kt = 0; kt < nkt; ++kt, ++si) {
       mbar_wait(smem_u32(&s_full), si & 1u);
       tc_fence_after();
-      const int kbase = kt * 128;
-      float tmax = -INFINITY;
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_s + trow + c0, v);
+      const int lim0 = p.valid - kt * 128 - cbase;     // columns [0, lim0) of this thread's 64 are real keys
+      if (lim0 > 0) {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(tmem_s + trow + cbase, v0);
+        tmem_ld32(tmem_s + trow + cbase + 32, v1);
         tmem_ld_wait();
+        float tmax = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < p.valid - kbase - c0) tmax = fmaxf(tmax, __uint_as_float(v[i]));
-      }
-      const float m_new = fmaxf(m, tmax);
-      float lsum = 0.f;
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_s + trow + c0, v);
-        tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) {
+          if (i < lim0) tmax = fmaxf(tmax, __uint_as_float(v0[i]));
+          if (i + 32 < lim0) tmax = fmaxf(tmax, __uint_as_float(v1[i]));
+        }
+        const float m_new = fmaxf(m, tmax);
+        float lsum = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < p.valid - kbase - c0) lsum += ex2f((__uint_as_float(v[i]) - m_new) * p.scale_log2e);
+        for (int i = 0; i < 32; ++i) {
+          if (i < lim0) lsum += ex2f((__uint_as_float(v0[i]) - m_new) * p.scale_log2e);
+          if (i + 32 < lim0) lsum += ex2f((__uint_as_float(v1[i]) - m_new) * p.scale_log2e);
+        }
+        l = l * ex2f((m - m_new) * p.scale_log2e) + lsum;   // m = -inf on the first tile: ex2(-inf) = 0
+        m = m_new;
       }
-      l = l * ex2f((m - m_new) * p.scale_log2e) + lsum;   // m = -inf on the first tile: ex2(-inf) = 0
-      m = m_new;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_empty));
     }
+    // ---- merge the two column halves of every row (named barrier over the 256 softmax threads)
+    row_stat[half][row] = make_float2(m, l);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    {
+      const float2 o = row_stat[half ^ 1][row];
+      const float mm = fmaxf(m, o.x);
+      // a half with no valid key at all has m = -inf, l = 0: its term vanishes (ex2(-inf) = 0; mm is finite since valid >= 1)
+      l = (m == -INFINITY ? 0.f : l * ex2f((m - mm) * p.scale_log2e)) + (o.x == -INFINITY ? 0.f : o.y * ex2f((o.x - mm) * p.scale_log2e));
+      m = mm;
+    }
     const float inv_l = 1.f / l;
-    // ---- pass 2: probabilities -> shared memory (A operand of the PV product)
+    // ---- pass 2: probabilities -> shared memory (A operand of the PV product); this thread fills rows of key block `half`
     for (int kt = 0; kt < nkt; ++kt, ++si) {
       mbar_wait(smem_u32(&s_full), si & 1u);
       tc_fence_after();
       mbar_wait(smem_u32(&p_empty), (kt & 1u) ^ 1u);     // the PV MMAs of the previous tile have consumed P
-      const int kbase = kt * 128;
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      const int lim0 = p.valid - kt * 128 - cbase;
+      uint8_t* prow = p_ptr + half * kTileBytes + row * 128;
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_s + trow + c0, v);
-        tmem_ld_wait();
+        if (lim0 > c0) {
+          tmem_ld32(tmem_s + trow + cbase + c0, v);
+          tmem_ld_wait();
+        }
+        const int lim = lim0 - c0;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {          // 8 keys = one 16-byte chunk of the K-major row
           uint32_t w[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int i = g * 8 + 2 * u;
-            const int lim = p.valid - kbase - c0;
             const float a = (i < lim) ? ex2f((__uint_as_float(v[i]) - m) * p.scale_log2e) * inv_l : 0.f;
             const float c = (i + 1 < lim) ? ex2f((__uint_as_float(v[i + 1]) - m) * p.scale_log2e) * inv_l : 0.f;
             w[u] = f32x2_to_f16x2_sat(a, c);
           }
-          const int key = c0 + g * 8;                       // 0..127 inside the tile
-          const int blk = key >> 6, chunk = (key & 63) >> 3;
-          uint8_t* dst = p_ptr + blk * kTileBytes + row * 128 + ((chunk ^ (row & 7)) << 4);
-          *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+          const int chunk = (c0 >> 3) + g;                  // 0..7 inside the 64-key block
+          *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
       fence_proxy_async_smem();        // generic-proxy writes of P visible to the tensor core's async proxy
@@ -228,7 +245,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fused_kernel(const __grid_c
     tc_fence_after();
     const int qi = q0 + row;
     __half* orow = p.out + ((size_t)b * p.nq + qi) * p.out_pitch + h * p.d;
-    for (int c0 = 0; c0 < p.d; c0 += 16) {
+    for (int c0 = half * 16; c0 < p.d; c0 += 32) {     // the two warps of a quarter alternate 16-column groups
       uint32_t v[16];
       tmem_ld16(tmem_o + trow + c0, v);
       tmem_ld_wait();
