@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fused_kernel(const __grid_c
   __shared__ uint32_t tmem_slot;
   __shared__ float2 row_stat[2][128];      // (max, sum) of each query row over one half of the key columns
 
+  pdl_launch_dependents();   // the output projection (a PDL-launched conv kernel) may start its prologue under this kernel's tail
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * 128, bh = blockIdx.y, b = bh / p.H, h = bh - b * p.H;
   const int chunks = (p.d + 63) / 64;                 // 64-channel K chunks of the QK^T contraction

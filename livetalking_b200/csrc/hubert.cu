@@ -6,6 +6,7 @@
 //   * the window gather of BaseASR._feature2chunks (base_asr.py:91-157) as HubertASR.run_step calls it (hubert.py:42-45)
 #include "ltb_internal.h"
 #include "ops.h"
+#include "ptx_sm100.cuh"
 
 namespace ltb {
 
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(1024) wave_stats_kernel(const float* __restric
 // out[t][c] = bias[c] + sum_k w[c][k] * (x[5t + k] - mean) * inv_std,  t < T0 = (n - 10) / 5 + 1 ; fp32 math, fp16 out [T0][512]
 __global__ void __launch_bounds__(256) hubert_conv0_kernel(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ w,
                                                            const float* __restrict__ bias, int T0, int C, __half* __restrict__ out) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   const int t = blockIdx.x;
   __shared__ float xs[10];
   if (threadIdx.x < 10) xs[threadIdx.x] = (x[5 * t + threadIdx.x] - stats[0]) * stats[1];
@@ -54,8 +56,7 @@ cudaError_t launch_hubert_conv0(const float* pcm, int n, const float* w, const f
   if (n < 10) return cudaErrorInvalidValue;
   wave_stats_kernel<<<1, 1024, 0, st>>>(pcm, n, stats);
   const int T0 = (n - 10) / 5 + 1;
-  hubert_conv0_kernel<<<T0, 256, 0, st>>>(pcm, stats, w, bias, T0, C, out);
-  return cudaGetLastError();
+  return launch_kernel_plain(hubert_conv0_kernel, dim3(T0), dim3(256), 0, st, pcm, stats, w, bias, T0, C, out);
 }
 
 // ------------------------------------------------------------------------------------------------ positional convolution
@@ -69,6 +70,7 @@ __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.f + er
 
 __global__ void __launch_bounds__(256) hubert_pos_conv_kernel(const __half* __restrict__ h, int T, int D, const __half* __restrict__ w,
                                                               const float* __restrict__ bias, __half* __restrict__ out) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   __shared__ uint32_t slab[kPcRows * kPcPitch];
   const int g = blockIdx.y, co = g * kPcCg + blockIdx.x * 4 + (threadIdx.x >> 6), tl = threadIdx.x & 63;
   for (int t0 = 0; t0 < T; t0 += 64) {
@@ -107,8 +109,7 @@ __global__ void __launch_bounds__(256) hubert_pos_conv_kernel(const __half* __re
 cudaError_t launch_hubert_pos_conv(const __half* h, int T, int D, int groups, int K, const __half* w, const float* bias, __half* out,
                                    cudaStream_t st) {
   if (K != kPcK || D % groups || D / groups != kPcCg || h == out) return cudaErrorInvalidValue;
-  hubert_pos_conv_kernel<<<dim3(kPcCg / 4, groups), 256, 0, st>>>(h, T, D, w, bias, out);
-  return cudaGetLastError();
+  return launch_kernel_plain(hubert_pos_conv_kernel, dim3(dim3(kPcCg / 4, groups)), dim3(256), 0, st, h, T, D, w, bias, out);
 }
 
 // ------------------------------------------------------------------------------------------------ window gather
@@ -118,6 +119,7 @@ cudaError_t launch_hubert_pos_conv(const __half* h, int T, int D, int groups, in
 // audiofeat.reshape(16,32,32) -> channel = row, pixel = feature index; ultralight_avatar.py:162).
 __global__ void __launch_bounds__(256) hubert_slice_kernel(const __half* __restrict__ hidden, int Tc, int T, int D, int B, int R, float start,
                                                            float mult, int win_l, float* __restrict__ out_f32, __half* __restrict__ out_nhwc) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   const int b = blockIdx.y, r = blockIdx.x;
   const int center = (int)(((float)b + start) * mult);
   const int left = (int)((float)center - (float)win_l * mult);
@@ -132,8 +134,7 @@ __global__ void __launch_bounds__(256) hubert_slice_kernel(const __half* __restr
 cudaError_t launch_hubert_slice(const __half* hidden, int Tc, int T, int D, int B, int R, float start, float mult, int win_l, float* out_f32,
                                 __half* out_nhwc, cudaStream_t st) {
   if (T < 1 || Tc < 1) return cudaErrorInvalidValue;
-  hubert_slice_kernel<<<dim3(R, B), 256, 0, st>>>(hidden, Tc, T, D, B, R, start, mult, win_l, out_f32, out_nhwc);
-  return cudaGetLastError();
+  return launch_kernel_plain(hubert_slice_kernel, dim3(dim3(R, B)), dim3(256), 0, st, hidden, Tc, T, D, B, R, start, mult, win_l, out_f32, out_nhwc);
 }
 
 }  // namespace ltb

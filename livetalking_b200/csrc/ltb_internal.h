@@ -64,6 +64,21 @@ inline cudaError_t launch_kernel_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// Ordinary (fully serialised) launch with the same call shape.  The element-wise / norm / paste kernels use it: they call
+// griddepcontrol.launch_dependents first thing, which lets a PDL-launched successor (a conv kernel: it executes griddepcontrol.wait
+// before it touches activations) run its prologue under this kernel's tail — but they are never started early themselves, so their
+// own loads (some through the non-coherent path: const __restrict__) need no special care.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.numAttrs = 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // cross-session batching: one descriptor per batch slot (device memory, rewritten before every step), so that ONE forward /
 // paste launch serves frames of different sessions (different avatars, unrelated frame indices)
 struct SlotDesc {

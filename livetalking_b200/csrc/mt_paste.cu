@@ -5,7 +5,9 @@
 //   m     = cvtColor(mask, BGR2GRAY) / 255      (15-bit fixed point: (3735 B + 19235 G + 9798 R + 16384) >> 15)
 //   body[y_s:y_e, x_s:x_e] = blendLinear(large, body_crop, m, 1-m) = sat_u8(rint((large*m + body*(1-m)) / (m + (1-m) + 1e-5)))
 // Byte work, bit-exact with OpenCV; one thread per output pixel of the full frame (copy outside the crop box).
+#include "ltb_internal.h"
 #include "ops.h"
+#include "ptx_sm100.cuh"
 
 namespace ltb {
 
@@ -54,6 +56,7 @@ __device__ __forceinline__ int resized_px(const uint8_t* __restrict__ pred, int 
 }
 
 __global__ void __launch_bounds__(256) mt_paste_kernel(const MtPasteArgs a) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   const int job = blockIdx.z, y = blockIdx.y;
   const int x = blockIdx.x * 256 + threadIdx.x;
   if (x >= a.W) return;
@@ -87,8 +90,7 @@ __global__ void __launch_bounds__(256) mt_paste_kernel(const MtPasteArgs a) {
 
 cudaError_t launch_mt_paste(const MtPasteArgs& a, int count, cudaStream_t st) {
   dim3 grid((a.W + 255) / 256, a.H, count);
-  mt_paste_kernel<<<grid, 256, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_kernel_plain(mt_paste_kernel, dim3(grid), dim3(256), 0, st, a);
 }
 
 }  // namespace ltb

@@ -7,6 +7,7 @@
 //     (avatars/musetalk/models/unet.py:12-27), VAE post-processing to u8 BGR (avatars/musetalk/models/vae.py:104-107).
 #include "ltb_internal.h"
 #include "ops.h"
+#include "ptx_sm100.cuh"
 
 namespace ltb {
 
@@ -29,6 +30,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 // NHWC row and the 8 per-channel partial sums stay in registers; groups are resolved once per thread at the end.
 __global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict__ x, int HW, int C, int Ctot, int c_off, int groups, int R,
                                                        float* __restrict__ stats) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   __shared__ float s_sum[64], s_sq[64];
   const int n = blockIdx.y;
   const int cpg = C / groups;
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
                                                        float eps, const float* __restrict__ stats, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, int silu, __half* __restrict__ out, int OCtot,
                                                        int oc_off, size_t total_vec) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   extern __shared__ float s_ab[];  // [2][C]
   __shared__ float s_mean[64], s_rstd[64];
   const int n = blockIdx.y;
@@ -174,8 +177,7 @@ cudaError_t launch_gn_stats(const __half* x, int N, int HW, int C, int Ctot, int
   const int max_splits = (HW + 4 * R - 1) / (4 * R);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
-  gn_stats_kernel<<<dim3(splits, N), threads, 0, st>>>(x, HW, C, Ctot, c_off, groups, R, stats);
-  return cudaGetLastError();
+  return launch_kernel_plain(gn_stats_kernel, dim3(dim3(splits, N)), dim3(threads), 0, st, x, HW, C, Ctot, c_off, groups, R, stats);
 }
 
 cudaError_t launch_gn_apply(const __half* x, int N, int HW, int C, int Ctot, int c_off, int groups, float eps, const float* stats,
@@ -185,9 +187,7 @@ cudaError_t launch_gn_apply(const __half* x, int N, int HW, int C, int Ctot, int
   int blocks = (int)((total_vec + 255) / 256);
   const int cap = (1184 + N - 1) / N;
   if (blocks > cap) blocks = cap;
-  gn_apply_kernel<<<dim3(blocks, N), 256, 2 * C * sizeof(float), st>>>(x, HW, C, Ctot, c_off, groups, eps, stats, gamma, beta, silu, out,
-                                                                        OCtot, oc_off, total_vec);
-  return cudaGetLastError();
+  return launch_kernel_plain(gn_apply_kernel, dim3(dim3(blocks, N)), dim3(256), 2 * C * sizeof(float), st, x, HW, C, Ctot, c_off, groups, eps, stats, gamma, beta, silu, out, OCtot, oc_off, total_vec);
 }
 
 cudaError_t launch_groupnorm(const __half* x, int N, int HW, int C, int Ctot, int c_off, int groups, float eps, const float* gamma,
@@ -202,6 +202,7 @@ constexpr int kLNMaxVec = 8;  // C <= 32*8*8 = 2048
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, int rows, int C, float eps,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         __half* __restrict__ out) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -253,8 +254,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
 cudaError_t launch_layernorm(const __half* x, int rows, int C, float eps, const float* gamma, const float* beta, __half* out,
                              cudaStream_t st) {
   if (C % 8 != 0 || C > 32 * 8 * kLNMaxVec) return cudaErrorInvalidValue;
-  layernorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, C, eps, gamma, beta, out);
-  return cudaGetLastError();
+  return launch_kernel_plain(layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, x, rows, C, eps, gamma, beta, out);
 }
 
 // ------------------------------------------------------------------------------------------------ softmax (warp per row)
@@ -263,6 +263,7 @@ cudaError_t launch_layernorm(const __half* x, int rows, int C, float eps, const 
 constexpr int kSMMaxVec = 6;  // cols <= 32*8*6 = 1536
 __global__ void __launch_bounds__(256) softmax_kernel(const __half* __restrict__ x, int rows, int cols, int ld, int valid, float scale,
                                                       __half* __restrict__ out) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -317,6 +318,7 @@ __global__ void __launch_bounds__(256) softmax_kernel(const __half* __restrict__
 constexpr int kSMWideVec = 4;
 __global__ void __launch_bounds__(256) softmax_wide_kernel(const __half* __restrict__ x, int cols, int ld, int valid, float scale,
                                                            __half* __restrict__ out) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   __shared__ float red[8];
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int nvec = cols / 8;
@@ -380,15 +382,15 @@ __global__ void __launch_bounds__(256) softmax_wide_kernel(const __half* __restr
 cudaError_t launch_softmax(const __half* x, int rows, int cols, int ld, int valid, float scale, __half* out, cudaStream_t st) {
   if (cols % 8 != 0 || cols > 256 * 8 * kSMWideVec || ld % 8 != 0 || valid > cols || valid < 1) return cudaErrorInvalidValue;
   if (cols > 32 * 8 * kSMMaxVec)
-    softmax_wide_kernel<<<rows, 256, 0, st>>>(x, cols, ld, valid, scale, out);
+    if (cudaError_t e_ = launch_kernel_plain(softmax_wide_kernel, dim3(rows), dim3(256), 0, st, x, cols, ld, valid, scale, out); e_ != cudaSuccess) return e_;
   else
-    softmax_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, cols, ld, valid, scale, out);
-  return cudaGetLastError();
+    return launch_kernel_plain(softmax_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, x, rows, cols, ld, valid, scale, out);
 }
 
 // ------------------------------------------------------------------------------------------------ GEGLU / GELU / add
 // h: rows x 2H  ->  out rows x H = h[:, :H] * gelu(h[:, H:])   (diffusers GEGLU: hidden, gate = proj(x).chunk(2))
 __global__ void __launch_bounds__(256) geglu_kernel(const __half* __restrict__ h, size_t total_vec, int H, __half* __restrict__ out) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   const unsigned vpr = H / 8;
   for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < (unsigned)total_vec; i += gridDim.x * 256u) {
     const size_t r = i / vpr;
@@ -409,13 +411,13 @@ cudaError_t launch_geglu(const __half* h, size_t rows, int H, __half* out, cudaS
   const size_t total = rows * (H / 8);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 1184) blocks = 1184;
-  geglu_kernel<<<blocks, 256, 0, st>>>(h, total, H, out);
-  return cudaGetLastError();
+  return launch_kernel_plain(geglu_kernel, dim3(blocks), dim3(256), 0, st, h, total, H, out);
 }
 
 // elementwise: out = act(x (+ y broadcast over rows with period `period` vectors)) ; act 0 none, 1 gelu(erf), 2 silu
 __global__ void __launch_bounds__(256) eltwise_kernel(const __half* __restrict__ x, const __half* __restrict__ y, size_t total_vec,
                                                       size_t period_vec, int act, __half* __restrict__ out) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   const unsigned tv = (unsigned)total_vec, pv = (unsigned)period_vec;
   for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < tv; i += gridDim.x * 256u) {
     const uint4 a = reinterpret_cast<const uint4*>(x)[i];
@@ -440,12 +442,12 @@ cudaError_t launch_eltwise(const __half* x, const __half* y, size_t n, size_t pe
   const size_t total = n / 8;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 1184) blocks = 1184;
-  eltwise_kernel<<<blocks, 256, 0, st>>>(x, y, total, y ? period / 8 : 1, act, out);
-  return cudaGetLastError();
+  return launch_kernel_plain(eltwise_kernel, dim3(blocks), dim3(256), 0, st, x, y, total, y ? period / 8 : 1, act, out);
 }
 
 // ------------------------------------------------------------------------------------------------ layout helpers
 __global__ void __launch_bounds__(256) upsample2x_kernel(const __half* __restrict__ x, int N, int H, int W, int C, __half* __restrict__ out) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   const unsigned vpp = C / 8;
   const unsigned total = (unsigned)N * (2 * H) * (2 * W) * vpp;   // < 2^32 for every tensor of the path
   for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
@@ -464,12 +466,12 @@ cudaError_t launch_upsample2x(const __half* x, int N, int H, int W, int C, __hal
   const size_t total = (size_t)N * 4 * H * W * (C / 8);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 2368) blocks = 2368;
-  upsample2x_kernel<<<blocks, 256, 0, st>>>(x, N, H, W, C, out);
-  return cudaGetLastError();
+  return launch_kernel_plain(upsample2x_kernel, dim3(blocks), dim3(256), 0, st, x, N, H, W, C, out);
 }
 
 __global__ void __launch_bounds__(256) copy_channels_kernel(const __half* __restrict__ src, size_t rows, int C, int SCtot, int sc_off,
                                                             __half* __restrict__ dst, int DCtot, int dc_off) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   const unsigned vpr = C / 8;
   const unsigned total = (unsigned)(rows * vpr);
   for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
@@ -485,13 +487,13 @@ cudaError_t launch_copy_channels(const __half* src, size_t rows, int C, int SCto
   int blocks = (int)((total + 255) / 256);
   if (blocks > 2368) blocks = 2368;
   if (blocks < 1) blocks = 1;
-  copy_channels_kernel<<<blocks, 256, 0, st>>>(src, rows, C, SCtot, sc_off, dst, DCtot, dc_off);
-  return cudaGetLastError();
+  return launch_kernel_plain(copy_channels_kernel, dim3(blocks), dim3(256), 0, st, src, rows, C, SCtot, sc_off, dst, DCtot, dc_off);
 }
 
 // V [B, n_keys, Ctot] (head h = channels [c_off + h*d, +d))  ->  VT [B, heads, d, n_pad]  (zero for key >= n_keys)
 __global__ void __launch_bounds__(256) transpose_heads_kernel(const __half* __restrict__ v, int n_keys, int Ctot, int c_off, int heads, int d,
                                                               int n_pad, __half* __restrict__ vt) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   __shared__ __half tile[32][33];
   const int bh = blockIdx.z, b = bh / heads, h = bh % heads;
   const int k0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
@@ -509,12 +511,12 @@ __global__ void __launch_bounds__(256) transpose_heads_kernel(const __half* __re
 cudaError_t launch_transpose_heads(const __half* v, int B, int n_keys, int Ctot, int c_off, int heads, int d, int n_pad, __half* vt,
                                    cudaStream_t st) {
   dim3 grid((n_pad + 31) / 32, (d + 31) / 32, B * heads);
-  transpose_heads_kernel<<<grid, 256, 0, st>>>(v, n_keys, Ctot, c_off, heads, d, n_pad, vt);
-  return cudaGetLastError();
+  return launch_kernel_plain(transpose_heads_kernel, dim3(grid), dim3(256), 0, st, v, n_keys, Ctot, c_off, heads, d, n_pad, vt);
 }
 
 // VAE decode post-processing (vae.py:104-107): (x/2+0.5).clamp(0,1) in fp16, *255, round-half-even, RGB->BGR, u8 NHWC
 __global__ void __launch_bounds__(256) vae_post_kernel(const __half* __restrict__ x, size_t npix, int Ctot, uint8_t* __restrict__ out) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < npix; i += (size_t)gridDim.x * 256) {
     const __half* px = x + i * Ctot;
     uint8_t o[3];
@@ -532,8 +534,7 @@ __global__ void __launch_bounds__(256) vae_post_kernel(const __half* __restrict_
 cudaError_t launch_vae_post(const __half* x, size_t npix, int Ctot, uint8_t* out, cudaStream_t st) {
   int blocks = (int)((npix + 255) / 256);
   if (blocks > 2368) blocks = 2368;
-  vae_post_kernel<<<blocks, 256, 0, st>>>(x, npix, Ctot, out);
-  return cudaGetLastError();
+  return launch_kernel_plain(vae_post_kernel, dim3(blocks), dim3(256), 0, st, x, npix, Ctot, out);
 }
 
 // u8 BGR image [N,H,W,3] -> fp16 NHWC [N,H,W,16] RGB normalised to [-1,1] (channels 3..15 zero); upper-half mask optional
@@ -567,6 +568,7 @@ cudaError_t launch_vae_pre(const uint8_t* img, int N, int H, int W, int half_mas
 // gather rows by mirror index: out[i] = table[mirror_index(n, *d_index + i)]  (latent / asset gather for a batch)
 __global__ void __launch_bounds__(256) gather_rows_kernel(const __half* __restrict__ table, int n, const int* __restrict__ d_index,
                                                           size_t row_vec, __half* __restrict__ out) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   const int i = blockIdx.y;
   const int index = *d_index + i;
   const int turn = index / n, res = index % n;
@@ -579,8 +581,7 @@ cudaError_t launch_gather_rows(const __half* table, int n, const int* d_index, i
   const size_t rv = row_elems / 8;
   int bx = (int)((rv + 255) / 256);
   if (bx > 64) bx = 64;
-  gather_rows_kernel<<<dim3(bx, B), 256, 0, st>>>(table, n, d_index, rv, out);
-  return cudaGetLastError();
+  return launch_kernel_plain(gather_rows_kernel, dim3(dim3(bx, B)), dim3(256), 0, st, table, n, d_index, rv, out);
 }
 
 }  // namespace ltb

@@ -7,6 +7,7 @@
 #include "cv_resize.cuh"
 #include "ltb_internal.h"
 #include "ops.h"
+#include "ptx_sm100.cuh"
 
 namespace ltb {
 
@@ -16,6 +17,7 @@ namespace ltb {
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const __half* __restrict__ x, int N, int IH, int IW, int ICtot, int ic_off, int C,
                                                         const __half* __restrict__ w, const float* __restrict__ bias, int stride, int relu,
                                                         __half* __restrict__ out, int OH, int OW, int OCtot, int oc_off) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   const int cg = C >> 3;
   const size_t total = (size_t)N * OH * OW * cg;
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
@@ -66,14 +68,14 @@ cudaError_t launch_dwconv3x3(const __half* x, int N, int IH, int IW, int ICtot, 
   const size_t total = (size_t)N * OH * OW * (C / 8);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  dwconv3x3_kernel<<<blocks, 256, 0, st>>>(x, N, IH, IW, ICtot, ic_off, C, w, bias, stride, relu, out, OH, OW, OCtot, oc_off);
-  return cudaGetLastError();
+  return launch_kernel_plain(dwconv3x3_kernel, dim3(blocks), dim3(256), 0, st, x, N, IH, IW, ICtot, ic_off, C, w, bias, stride, relu, out, OH, OW, OCtot, oc_off);
 }
 
 // ------------------------------------------------------------------------------------------------ bilinear x2, align_corners=True
 // F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True): src = dst * (in-1)/(out-1); fp32 lerp, fp16 out.
 __global__ void __launch_bounds__(256) upsample_bilinear2x_kernel(const __half* __restrict__ x, int N, int H, int W, int ICtot, int ic_off, int C,
                                                                   __half* __restrict__ out, int OCtot, int oc_off) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   const int cg = C >> 3, OH = 2 * H, OW = 2 * W;
   const float sy = OH > 1 ? (float)(H - 1) / (float)(OH - 1) : 0.f, sx = OW > 1 ? (float)(W - 1) / (float)(OW - 1) : 0.f;
   const size_t total = (size_t)N * OH * OW * cg;
@@ -110,8 +112,7 @@ cudaError_t launch_upsample_bilinear2x(const __half* x, int N, int H, int W, int
   const size_t total = (size_t)N * 4 * H * W * (C / 8);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  upsample_bilinear2x_kernel<<<blocks, 256, 0, st>>>(x, N, H, W, ICtot, ic_off, C, out, OCtot, oc_off);
-  return cudaGetLastError();
+  return launch_kernel_plain(upsample_bilinear2x_kernel, dim3(blocks), dim3(256), 0, st, x, N, H, W, ICtot, ic_off, C, out, OCtot, oc_off);
 }
 
 // ------------------------------------------------------------------------------------------------ LightReal input glue
@@ -119,6 +120,7 @@ cudaError_t launch_upsample_bilinear2x(const __half* x, int N, int H, int W, int
 // cv2.rectangle((5,5,150,145)) = columns [5,154], rows [5,149] zeroed, ch 6-15 = 0 (K padding of the first 1x1 conv).
 __global__ void __launch_bounds__(256) ul_prep_kernel(const uint8_t* __restrict__ faces, int nf, const int* __restrict__ d_index, int B,
                                                       __half* __restrict__ out) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   const int total = B * 160 * 160;
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= total) return;
@@ -140,8 +142,7 @@ __global__ void __launch_bounds__(256) ul_prep_kernel(const uint8_t* __restrict_
 }
 
 cudaError_t launch_ul_prep(const uint8_t* faces, int nf, const int* d_index, int B, __half* out, cudaStream_t st) {
-  ul_prep_kernel<<<(B * 25600 + 255) / 256, 256, 0, st>>>(faces, nf, d_index, B, out);
-  return cudaGetLastError();
+  return launch_kernel_plain(ul_prep_kernel, dim3((B * 25600 + 255) / 256), dim3(256), 0, st, faces, nf, d_index, B, out);
 }
 
 // ------------------------------------------------------------------------------------------------ LightReal.paste_back_frame
@@ -161,6 +162,7 @@ __device__ __forceinline__ int ul_src(const uint8_t* __restrict__ face, const fl
 }
 
 __global__ void __launch_bounds__(256) ul_paste_kernel(const UlPasteArgs a) {
+  pdl_launch_dependents();   // a PDL-launched successor (the conv kernels) may start its prologue now; it waits before reading
   const int job = blockIdx.z, y = blockIdx.y;
   const int x = blockIdx.x * 256 + threadIdx.x;
   if (x >= a.W) return;
@@ -205,8 +207,7 @@ cudaError_t launch_ul_paste(const uint8_t* frames, const uint8_t* faces, const i
                             int index, int explicit_idx, int slot0, int count, cudaStream_t st) {
   UlPasteArgs a{frames, faces, coords, pred, out, nf, H, W, index, explicit_idx, slot0};
   dim3 grid((W + 255) / 256, H, count);
-  ul_paste_kernel<<<grid, 256, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_kernel_plain(ul_paste_kernel, dim3(grid), dim3(256), 0, st, a);
 }
 
 }  // namespace ltb

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_traffic_from_ncu_reproduces_committed_json(tmp_path):
-    src = os.path.join(ROOT, "profiles", "r02f_launches_wav2lip.csv")
+    src = os.path.join(ROOT, "profiles", "r02q_launches_wav2lip.csv")
     out = str(tmp_path / "traffic.json")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "traffic_from_ncu.py"), src, out], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
