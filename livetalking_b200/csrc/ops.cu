@@ -381,10 +381,8 @@ __global__ void __launch_bounds__(256) softmax_wide_kernel(const __half* __restr
 
 cudaError_t launch_softmax(const __half* x, int rows, int cols, int ld, int valid, float scale, __half* out, cudaStream_t st) {
   if (cols % 8 != 0 || cols > 256 * 8 * kSMWideVec || ld % 8 != 0 || valid > cols || valid < 1) return cudaErrorInvalidValue;
-  if (cols > 32 * 8 * kSMMaxVec)
-    if (cudaError_t e_ = launch_kernel_plain(softmax_wide_kernel, dim3(rows), dim3(256), 0, st, x, cols, ld, valid, scale, out); e_ != cudaSuccess) return e_;
-  else
-    return launch_kernel_plain(softmax_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, x, rows, cols, ld, valid, scale, out);
+  if (cols > 32 * 8 * kSMMaxVec) return launch_kernel_plain(softmax_wide_kernel, dim3(rows), dim3(256), 0, st, x, cols, ld, valid, scale, out);
+  return launch_kernel_plain(softmax_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, x, rows, cols, ld, valid, scale, out);
 }
 
 // ------------------------------------------------------------------------------------------------ GEGLU / GELU / add
