@@ -4,7 +4,7 @@
         python tools/ncu_layers.py <case>
 
 cases: gather_s2 (L14 16->32 stride 2 @256, cp.async gather kernel), convt (L50 ConvT 160->64 @128), ystack (L53 80->32 @256),
-narrow64 (L52 64->64 + residual @256), wide128 (L49 128->128 + residual @128)."""
+narrow64 (L52 64->64 + residual @256), wide128 (L49 128->128 + residual @128), s2_tma (L21 64->128 stride 2 @64)."""
 import os
 import sys
 
@@ -17,6 +17,7 @@ CASES = {  # N, H, Cin, Cout, k, stride, pad, transposed, residual
     "ystack": (16, 256, 80, 32, 3, (1, 1), 1, False, False),
     "narrow64": (16, 256, 64, 64, 3, (1, 1), 1, False, True),
     "wide128": (16, 128, 128, 128, 3, (1, 1), 1, False, True),
+    "s2_tma": (16, 64, 64, 128, 3, (2, 2), 1, False, False),          # L21: stride-2 parity-plane TMA mode of the halo kernel
 }
 
 
