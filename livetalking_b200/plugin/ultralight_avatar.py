@@ -77,6 +77,9 @@ def load_avatar(avatar_id):
     p = f"./data/avatars/{avatar_id}"
     engine.set_device(int(os.environ.get("LTB_DEVICE", "0")))
     sd = torch.load(f"{p}/ultralight.pth", map_location="cpu")
+    if os.path.exists(f"{p}/avatar.ltbav"):            # packed form (`python -m livetalking_b200.avatar_pack <dir>`: the wav2lip layout —
+        from .. import avatar_pack                     # full_imgs / face_imgs / coords.pkl — holds 168x168 crops just as well)
+        return make_avatar(sd, *avatar_pack.load_packed(f"{p}/avatar.ltbav").wav2lip_lists())
     with open(f"{p}/coords.pkl", "rb") as f:
         coords = pickle.load(f)
     key = lambda x: int(os.path.splitext(os.path.basename(x))[0])  # noqa: E731

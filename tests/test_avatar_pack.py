@@ -124,3 +124,29 @@ def test_pack_rejects_bad_input(tmp_path):
         AP.pack_wav2lip_lists(frames[:2] + [np.zeros((10, 10, 3), np.uint8)], faces, coords, str(tmp_path / "x.ltbav"))
     with pytest.raises(AP.AvatarPackError):                               # count mismatch
         AP.pack_wav2lip_lists(frames, faces[:2], coords, str(tmp_path / "y.ltbav"))
+
+
+def test_ultralight_directory_packs_with_the_wav2lip_layout(tmp_path):
+    """An UltraLight avatar directory (avatars/ultralight_avatar.py:63-82) has the wav2lip layout with 168x168 crops and
+    (x1,y1,x2,y2) boxes: the same packer / loader round-trips it bit for bit (plugin.ultralight_avatar.load_avatar prefers the pack)."""
+    root = str(tmp_path / "avatars" / "ul")
+    rng = np.random.default_rng(3)
+    os.makedirs(os.path.join(root, "full_imgs"))
+    os.makedirs(os.path.join(root, "face_imgs"))
+    frames, faces, coords = [], [], []
+    for i in range(4):
+        fr, fa = rng.integers(0, 256, (60, 80, 3), dtype=np.uint8), rng.integers(0, 256, (168, 168, 3), dtype=np.uint8)
+        cv2.imwrite(os.path.join(root, "full_imgs", f"{i:08d}.png"), fr)
+        cv2.imwrite(os.path.join(root, "face_imgs", f"{i:08d}.png"), fa)
+        frames.append(fr)
+        faces.append(fa)
+        coords.append((5 + i, 4, 45 + i, 50))
+    with open(os.path.join(root, "coords.pkl"), "wb") as f:
+        pickle.dump(coords, f)
+    out = AP.pack_wav2lip(root)
+    fr2, fa2, co2 = AP.load_packed(out, verify=True).wav2lip_lists()
+    assert len(fr2) == len(fa2) == 4 and fa2[0].shape == (168, 168, 3)
+    for a, b in zip(frames + faces, list(fr2) + list(fa2)):
+        assert np.array_equal(a, b)
+    assert [tuple(c) for c in co2] == coords
+    assert fr2[0].flags.writeable                       # host frames are copy-on-write (the reference draws into them)
