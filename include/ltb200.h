@@ -263,6 +263,10 @@ int ltb_op_vae_post(ltb_ctx* c, const void* x, long long npix, int Ctot, void* o
  * replacing the CPU bgr24 -> yuv420p conversion behind VideoFrame.from_ndarray (avatars/base_avatar.py:449-453).
  * OpenCV COLOR_BGR2YUV_I420 arithmetic (BT.601 limited range); H even, W % 4 == 0. */
 int ltb_op_bgr_to_i420(ltb_ctx* c, const void* bgr_u8, int N, int H, int W, void* out_i420);
+/* The watermark of avatars/base_avatar.py:449 (cv2.putText(frame, "LiveTalking", (10,20), FONT_HERSHEY_SIMPLEX, 0.3, (128,128,128), 1))
+ * for frames that stay on the device: writes colour (b,g,r) into the n pixels pix_yx[k] = (y, x) (int32, device) of every frame
+ * [N,H,W,3]; the pixel set is what OpenCV itself rasterises for that text (livetalking_b200/watermark.py).  Bit-exact. */
+int ltb_op_stamp_pixels(ltb_ctx* c, void* frames_u8, int N, int H, int W, const void* pix_yx, int n, int b, int g, int r);
 /* VAE.preprocess_img, avatars/musetalk/models/vae.py:51-82 (uint8 BGR -> fp16 RGB [-1,1], 8-channel padded NHWC) */
 int ltb_op_vae_pre(ltb_ctx* c, const void* img_u8, int N, int H, int W, int half_mask, void* out);
 /* out[i] = table[mirror_index(n, *d_index + i)], i < B  (latent gather of MuseReal.inference_batch, musetalk_avatar.py:134-139) */

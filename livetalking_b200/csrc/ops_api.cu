@@ -484,6 +484,15 @@ int ltb_op_bgr_to_i420(ltb_ctx* c, const void* bgr_u8, int N, int H, int W, void
   c->launches += 1;
   return 0;
 }
+int ltb_op_stamp_pixels(ltb_ctx* c, void* frames_u8, int N, int H, int W, const void* pix_yx, int n, int b, int g, int r) {
+  if (!c || !frames_u8 || (!pix_yx && n > 0)) return LTB_FAIL("stamp_pixels: null argument");
+  if (N < 0 || n < 0 || H <= 0 || W <= 0) return LTB_FAIL("stamp_pixels: bad size");
+  LTB_CTX_ENTER(c);
+  cudaError_t e = launch_stamp_pixels(static_cast<uint8_t*>(frames_u8), N, H, W, static_cast<const int*>(pix_yx), n, b, g, r, c->st);
+  if (e != cudaSuccess) return LTB_FAIL(std::string("stamp_pixels: ") + cudaGetErrorString(e));
+  c->launches += 1;
+  return 0;
+}
 int ltb_op_vae_pre(ltb_ctx* c, const void* img_u8, int N, int H, int W, int half_mask, void* out) {
   if (!c || !img_u8 || !out) return LTB_FAIL("vae_pre: null argument");
   LTB_CTX_ENTER(c);

@@ -72,4 +72,27 @@ cudaError_t launch_bgr_to_i420(const uint8_t* bgr, int N, int H, int W, uint8_t*
   return cudaGetLastError();
 }
 
+// The reference's watermark (avatars/base_avatar.py:449): cv2.putText(frame, "LiveTalking", (10,20), FONT_HERSHEY_SIMPLEX, 0.3,
+// (128,128,128), 1).  With thickness 1 and the default LINE_8 OpenCV writes the colour into a frame-independent set of pixels (no
+// blending), so the set is rasterised ONCE on the host by OpenCV itself (livetalking_b200/watermark.py) and stamped here into frames
+// that stay resident for the encoder hand-off.  pix: int32 [n][2] = (y, x); pixels outside the frame are skipped (as cv2 clips).
+__global__ void __launch_bounds__(256) stamp_pixels_kernel(uint8_t* __restrict__ frames, int N, int H, int W, const int* __restrict__ pix, int n,
+                                                           int b, int g, int r) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n * N) return;
+  const int f = i / n, k = i - f * n;
+  const int y = pix[2 * k], x = pix[2 * k + 1];
+  if (y < 0 || y >= H || x < 0 || x >= W) return;
+  uint8_t* p = frames + (((size_t)f * H + y) * W + x) * 3;
+  p[0] = (uint8_t)b;
+  p[1] = (uint8_t)g;
+  p[2] = (uint8_t)r;
+}
+
+cudaError_t launch_stamp_pixels(uint8_t* frames, int N, int H, int W, const int* pix, int n, int b, int g, int r, cudaStream_t st) {
+  if (N <= 0 || n <= 0) return cudaSuccess;
+  stamp_pixels_kernel<<<(N * n + 255) / 256, 256, 0, st>>>(frames, N, H, W, pix, n, b, g, r);
+  return cudaGetLastError();
+}
+
 }  // namespace ltb

@@ -258,6 +258,13 @@ class Ctx:
         """uint8 BGR [N,H,W,3] -> planar I420 [N, H*3/2, W] (encoder hand-off; cv2.COLOR_BGR2YUV_I420 arithmetic)."""
         check(lib().ltb_op_bgr_to_i420(self._h, C.c_void_p(frames_u8.ptr), N, H, W, C.c_void_p(out_u8.ptr)))
 
+    def stamp_pixels(self, frames_u8: DevTensor, N: int, H: int, W: int, pix_yx: DevTensor, color_bgr=(128, 128, 128)):
+        """Write `color_bgr` into the pixels pix_yx (int32 (n, 2) = (y, x)) of every frame: the resident form of cv2.putText's
+        thickness-1 LINE_8 rasterisation (livetalking_b200/watermark.py)."""
+        n = int(pix_yx.shape[0])
+        check(lib().ltb_op_stamp_pixels(self._h, C.c_void_p(frames_u8.ptr), N, H, W, C.c_void_p(pix_yx.ptr), n, int(color_bgr[0]),
+                                        int(color_bgr[1]), int(color_bgr[2])))
+
     def vae_post(self, x: DevTensor, npix: int, out_u8: DevTensor):
         check(lib().ltb_op_vae_post(self._h, C.c_void_p(x.ptr), npix, x.pitch, C.c_void_p(out_u8.ptr)))
 
