@@ -24,7 +24,8 @@ _REF_MODULES = ("avatars", "avatars.base_avatar", "avatars.audio_features", "ava
                 "utils.image", "utils.logger")
 _PLUGIN_MODULES = ("livetalking_b200.plugin", "livetalking_b200.plugin.base_asr", "livetalking_b200.plugin.mel_asr",
                    "livetalking_b200.plugin.wav2lip_avatar", "livetalking_b200.plugin.whisper_asr",
-                   "livetalking_b200.plugin.musetalk_avatar")
+                   "livetalking_b200.plugin.musetalk_avatar", "livetalking_b200.plugin.hubert_asr",
+                   "livetalking_b200.plugin.ultralight_avatar")
 
 
 def available() -> bool:
@@ -71,6 +72,7 @@ def reference_runtime(workdir: str):
                                    plugin_w2l=importlib.import_module("livetalking_b200.plugin.wav2lip_avatar"),
                                    plugin_base_asr=importlib.import_module("livetalking_b200.plugin.base_asr"))
         ns.load_musetalk = lambda: importlib.import_module("livetalking_b200.plugin.musetalk_avatar")
+        ns.load_ultralight = lambda: importlib.import_module("livetalking_b200.plugin.ultralight_avatar")
         yield ns
     finally:
         sys.path.remove(REF)
