@@ -595,10 +595,11 @@ class MuseTalkBench:
             res["concurrent_sessions"] = self._sessions(args, av, hw, n_sessions, B_sess)
         if batch_sessions > 0:
             res["cross_session"] = self._cross_session(args, hw, batch_sessions, B)
-            try:                                       # eight sessions per launch (batch 64): how far the batch-size lever goes
-                res["cross_session_x8"] = self._cross_session(args, hw, 2 * batch_sessions, B)
-            except Exception as e:
-                res["cross_session_x8"] = {"error": repr(e)[:200]}
+            if self.world == 1:                        # single-GPU probe only (a one-sided failure must not strand other ranks in a collective)
+                try:                                   # eight sessions per launch (batch 64): how far the batch-size lever goes
+                    res["cross_session_x8"] = self._cross_session(args, hw, 2 * batch_sessions, B)
+                except Exception as e:
+                    res["cross_session_x8"] = {"error": repr(e)[:200]}
         return res
 
     def _cross_session(self, args, hw, G, Bs):
